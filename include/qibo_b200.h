@@ -1,0 +1,166 @@
+/*
+ * qibo_b200 -- C ABI of the B200-native state-vector engine (drop-in boundary).
+ *
+ * The reference (qiboteam/qibo 0.3.5) has no FFI: its hot path is Python/NumPy behind the
+ * `qibo.backends.Backend` plugin API.  Each entry point below names the reference method whose
+ * arithmetic it replaces (paths relative to /root/reference/src/qibo).  The Python host layer
+ * (`qibo_b200/backend.py`, a `Backend` subclass loaded through `MetaBackend.load`,
+ * backends/__init__.py:325-350) binds these through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are caller-owned (torch allocates them in the
+ *     Python host; `qb_malloc` exists for non-torch hosts);
+ *   - qubit ids are Qibo's: qubit 0 is the MOST significant bit of the flat state index
+ *     (tests/test_gates_gates.py:39-43), qubit q <-> bit position nqubits-1-q;
+ *   - matrices/diagonals are HOST pointers to interleaved complex128 (re,im doubles), row-major, the
+ *     row/column index having targets[0] as its most significant bit (gates/abstract.py:439-442);
+ *     they are evaluated in double on the host and cast to the state's dtype before the multiply, as
+ *     npmatrices.py:21-24 does;
+ *   - every call returns 0 on success or a negative QB_ERR_* code; the message is in qb_last_error()
+ *     (thread-local).  Nothing throws or aborts across the ABI;
+ *   - work is enqueued on the handle's CUDA stream; calls that return host data synchronise that stream.
+ *   - there is NO CPU fallback: without a CUDA device qb_create fails with QB_ERR_CUDA.
+ */
+#ifndef QIBO_B200_H
+#define QIBO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_VERSION 100 /* 0.1.0 */
+
+/* state dtypes (Backend.dtype, backends/abstract.py:133-179) */
+#define QB_C64 0  /* complex64  : float2  amplitudes */
+#define QB_C128 1 /* complex128 : double2 amplitudes */
+/* real dtypes of probability vectors (real(state).dtype, abstract.py:2751) */
+#define QB_F32 0
+#define QB_F64 1
+
+#define QB_OK 0
+#define QB_ERR_INVALID (-1)     /* bad argument            -> ValueError in the host layer          */
+#define QB_ERR_OOM (-2)         /* cudaErrorMemoryAllocation -> Backend.oom_error -> RuntimeError    */
+#define QB_ERR_CUDA (-3)        /* any other CUDA failure / no device                                */
+#define QB_ERR_UNSUPPORTED (-4) /* -> NotImplementedError                                            */
+
+#define QB_MAX_QUBITS 40
+#define QB_MAX_OP_TARGETS 6   /* dense blocks: FusedGate / Unitary up to 6 targets                   */
+#define QB_MAX_OP_CONTROLS 32
+
+typedef struct qb_context* qb_handle;
+
+/* ---- library / context -------------------------------------------------------------------------- */
+int qb_version(void);
+const char* qb_last_error(void);
+int qb_device_count(int* count);
+/* One context per (device, stream).  stream == NULL: the library creates its own non-blocking stream.
+ * Replaces NumpyBackend.__init__/set_device (backends/numpy.py:20-36, 76-87). */
+int qb_create(int device, void* cuda_stream, qb_handle* out);
+int qb_destroy(qb_handle h);
+int qb_set_stream(qb_handle h, void* cuda_stream);
+int qb_sync(qb_handle h);
+int qb_mem_info(qb_handle h, size_t* free_bytes, size_t* total_bytes);
+int qb_malloc(qb_handle h, size_t bytes, void** dptr);
+int qb_free(qb_handle h, void* dptr);
+/* kind: 0 host->device, 1 device->host, 2 device->device.  Replaces Backend.cast / to_numpy
+ * (backends/numpy.py:38-64, 98-107) for the state buffer. */
+int qb_memcpy(qb_handle h, void* dst, const void* src, size_t bytes, int kind);
+
+/* ---- K6: state construction (abstract.py:2243-2273 zero_state, :2199-2241 plus/minus_state) ------- */
+int qb_state_set_basis(qb_handle h, void* state, int nqubits, int dtype, uint64_t index);
+int qb_state_fill(qb_handle h, void* state, int nqubits, int dtype, double re, double im);
+/* complex64 <-> complex128 conversion of `count` amplitudes (Backend.cast with a dtype change) */
+int qb_state_cast(qb_handle h, void* dst, int dst_dtype, const void* src, int src_dtype, uint64_t count);
+/* sum |amp|^2 over the buffer (deterministic two-stage reduction) */
+int qb_state_norm2(qb_handle h, const void* state, int nqubits, int dtype, double* out_host);
+
+/* ---- K1: one gate, one sweep (abstract.py:2322-2361 apply_gate; :3176-3197 _apply_gate_controlled_by)
+ * `matrix` is the 2^nt x 2^nt target matrix; `controls` are the control_qubits of a `controlled_by`
+ * gate (may be empty).  Named controlled gates (CNOT, CZ, CU1, TOFFOLI...) may be passed with their
+ * full matrix over gate.qubits and no controls: the library detects control / diagonal / swap
+ * structure exactly and touches only the amplitudes that can change.  In place. */
+int qb_apply_matrix(qb_handle h, void* state, int nqubits, int dtype, const double* matrix, int ntargets,
+                    const int* targets, int ncontrols, const int* controls);
+/* same with only the diagonal given (2^nt complex entries) */
+int qb_apply_diagonal(qb_handle h, void* state, int nqubits, int dtype, const double* diag, int ntargets,
+                      const int* targets, int ncontrols, const int* controls);
+
+/* ---- K2: a whole gate queue, several gates per HBM sweep (abstract.py:3321-3322 the gate loop of
+ * _execute_circuit; FusedGate blocks from models/circuit.py:954-1003 arrive as dense ops) ----------- */
+typedef struct {
+  int32_t ntargets;
+  int32_t ncontrols;
+  int32_t targets[QB_MAX_OP_TARGETS];
+  int32_t controls[QB_MAX_OP_CONTROLS];
+  int32_t is_diagonal;  /* 1: `data` holds 2^nt diagonal entries instead of a matrix */
+  int32_t reserved;
+  const double* data;   /* host, interleaved complex128 */
+} qb_op;
+
+typedef struct {
+  int32_t nops;            /* gates submitted                                   */
+  int32_t nsweeps;         /* HBM sweeps (kernel launches) they were packed into */
+  int32_t ndense_passes;   /* shared-memory passes over tiles, total             */
+  int32_t ndiag_ops;       /* diagonal bundles applied                           */
+  double bytes_moved;      /* algorithmic bytes: sum over sweeps of 2*B*2^n      */
+  float elapsed_ms;        /* CUDA-event time of the whole program (flags & QB_PROGRAM_TIME) */
+  float reserved;
+} qb_program_stats;
+
+#define QB_PROGRAM_TIME 1      /* bracket with CUDA events, synchronise, fill elapsed_ms */
+#define QB_PROGRAM_NO_FUSE 2   /* one sweep per gate (gate-by-gate accounting)           */
+int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
+                     qb_program_stats* stats /* may be NULL */);
+/* host-only: run the sweep planner without touching a device (used by the CPU test-suite) */
+int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program_stats* stats,
+                    int32_t* sweep_of_op /* nops entries, may be NULL */);
+
+/* ---- K3: probabilities and marginals (abstract.py:2734-2758 + _order_probabilities :3371-3381) ----
+ * out[idx] with idx bits ordered as `qubits` (caller order, qubits[0] = MSB); out is a DEVICE buffer of
+ * 2^nmeasured reals of the state's real dtype (float for complex64, double for complex128). */
+int qb_probabilities(qb_handle h, const void* state, int nqubits, int dtype, const int* qubits, int nmeasured,
+                     void* probs_out);
+
+/* ---- K4: shot sampling (abstract.py:2774-2781 sample_shots -> np.random.choice: sequential float64
+ * cumsum, divide by last, searchsorted side="right") ---------------------------------------------------
+ * mode 0: numpy-exact sequential-order scan (bit-identical CDF to np.cumsum);
+ * mode 1: parallel three-phase scan (deterministic, rounding differs from np.cumsum at ~1e-16). */
+#define QB_SCAN_EXACT 0
+#define QB_SCAN_PARALLEL 1
+int qb_cdf(qb_handle h, const void* probs, int rdtype, uint64_t nbins, double* cdf_out, int mode);
+/* idx = #{k : cdf[k] <= u}; uniforms and out are DEVICE buffers */
+int qb_sample_cdf(qb_handle h, const double* cdf, uint64_t nbins, const double* uniforms, uint64_t nshots,
+                  int64_t* out);
+/* convenience with HOST uniforms/out (the plugin call): scan + search, scratch CDF owned by the context.
+ * total_out (may be NULL) receives sum(probs) before normalisation -- np.random.choice validates it. */
+int qb_sample(qb_handle h, const void* probs, int rdtype, uint64_t nbins, const double* uniforms_host,
+              uint64_t nshots, int64_t* out_host, int mode, double* total_out);
+
+/* ---- K5: collapse (abstract.py:2424-2440 collapse_state -> _collapse_statevector :3279-3304) ------
+ * `qubits` sorted ascending; `outcome` is the decimal of the measured bits, qubits[0] = MSB. */
+int qb_collapse(qb_handle h, void* state, int nqubits, int dtype, const int* qubits, int nmeasured,
+                uint64_t outcome, int normalize);
+
+/* ---- K7: global<->local qubit exchange for the distributed scheme (models/distcircuit.py; the
+ * executor Backend.execute_distributed_circuit is NotImplemented in-tree, abstract.py:2638-2647) -----
+ * Copies the half of the shard with local qubit `local_qubit` == `bit` into/out of a contiguous
+ * staging buffer of 2^(nqubits-1) amplitudes (pack: state -> staging; unpack: staging -> state). */
+int qb_pack_half(qb_handle h, const void* state, int nqubits, int dtype, int local_qubit, int bit, void* staging);
+int qb_unpack_half(qb_handle h, void* state, int nqubits, int dtype, int local_qubit, int bit, const void* staging);
+/* Fused exchange over NVLink peer memory: reads the partner's half directly through a peer-mapped
+ * pointer (`peer_state`) and writes it into this shard's half; both ranks must bracket it with a
+ * barrier.  Swaps this rank's (local_qubit == 1 - rank_bit) half with the partner's. */
+int qb_exchange_half_p2p(qb_handle h, void* state, const void* peer_staging, int nqubits, int dtype,
+                         int local_qubit, int bit);
+/* CUDA IPC plumbing so that ranks (one process per GPU) can map each other's buffers */
+int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes);
+int qb_ipc_open_handle(qb_handle h, const void* handle_64bytes, void** dptr_out);
+int qb_ipc_close_handle(qb_handle h, void* dptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIBO_B200_H */

@@ -1,0 +1,431 @@
+"""`B200Backend`: the drop-in `qibo.backends.Backend` subclass.
+
+Loaded through Qibo's own plugin convention -- ``qibo.set_backend("qibo_b200")`` ->
+``construct_backend`` -> ``qibo_b200.MetaBackend.load`` (backends/__init__.py:325-350).  It derives from
+the reference ``NumpyBackend`` (backends/numpy.py:20) so that the ~150-method array API, the gate-matrix
+table (npmatrices.py) and ``matrix_fused`` keep working on the host for Qibo's non-hot-path code, and
+overrides every method on the state-vector hot path with calls into libqibo_b200.so:
+
+    apply_gate / apply_gate_density_matrix          abstract.py:2322-2361, 3176-3197   -> qb_apply_matrix
+    execute_circuit / _execute_circuit (gate loop)   abstract.py:2442-2512, 3306-3344   -> qb_apply_program
+    execute_circuit_repeated                         abstract.py:2532-2636
+    execute_distributed_circuit                      abstract.py:2638-2647 (NotImplemented in-tree)
+    calculate_probabilities                          abstract.py:2734-2758              -> qb_probabilities
+    sample_shots / sample_frequencies                abstract.py:2760-2781              -> qb_sample
+    collapse_state                                   abstract.py:2424-2440, 3279-3304   -> qb_collapse
+    zero_state / plus_state / minus_state            abstract.py:2199-2273              -> qb_state_*
+
+States returned to Qibo are :class:`qibo_b200.array.DeviceArray` objects (GPU resident, torch tensor
+inside).  This module imports qibo; everything below it (engine, ops, C ABI) does not.
+"""
+
+from collections import Counter
+
+import numpy as np
+import torch
+
+from qibo import __version__ as qibo_version
+from qibo.backends.numpy import NumpyBackend
+from qibo.config import SHOT_BATCH_SIZE, log, raise_error
+from qibo.gates.abstract import Gate
+from qibo.result import CircuitResult, MeasurementOutcomes, QuantumState
+
+from qibo_b200 import _lib
+from qibo_b200.array import DeviceArray
+from qibo_b200.engine import Engine, frequencies_from_samples
+from qibo_b200.ops import Op
+
+_COMPLEX = {"complex128": np.dtype("complex128"), "complex64": np.dtype("complex64"),
+            "float64": np.dtype("complex128"), "float32": np.dtype("complex64")}
+
+
+class B200Backend(NumpyBackend):
+    def __init__(self, device=None, dtype="complex128"):
+        super().__init__()
+        self.name = "qibo_b200"
+        self.platform = "cuda-sm100a"
+        self.supports_multigpu = True
+        self.oom_error = (torch.cuda.OutOfMemoryError, _lib.QiboB200OutOfMemory, MemoryError)
+        self.tensor_types = (np.ndarray,)
+        self.versions = {"qibo": qibo_version, "numpy": np.__version__, "torch": torch.__version__,
+                         "qibo_b200": _lib.load().qb_version()}
+        self._engines = {}
+        index = 0
+        if device is not None:
+            index = self._parse_device(device)
+        elif torch.distributed.is_available() and torch.distributed.is_initialized():
+            import os
+
+            index = int(os.environ.get("LOCAL_RANK", 0))
+        self.device = f"/GPU:{index}"
+        self.engine_gpu = self._engine(index)  # raises without a CUDA device: there is no CPU path
+        if dtype != self.dtype:
+            self.set_dtype(dtype)
+
+    # ------------------------------------------------------------------ configuration -------------
+    @staticmethod
+    def _parse_device(device):
+        if isinstance(device, int):
+            return device
+        name = str(device)
+        if not name.upper().startswith("/GPU:"):
+            raise_error(ValueError, f"Device {device} is not available for qibo_b200 backend (GPU only).")
+        return int(name.split(":")[1])
+
+    def _engine(self, index):
+        if index not in self._engines:
+            if index >= torch.cuda.device_count():
+                raise_error(ValueError, f"Device /GPU:{index} is not available ({torch.cuda.device_count()} GPUs visible).")
+            self._engines[index] = Engine(index)
+        return self._engines[index]
+
+    def set_device(self, device):
+        index = self._parse_device(device)
+        self.engine_gpu = self._engine(index)
+        self.device = f"/GPU:{index}"
+
+    def set_threads(self, nthreads):
+        """A CPU notion (backends/numpy.py:89-96): accepted and ignored, the work runs on the GPU."""
+        if not isinstance(nthreads, int) or nthreads < 1:
+            raise_error(TypeError if not isinstance(nthreads, int) else ValueError, "nthreads must be a positive integer.")
+        self.nthreads = 1
+
+    @property
+    def _cdtype(self):
+        """complex dtype the state is held in (float32/float64 backends hold a complex state)."""
+        return _COMPLEX[str(np.dtype(self.dtype))] if not isinstance(self.dtype, str) else _COMPLEX[self.dtype]
+
+    # ------------------------------------------------------------------ casting / interop -----------
+    def is_device(self, x):
+        return isinstance(x, DeviceArray)
+
+    def cast(self, array, dtype=None, copy=False):
+        """DeviceArray -> host ndarray for Qibo's inherited NumPy code paths (interop).
+        Hot-path methods never route a device state through here."""
+        if isinstance(array, DeviceArray):
+            host = array.numpy()
+            return host if dtype is None else host.astype(dtype, copy=False)
+        if isinstance(array, (list, tuple)) and any(isinstance(x, DeviceArray) for x in array):
+            array = [np.asarray(x) for x in array]
+        return super().cast(array, dtype=dtype, copy=copy)
+
+    def to_numpy(self, array):
+        if isinstance(array, DeviceArray):
+            return array.numpy()
+        return super().to_numpy(array)
+
+    def _to_device(self, state, complex_dtype=None):
+        """Accept a DeviceArray / ndarray / list state -> complex DeviceArray on this backend's GPU."""
+        eng = self.engine_gpu
+        if isinstance(state, DeviceArray):
+            if state.dtype.kind == "c":
+                return state
+            return eng.upload(state.numpy().astype(np.complex128 if state.dtype == np.float64 else np.complex64))
+        host = np.asarray(state)
+        if host.dtype.kind != "c":
+            host = host.astype(np.complex64 if host.dtype == np.float32 else np.complex128)
+        elif host.dtype not in (np.complex64, np.complex128):
+            host = host.astype(np.complex128)
+        if complex_dtype is not None:
+            host = host.astype(complex_dtype, copy=False)
+        return eng.upload(host)
+
+    # ------------------------------------------------------------------ state constructors ----------
+    def _state_dtype(self, dtype):
+        if dtype is None:
+            return self._cdtype
+        d = np.dtype(dtype)
+        return d if d.kind == "c" else (np.dtype("complex64") if d == np.float32 else np.dtype("complex128"))
+
+    def zero_state(self, nqubits, density_matrix=False, dtype=None):
+        n = 2 * nqubits if density_matrix else nqubits
+        state = self.engine_gpu.basis_state(n, self._state_dtype(dtype), 0)
+        return state.reshape(2**nqubits, 2**nqubits) if density_matrix else state
+
+    def plus_state(self, nqubits, density_matrix=False, dtype=None):
+        n = 2 * nqubits if density_matrix else nqubits
+        value = 1.0 / 2**nqubits if density_matrix else 1.0 / np.sqrt(2**nqubits)
+        state = self.engine_gpu.filled_state(n, value, self._state_dtype(dtype))
+        return state.reshape(2**nqubits, 2**nqubits) if density_matrix else state
+
+    def minus_state(self, nqubits, density_matrix=False, dtype=None):
+        # |-> on every qubit = Z on every qubit of |+...+>
+        state = self.plus_state(nqubits, density_matrix=False, dtype=dtype)
+        z = np.array([1, -1], dtype=np.complex128)
+        ops = [Op(z, (q,), is_diagonal=True) for q in range(nqubits)]
+        self.engine_gpu.apply_program(state, nqubits, ops)
+        if density_matrix:
+            host = state.numpy()
+            return self.engine_gpu.upload(np.outer(host, host.conj()))
+        return state
+
+    # ------------------------------------------------------------------ gate -> Op ---------------------
+    def _gate_ops(self, gate, nqubits, density_matrix=False):
+        """Gate object -> list of Ops.  Named controlled gates arrive with their full matrix over
+        gate.qubits (the library recovers the control structure exactly); `controlled_by` gates arrive as
+        target matrix + controls (abstract.py:3176-3197).  Density matrices are 2n-qubit vectors: U on the
+        row qubits, conj(U) on the column qubits (abstract.py:2341-2348)."""
+        matrix = np.asarray(gate.matrix(self))
+        if gate.is_controlled_by:
+            targets, controls = tuple(gate.target_qubits), tuple(gate.control_qubits)
+        else:
+            targets, controls = tuple(gate.qubits), ()
+        matrix = matrix.astype(np.complex128, copy=False)
+        if not density_matrix:
+            return [Op(matrix, targets, controls, name=gate.__class__.__name__)]
+        return [
+            Op(np.conj(matrix), tuple(q + nqubits for q in targets), tuple(q + nqubits for q in controls)),
+            Op(matrix, targets, controls),
+        ]
+
+    # ------------------------------------------------------------------ G1/G2: apply_gate ---------------
+    def apply_gate(self, gate, state, nqubits):
+        """In place on DeviceArray states (returns the same object, as qibojit documents,
+        doc/source/getting-started/backends.rst:57-61); host arrays are uploaded first and left untouched."""
+        density_matrix = len(state.shape) == 2
+        dev = self._to_device(state)
+        flat = dev.reshape(-1) if density_matrix else dev
+        n = 2 * nqubits if density_matrix else nqubits
+        for op in self._gate_ops(gate, nqubits, density_matrix):
+            self.engine_gpu.apply_op(flat, n, op)
+        return dev
+
+    def apply_gate_density_matrix(self, gate, state, nqubits):
+        """Older-API alias named by the north star; the reference dispatches on ndim inside apply_gate."""
+        return self.apply_gate(gate, state, nqubits)
+
+    def apply_gate_half_density_matrix(self, gate, state, nqubits):
+        """abstract.py:2363-2383: only the left multiplication U rho."""
+        if gate.is_controlled_by:  # pragma: no cover
+            raise_error(NotImplementedError, "Gate density matrix half call is not implemented for ``controlled_by`` gates.")
+        dev = self._to_device(state)
+        flat = dev.reshape(-1)
+        op = self._gate_ops(gate, nqubits, density_matrix=True)[1]
+        self.engine_gpu.apply_op(flat, 2 * nqubits, op)
+        return dev
+
+    # ------------------------------------------------------------------ E1: circuits ----------------------
+    @staticmethod
+    def _is_plain(gate):
+        """True for gates whose apply() is Gate.apply -> backend.apply_gate (everything but M, callbacks, channels)."""
+        return type(gate).apply is Gate.apply
+
+    def _run_queue(self, queue, state, nqubits, density_matrix):
+        """The gate loop of _execute_circuit (abstract.py:3321-3322), with maximal runs of plain gates handed
+        to the sweep planner in one C call."""
+        flat_n = 2 * nqubits if density_matrix else nqubits
+        pending = []
+
+        def flush(st):
+            if pending:
+                flat = st.reshape(-1) if density_matrix else st
+                self.engine_gpu.apply_program(flat, flat_n, pending)
+                pending.clear()
+            return st
+
+        for gate in queue:
+            if self._is_plain(gate):
+                pending.extend(self._gate_ops(gate, nqubits, density_matrix))
+            else:
+                state = flush(state)
+                state = gate.apply(self, state, nqubits)
+                if not isinstance(state, DeviceArray):
+                    state = self._to_device(state)
+        return flush(state)
+
+    def _execute_circuit(self, circuit, initial_state=None, nshots=1000):
+        nqubits = circuit.nqubits
+        density_matrix = circuit.density_matrix
+        if initial_state is None:
+            state = self.zero_state(nqubits, density_matrix=density_matrix)
+        else:
+            # the caller's array is never clobbered (SURVEY 8b ownership): device inputs are cloned
+            state = self._to_device(initial_state)
+            if state is initial_state:
+                state = state.copy()
+        state = self._run_queue(circuit.queue, state, nqubits, density_matrix)
+
+        if circuit.measurements:
+            circuit._final_state = CircuitResult(state, circuit.measurements, backend=self, nshots=nshots)
+        else:
+            circuit._final_state = QuantumState(state, backend=self)
+        return circuit._final_state
+
+    def execute_circuit(self, circuit, initial_state=None, nshots=1000):
+        """abstract.py:2442-2512 with device-aware initial-state handling."""
+        nqubits = circuit.nqubits
+        density_matrix = circuit.density_matrix
+        self._validate_nqubits(nqubits, density_matrix=density_matrix)
+
+        if isinstance(initial_state, type(circuit)):
+            if not bool(initial_state.density_matrix == density_matrix):
+                raise_error(ValueError, f"Cannot set circuit with density_matrix {initial_state.density_matrix} as"
+                            + f"initial state for circuit with density_matrix {density_matrix}.")
+            if not bool(initial_state.accelerators == circuit.accelerators):  # pragma: no cover
+                raise_error(ValueError, "Cannot set circuit with different accelerators as initial state.")
+            return self.execute_circuit(initial_state + circuit, None, nshots)
+
+        if initial_state is not None:
+            valid_shape = 2 * (2**nqubits,) if density_matrix else (2**nqubits,)
+            shape = tuple(initial_state.shape) if hasattr(initial_state, "shape") else tuple(np.shape(initial_state))
+            if shape != valid_shape:
+                raise_error(ValueError, f"Given initial state has shape {shape}" + f"instead of the expected {valid_shape}.")
+
+        if circuit.repeated_execution:
+            if not circuit.measurements and not circuit.has_collapse:
+                raise_error(
+                    RuntimeError,
+                    "Attempting to perform noisy simulation with `density_matrix=False` "
+                    + "and no Measurement gate in the Circuit. If you wish to retrieve the "
+                    + "statistics of the outcomes please include measurements in the circuit, "
+                    + "otherwise set `density_matrix=True` to recover the final state.",
+                )
+            return self.execute_circuit_repeated(circuit, nshots, initial_state)
+
+        if circuit.accelerators:
+            return self.execute_distributed_circuit(circuit, initial_state, nshots)
+
+        try:
+            return self._execute_circuit(circuit, initial_state=initial_state, nshots=nshots)
+        except self.oom_error:
+            raise_error(
+                RuntimeError,
+                f"State does not fit in {self.device} memory."
+                "Please switch the execution device to a "
+                "different one using ``qibo.set_device``.",
+            )
+
+    def execute_circuit_repeated(self, circuit, nshots, initial_state=None):
+        """abstract.py:2532-2636: one full simulation per shot, state kept on the device throughout."""
+        density_matrix = circuit.density_matrix
+        if circuit.has_collapse and not circuit.measurements and not density_matrix:
+            raise_error(
+                RuntimeError,
+                "The circuit contains only collapsing measurements (`collapse=True`) but "
+                + "`density_matrix=False`. Please set `density_matrix=True` to retrieve "
+                + "the final state after execution.",
+            )
+        results, final_states, samples = [], [], []
+        nqubits = circuit.nqubits
+        if initial_state is None:
+            state_copy = self.zero_state(nqubits, density_matrix=density_matrix)
+        else:
+            state_copy = self._to_device(initial_state)
+
+        for _ in range(nshots):
+            state = state_copy.copy()
+            for gate in circuit.queue:
+                if gate.symbolic_parameters:
+                    gate.substitute_symbols()
+            state = self._run_queue(circuit.queue, state, nqubits, density_matrix)
+            if density_matrix:
+                final_states.append(state)
+            if circuit.measurements:
+                result = CircuitResult(state, circuit.measurements, backend=self, nshots=1)
+                sample = result.samples()[0]
+                results.append(sample)
+                if not density_matrix:
+                    samples.append("".join([str(int(s)) for s in sample]))
+                for gate in circuit.measurements:
+                    gate.result.reset()
+
+        if density_matrix:  # this implies also it has_collapse
+            acc = final_states[0].tensor.clone()
+            for st in final_states[1:]:
+                acc += st.tensor
+            final_state = DeviceArray(acc / len(final_states))
+            if circuit.measurements:
+                final_result = CircuitResult(final_state, circuit.measurements, backend=self,
+                                             samples=self.aggregate_shots(results), nshots=nshots)
+            else:
+                final_result = QuantumState(final_state, backend=self)
+            circuit._final_state = final_result
+            return final_result
+
+        final_result = MeasurementOutcomes(circuit.measurements, backend=self, samples=self.aggregate_shots(results), nshots=nshots)
+        final_result._repeated_execution_frequencies = self.calculate_frequencies(samples)
+        circuit._final_state = final_result
+        return final_result
+
+    def execute_distributed_circuit(self, circuit, initial_state=None, nshots=None):
+        """D2 (NotImplemented in the reference, abstract.py:2638-2647).  One process per GPU: when
+        torch.distributed is initialised with W ranks the state is sharded over log2(W) global qubits
+        (qibo_b200.distributed); in a single process the logical devices of ``accelerators`` collapse onto
+        this GPU and the circuit runs as one shard -- same results, same return types."""
+        from qibo_b200 import distributed
+
+        if distributed.world_size() > 1:
+            return distributed.execute_circuit(self, circuit, initial_state, nshots)
+        try:
+            return self._execute_circuit(circuit, initial_state=initial_state, nshots=1000 if nshots is None else nshots)
+        except self.oom_error:
+            raise_error(RuntimeError, f"State does not fit in {self.device} memory.")
+
+    # ------------------------------------------------------------------ P1: probabilities ------------------
+    def calculate_probabilities(self, state, qubits, nqubits, density_matrix=False):
+        qubits = [int(q) for q in qubits]
+        if density_matrix:
+            # diag(rho) marginal: host path of the reference on the (small) matrix -- X1 is outside the BASELINE configs
+            return super().calculate_probabilities(self.cast(state, dtype=state.dtype), qubits, nqubits, density_matrix=True)
+        dev = self._to_device(state)
+        return self.engine_gpu.probabilities(dev, qubits, nqubits)
+
+    # ------------------------------------------------------------------ S1/S2: sampling ----------------------
+    def _probs_to_device(self, probabilities):
+        if isinstance(probabilities, DeviceArray):
+            if probabilities.dtype.kind == "f":
+                return probabilities
+            probabilities = probabilities.numpy()
+        host = np.asarray(probabilities)
+        if host.dtype not in (np.float32, np.float64):
+            host = host.astype(np.float64)
+        return self.engine_gpu.upload(np.ascontiguousarray(host))
+
+    def sample_shots(self, probabilities, nshots):
+        """np.random.choice semantics (abstract.py:2774-2781): uniforms from the global legacy RNG
+        (Backend.set_seed = np.random.seed), device scan + inverse-CDF search; int64 host array out."""
+        probs = self._probs_to_device(probabilities)
+        nshots = int(nshots)
+        uniforms = np.random.random_sample(nshots)
+        samples, total = self.engine_gpu.sample(probs, uniforms, return_total=True)
+        atol = max(np.sqrt(np.finfo(np.float64).eps), np.sqrt(np.finfo(probs.dtype).eps))
+        if abs(total - 1.0) > atol:  # numpy/random/mtrand.pyx: "probabilities do not sum to 1"
+            raise_error(ValueError, "probabilities do not sum to 1")
+        return samples
+
+    def sample_frequencies(self, probabilities, nshots):
+        """abstract.py:2760-2772: renormalise, draw in 2^18 batches from one RNG stream, histogram.
+        The histogram is built from the (host) sample vector -- no 2^m-entry Python loop."""
+        probs = self._probs_to_device(probabilities)
+        nshots = int(nshots)
+        freqs = Counter()
+        batches = (nshots // SHOT_BATCH_SIZE) * [SHOT_BATCH_SIZE] + [nshots % SHOT_BATCH_SIZE]
+        for b in batches:
+            if b == 0:
+                continue
+            uniforms = np.random.random_sample(b)
+            freqs.update(frequencies_from_samples(self.engine_gpu.sample(probs, uniforms)))
+        return Counter({int(k): int(v) for k, v in sorted(freqs.items())})
+
+    def calculate_frequencies(self, samples):
+        if isinstance(samples, DeviceArray):
+            samples = samples.numpy()
+        return super().calculate_frequencies(samples)
+
+    # ------------------------------------------------------------------ C1: collapse ----------------------------
+    def collapse_state(self, state, qubits, shot, nqubits, normalize=True, density_matrix=False):
+        if density_matrix:
+            out = super().collapse_state(self.cast(state, dtype=state.dtype), list(qubits), shot, nqubits, normalize, True)
+            return self.engine_gpu.upload(out)
+        dev = self._to_device(state)
+        outcome = int(np.asarray(shot).ravel()[0])
+        self.engine_gpu.collapse(dev, nqubits, [int(q) for q in qubits], outcome, normalize)
+        return dev
+
+    # ------------------------------------------------------------------ testing helpers ----------------------------
+    def assert_allclose(self, value, target, rtol=1e-7, atol=0.0):
+        if isinstance(value, (CircuitResult, QuantumState)):
+            value = value.state()
+        if isinstance(target, (CircuitResult, QuantumState)):
+            target = target.state()
+        np.testing.assert_allclose(self.to_numpy(value), self.to_numpy(target), rtol=rtol, atol=atol)

@@ -1,0 +1,762 @@
+// qibo_b200: C-ABI entry points (include/qibo_b200.h).  Host-side dispatch only; kernels live in *.cuh.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/qibo_b200.h"
+#include "qb_canon.hpp"
+#include "qb_common.cuh"
+#include "qb_gate_kernels.cuh"
+#include "qb_measure_kernels.cuh"
+#include "qb_planner.hpp"
+#include "qb_sweep.cuh"
+
+using namespace qb;
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct qb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::mutex mu;  // one backend object may be entered from several joblib threads (parallel.py:53)
+  // scratch (grown on demand, stream-ordered reuse)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  double* cdf = nullptr;
+  size_t cdf_bytes = 0;
+  // device + pinned-host program buffers for the sweep kernel
+  void* prog_dev = nullptr;
+  void* prog_host = nullptr;
+  size_t prog_bytes = 0;
+  cudaEvent_t prog_done = nullptr;  // last kernel that read prog_dev
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();  // clear sticky-less errors
+  return e == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA;
+}
+#define QB_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+  } while (0)
+#define QB_CHECK_LAUNCH(what)                             \
+  do {                                                    \
+    cudaError_t _e = cudaGetLastError();                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, what);    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static int ensure_scratch(qb_context* h, size_t bytes) {
+  if (h->scratch_bytes >= bytes) return QB_OK;
+  if (h->scratch) {
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->scratch);
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+  }
+  size_t want = bytes < (size_t(1) << 20) ? (size_t(1) << 20) : bytes;
+  QB_CUDA(cudaMalloc(&h->scratch, want));
+  h->scratch_bytes = want;
+  return QB_OK;
+}
+
+static bool valid_state_args(const void* state, int nqubits, int dtype) {
+  return state != nullptr && nqubits >= 1 && nqubits <= QB_MAX_QUBITS && (dtype == QB_C64 || dtype == QB_C128);
+}
+
+int qb_version(void) { return QB_VERSION; }
+const char* qb_last_error(void) { return g_err.c_str(); }
+
+int qb_device_count(int* count) {
+  if (!count) return fail(QB_ERR_INVALID, "null count");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return cuda_fail(e, "cudaGetDeviceCount");
+  }
+  *count = c;
+  return QB_OK;
+}
+
+int qb_create(int device, void* cuda_stream, qb_handle* out) {
+  if (!out) return fail(QB_ERR_INVALID, "null handle pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(QB_ERR_CUDA, "qibo_b200 needs a CUDA device (no CPU fallback): " +
+                                 std::string(e == cudaSuccess ? "no device found" : cudaGetErrorString(e)));
+  if (device < 0 || device >= count) return fail(QB_ERR_INVALID, "device index out of range");
+  DeviceGuard guard(device);
+  qb_context* h = new qb_context();
+  h->device = device;
+  cudaDeviceProp prop;
+  QB_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  if (cuda_stream) {
+    h->stream = (cudaStream_t)cuda_stream;
+  } else {
+    QB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  QB_CUDA(cudaEventCreateWithFlags(&h->prog_done, cudaEventDisableTiming));
+  QB_CUDA(cudaEventCreate(&h->ev0));
+  QB_CUDA(cudaEventCreate(&h->ev1));
+  int rc = sweep_configure(prop);
+  if (rc != QB_OK) {
+    delete h;
+    return fail(rc, "sweep kernel configuration failed (needs sm_100a, 227 KB shared memory per block)");
+  }
+  *out = h;
+  return QB_OK;
+}
+
+int qb_destroy(qb_handle h) {
+  if (!h) return QB_OK;
+  DeviceGuard guard(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->cdf) cudaFree(h->cdf);
+  if (h->prog_dev) cudaFree(h->prog_dev);
+  if (h->prog_host) cudaFreeHost(h->prog_host);
+  if (h->prog_done) cudaEventDestroy(h->prog_done);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QB_OK;
+}
+
+int qb_set_stream(qb_handle h, void* cuda_stream) {
+  if (!h) return fail(QB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->own_stream = false;
+  if (cuda_stream) {
+    h->stream = (cudaStream_t)cuda_stream;
+  } else {
+    QB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  return QB_OK;
+}
+
+int qb_sync(qb_handle h) {
+  if (!h) return fail(QB_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB_OK;
+}
+
+int qb_mem_info(qb_handle h, size_t* free_bytes, size_t* total_bytes) {
+  if (!h || !free_bytes || !total_bytes) return fail(QB_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  QB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  return QB_OK;
+}
+
+int qb_malloc(qb_handle h, size_t bytes, void** dptr) {
+  if (!h || !dptr) return fail(QB_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  QB_CUDA(cudaMalloc(dptr, bytes));
+  return QB_OK;
+}
+
+int qb_free(qb_handle h, void* dptr) {
+  if (!h) return fail(QB_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  QB_CUDA(cudaFree(dptr));
+  return QB_OK;
+}
+
+int qb_memcpy(qb_handle h, void* dst, const void* src, size_t bytes, int kind) {
+  if (!h || (!dst && bytes) || (!src && bytes)) return fail(QB_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  QB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, h->stream));
+  if (kind != 2) QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6
+// ---------------------------------------------------------------------------------------------------
+static int grid_for(uint64_t count, int threads, int sm_count, int waves = 16) {
+  uint64_t blocks = (count + threads - 1) / threads;
+  uint64_t cap = uint64_t(sm_count) * waves;
+  return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+int qb_state_set_basis(qb_handle h, void* state, int nqubits, int dtype, uint64_t index) {
+  if (!h || !valid_state_args(state, nqubits, dtype)) return fail(QB_ERR_INVALID, "bad state arguments");
+  uint64_t count = uint64_t(1) << nqubits;
+  if (index >= count) return fail(QB_ERR_INVALID, "basis index out of range");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int grid = grid_for(count, 256, h->sm_count);
+  if (dtype == QB_C128)
+    k6_fill<double2><<<grid, 256, 0, h->stream>>>((double2*)state, count, cmake<double2>(0, 0), index, 1);
+  else
+    k6_fill<float2><<<grid, 256, 0, h->stream>>>((float2*)state, count, cmake<float2>(0, 0), index, 1);
+  QB_CHECK_LAUNCH("k6_fill");
+  return QB_OK;
+}
+
+int qb_state_fill(qb_handle h, void* state, int nqubits, int dtype, double re, double im) {
+  if (!h || !valid_state_args(state, nqubits, dtype)) return fail(QB_ERR_INVALID, "bad state arguments");
+  uint64_t count = uint64_t(1) << nqubits;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int grid = grid_for(count, 256, h->sm_count);
+  if (dtype == QB_C128)
+    k6_fill<double2><<<grid, 256, 0, h->stream>>>((double2*)state, count, cmake<double2>(re, im), 0, 0);
+  else
+    k6_fill<float2><<<grid, 256, 0, h->stream>>>((float2*)state, count, cmake<float2>((float)re, (float)im), 0, 0);
+  QB_CHECK_LAUNCH("k6_fill");
+  return QB_OK;
+}
+
+int qb_state_cast(qb_handle h, void* dst, int dst_dtype, const void* src, int src_dtype, uint64_t count) {
+  if (!h || !dst || !src) return fail(QB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int grid = grid_for(count, 256, h->sm_count);
+  if (dst_dtype == QB_C128 && src_dtype == QB_C64)
+    k6_cast<double2, float2><<<grid, 256, 0, h->stream>>>((double2*)dst, (const float2*)src, count);
+  else if (dst_dtype == QB_C64 && src_dtype == QB_C128)
+    k6_cast<float2, double2><<<grid, 256, 0, h->stream>>>((float2*)dst, (const double2*)src, count);
+  else if (dst_dtype == src_dtype && (dst_dtype == QB_C64 || dst_dtype == QB_C128)) {
+    QB_CUDA(cudaMemcpyAsync(dst, src, count * (dst_dtype == QB_C128 ? 16 : 8), cudaMemcpyDeviceToDevice, h->stream));
+    return QB_OK;
+  } else
+    return fail(QB_ERR_INVALID, "bad dtype");
+  QB_CHECK_LAUNCH("k6_cast");
+  return QB_OK;
+}
+
+// sum |amp|^2 over the slice (idx & mask) == val into scratch[0] (device), deterministic
+static int slice_norm2_device(qb_context* h, const void* state, int nqubits, int dtype, const std::vector<int>& pos_sorted,
+                              uint64_t val, double** result_dev) {
+  int m = (int)pos_sorted.size();
+  uint64_t ngroups = uint64_t(1) << (nqubits - m);
+  int grid = grid_for(ngroups, RED_THREADS, h->sm_count, 8);
+  int rc = ensure_scratch(h, (size_t)(grid + 8) * sizeof(double));
+  if (rc != QB_OK) return rc;
+  double* partial = (double*)h->scratch + 8;
+  double* out = (double*)h->scratch;
+  InsertList ins;
+  ins.n = m;
+  for (int i = 0; i < m; ++i) ins.pos[i] = (uint8_t)pos_sorted[i];
+  if (dtype == QB_C128)
+    k5_slice_norm2<double2><<<grid, RED_THREADS, 0, h->stream>>>((const double2*)state, ngroups, ins, val, partial);
+  else
+    k5_slice_norm2<float2><<<grid, RED_THREADS, 0, h->stream>>>((const float2*)state, ngroups, ins, val, partial);
+  QB_CHECK_LAUNCH("k5_slice_norm2");
+  k5_sum_partials<<<1, 32, 0, h->stream>>>(partial, grid, out);
+  QB_CHECK_LAUNCH("k5_sum_partials");
+  *result_dev = out;
+  return QB_OK;
+}
+
+int qb_state_norm2(qb_handle h, const void* state, int nqubits, int dtype, double* out_host) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !out_host) return fail(QB_ERR_INVALID, "bad state arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  double* dev = nullptr;
+  int rc = slice_norm2_device(h, state, nqubits, dtype, {}, 0, &dev);
+  if (rc != QB_OK) return rc;
+  QB_CUDA(cudaMemcpyAsync(out_host, dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------------
+template <typename C> static C to_c(cd v) {
+  return cmake<C>((typename real_of<C>::type)v.real(), (typename real_of<C>::type)v.imag());
+}
+
+static void fill_insert_and_offsets(const CanonOp& op, InsertList& ins, uint64_t* off) {
+  std::vector<int> all(op.tpos);
+  all.insert(all.end(), op.cpos.begin(), op.cpos.end());
+  std::sort(all.begin(), all.end());
+  ins.n = (int)all.size();
+  for (int i = 0; i < ins.n; ++i) ins.pos[i] = (uint8_t)all[i];
+  int k = (int)op.tpos.size();
+  for (int j = 0; j < (1 << k); ++j) {
+    uint64_t o = 0;
+    for (int i = 0; i < k; ++i)
+      if ((j >> (k - 1 - i)) & 1) o |= uint64_t(1) << op.tpos[i];
+    off[j] = o;
+  }
+}
+
+template <typename C, int K, int UNROLL>
+static int launch_dense(qb_context* h, void* state, int nqubits, const CanonOp& op) {
+  static DenseParams<C, K> p;  // large (up to 16 KB): keep off the stack; guarded by h->mu per context
+  static std::mutex pm;
+  std::lock_guard<std::mutex> lk(pm);
+  fill_insert_and_offsets(op, p.ins, p.off);
+  p.cmask = op.cmask();
+  p.ngroups = uint64_t(1) << (nqubits - p.ins.n);
+  for (int i = 0; i < (1 << (2 * K)); ++i) p.m[i] = to_c<C>(op.data[i]);
+  uint64_t per_block = uint64_t(K1_THREADS) * UNROLL;
+  uint64_t grid = (p.ngroups + per_block - 1) / per_block;
+  k1_dense<C, K, UNROLL><<<(unsigned)grid, K1_THREADS, 0, h->stream>>>((C*)state, p);
+  QB_CHECK_LAUNCH("k1_dense");
+  return QB_OK;
+}
+
+template <typename C, int K, int UNROLL>
+static int launch_diag(qb_context* h, void* state, int nqubits, const CanonOp& op) {
+  DiagParams<C, K> p;
+  fill_insert_and_offsets(op, p.ins, p.off);
+  p.cmask = op.cmask();
+  p.ngroups = uint64_t(1) << (nqubits - p.ins.n);
+  for (int i = 0; i < (1 << K); ++i) p.d[i] = to_c<C>(op.data[i]);
+  uint64_t per_block = uint64_t(K1_THREADS) * UNROLL;
+  uint64_t grid = (p.ngroups + per_block - 1) / per_block;
+  k1_diag<C, K, UNROLL><<<(unsigned)grid, K1_THREADS, 0, h->stream>>>((C*)state, p);
+  QB_CHECK_LAUNCH("k1_diag");
+  return QB_OK;
+}
+
+template <typename C> static int launch_slice(qb_context* h, void* state, int nqubits, const CanonOp& op) {
+  SliceParams<C> p;
+  uint64_t off[4] = {0, 0, 0, 0};
+  fill_insert_and_offsets(op, p.ins, off);
+  p.cmask = op.cmask();
+  p.ngroups = uint64_t(1) << (nqubits - p.ins.n);
+  constexpr int UNROLL = 4;
+  uint64_t per_block = uint64_t(K1_THREADS) * UNROLL;
+  uint64_t grid = (p.ngroups + per_block - 1) / per_block;
+  if (op.kind == CK_PHASE) {
+    p.phase = to_c<C>(op.data[0]);
+    p.off01 = p.off10 = 0;
+    k1_phase<C, UNROLL><<<(unsigned)grid, K1_THREADS, 0, h->stream>>>((C*)state, p);
+  } else {
+    p.phase = cmake<C>(1, 0);
+    p.off01 = off[1];
+    p.off10 = off[2];
+    k1_swap<C, UNROLL><<<(unsigned)grid, K1_THREADS, 0, h->stream>>>((C*)state, p);
+  }
+  QB_CHECK_LAUNCH("k1_slice");
+  return QB_OK;
+}
+
+template <typename C> static int apply_canon_k1(qb_context* h, void* state, int nqubits, const CanonOp& op) {
+  int k = (int)op.tpos.size();
+  switch (op.kind) {
+    case CK_NOOP:
+      return QB_OK;
+    case CK_PHASE:
+    case CK_SWAP:
+      return launch_slice<C>(h, state, nqubits, op);
+    case CK_DENSE:
+      switch (k) {
+        case 1: return launch_dense<C, 1, 4>(h, state, nqubits, op);
+        case 2: return launch_dense<C, 2, 2>(h, state, nqubits, op);
+        case 3: return launch_dense<C, 3, 1>(h, state, nqubits, op);
+        case 4: return launch_dense<C, 4, 1>(h, state, nqubits, op);
+        case 5: return launch_dense<C, 5, 1>(h, state, nqubits, op);
+        default: return fail(QB_ERR_UNSUPPORTED, "dense gates on more than 5 target qubits are not supported");
+      }
+    case CK_DIAG:
+      switch (k) {
+        case 1: return launch_diag<C, 1, 4>(h, state, nqubits, op);
+        case 2: return launch_diag<C, 2, 2>(h, state, nqubits, op);
+        case 3: return launch_diag<C, 3, 1>(h, state, nqubits, op);
+        case 4: return launch_diag<C, 4, 1>(h, state, nqubits, op);
+        case 5: return launch_diag<C, 5, 1>(h, state, nqubits, op);
+        case 6: return launch_diag<C, 6, 1>(h, state, nqubits, op);
+        default: return fail(QB_ERR_UNSUPPORTED, "diagonal gates on more than 6 target qubits are not supported");
+      }
+  }
+  return fail(QB_ERR_INVALID, "bad canonical op");
+}
+
+static int apply_gate_common(qb_handle h, void* state, int nqubits, int dtype, const double* data, bool is_diag,
+                             int ntargets, const int* targets, int ncontrols, const int* controls) {
+  if (!h || !valid_state_args(state, nqubits, dtype)) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (!data || (ntargets > 0 && !targets) || (ncontrols > 0 && !controls)) return fail(QB_ERR_INVALID, "null gate argument");
+  if (ntargets > QB_MAX_OP_TARGETS) return fail(QB_ERR_UNSUPPORTED, "too many target qubits");
+  CanonOp op;
+  std::string err;
+  if (!canonicalize(nqubits, data, is_diag, ntargets, targets, ncontrols, controls, op, err)) return fail(QB_ERR_INVALID, err);
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  return dtype == QB_C128 ? apply_canon_k1<double2>(h, state, nqubits, op) : apply_canon_k1<float2>(h, state, nqubits, op);
+}
+
+int qb_apply_matrix(qb_handle h, void* state, int nqubits, int dtype, const double* matrix, int ntargets, const int* targets,
+                    int ncontrols, const int* controls) {
+  return apply_gate_common(h, state, nqubits, dtype, matrix, false, ntargets, targets, ncontrols, controls);
+}
+
+int qb_apply_diagonal(qb_handle h, void* state, int nqubits, int dtype, const double* diag, int ntargets, const int* targets,
+                      int ncontrols, const int* controls) {
+  return apply_gate_common(h, state, nqubits, dtype, diag, true, ntargets, targets, ncontrols, controls);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: whole programs
+// ---------------------------------------------------------------------------------------------------
+static int canonicalize_program(int nqubits, const qb_op* ops, int nops, std::vector<CanonOp>& out) {
+  out.clear();
+  out.reserve(nops);
+  std::string err;
+  for (int i = 0; i < nops; ++i) {
+    const qb_op& o = ops[i];
+    if (o.ntargets < 0 || o.ntargets > QB_MAX_OP_TARGETS || o.ncontrols < 0 || o.ncontrols > QB_MAX_OP_CONTROLS || !o.data)
+      return fail(QB_ERR_INVALID, "bad op " + std::to_string(i));
+    CanonOp c;
+    if (!canonicalize(nqubits, o.data, o.is_diagonal != 0, o.ntargets, o.targets, o.ncontrols, o.controls, c, err))
+      return fail(QB_ERR_INVALID, "op " + std::to_string(i) + ": " + err);
+    out.push_back(std::move(c));
+  }
+  return QB_OK;
+}
+
+int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program_stats* stats,
+                    int32_t* sweep_of_op) {
+  if (nqubits < 1 || nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128) || nops < 0 || (nops && !ops))
+    return fail(QB_ERR_INVALID, "bad program arguments");
+  std::vector<CanonOp> canon;
+  int rc = canonicalize_program(nqubits, ops, nops, canon);
+  if (rc != QB_OK) return rc;
+  Plan plan;
+  std::string err;
+  if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, err)) return fail(QB_ERR_UNSUPPORTED, err);
+  if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
+  if (sweep_of_op)
+    for (int i = 0; i < nops; ++i) sweep_of_op[i] = plan.sweep_of_op[i];
+  return QB_OK;
+}
+
+int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
+                     qb_program_stats* stats) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || nops < 0 || (nops && !ops))
+    return fail(QB_ERR_INVALID, "bad program arguments");
+  std::vector<CanonOp> canon;
+  int rc = canonicalize_program(nqubits, ops, nops, canon);
+  if (rc != QB_OK) return rc;
+  Plan plan;
+  std::string err;
+  if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, err)) return fail(QB_ERR_UNSUPPORTED, err);
+  if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
+
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  // upload the compiled sweeps (pinned staging -> device program buffer)
+  size_t need = plan.blob.size();
+  if (need > h->prog_bytes) {
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->prog_dev) cudaFree(h->prog_dev);
+    if (h->prog_host) cudaFreeHost(h->prog_host);
+    h->prog_dev = h->prog_host = nullptr;
+    h->prog_bytes = 0;
+    size_t want = need < (size_t(1) << 20) ? (size_t(1) << 20) : need * 2;
+    QB_CUDA(cudaMalloc(&h->prog_dev, want));
+    QB_CUDA(cudaMallocHost(&h->prog_host, want));
+    h->prog_bytes = want;
+  } else {
+    QB_CUDA(cudaEventSynchronize(h->prog_done));  // previous program may still be reading the buffers
+  }
+  if (need) {
+    memcpy(h->prog_host, plan.blob.data(), need);
+    QB_CUDA(cudaMemcpyAsync(h->prog_dev, h->prog_host, need, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (flags & QB_PROGRAM_TIME) QB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  for (size_t s = 0; s < plan.sweeps.size(); ++s) {
+    rc = launch_sweep(h->stream, h->sm_count, state, nqubits, dtype, plan.sweeps[s], (const char*)h->prog_dev);
+    if (rc != QB_OK) return fail(rc, "sweep launch failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
+  }
+  QB_CUDA(cudaEventRecord(h->prog_done, h->stream));
+  if (flags & QB_PROGRAM_TIME) {
+    QB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    QB_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (stats) stats->elapsed_ms = ms;
+  }
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------------------------------
+int qb_probabilities(qb_handle h, const void* state, int nqubits, int dtype, const int* qubits, int nmeasured,
+                     void* probs_out) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !probs_out) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (nmeasured < 0 || nmeasured > nqubits || (nmeasured && !qubits)) return fail(QB_ERR_INVALID, "bad measured qubits");
+  ProbParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = nqubits;
+  p.nlow = nqubits < 5 ? nqubits : 5;
+  for (int i = 0; i < 48; ++i) p.outbit[i] = -1;
+  uint64_t mmask = 0;
+  for (int i = 0; i < nmeasured; ++i) {
+    int q = qubits[i];
+    if (q < 0 || q >= nqubits) return fail(QB_ERR_INVALID, "measured qubit out of range");
+    int pos = nqubits - 1 - q;
+    if ((mmask >> pos) & 1) return fail(QB_ERR_INVALID, "repeated measured qubit");
+    mmask |= uint64_t(1) << pos;
+    p.outbit[pos] = (int8_t)(nmeasured - 1 - i);
+  }
+  uint64_t lowmask = (uint64_t(1) << p.nlow) - 1;
+  uint64_t all = nqubits == 64 ? ~uint64_t(0) : ((uint64_t(1) << nqubits) - 1);
+  p.low_unmeasured = (uint32_t)(~mmask & lowmask);
+  p.mhigh_mask = mmask & ~lowmask;
+  p.uhigh_mask = ~mmask & all & ~lowmask;
+  p.n_mhigh = __builtin_popcountll(p.mhigh_mask);
+  p.n_uhigh = __builtin_popcountll(p.uhigh_mask);
+  p.nbins = uint64_t(1) << nmeasured;
+  // want >= ~2^14 warps; never split below 4 iterations per warp
+  int want = 14 - p.n_mhigh;
+  if (want < 0) want = 0;
+  int maxsplit = p.n_uhigh - 2;
+  if (maxsplit < 0) maxsplit = 0;
+  p.log_split = want < maxsplit ? want : maxsplit;
+  // bound the partial buffer (2^log_split * nbins doubles) to 64 MiB
+  while (p.log_split > 0 && ((p.nbins << p.log_split) * sizeof(double)) > (size_t(64) << 20)) --p.log_split;
+
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  double* partial = nullptr;
+  if (p.log_split > 0) {
+    int rc = ensure_scratch(h, (size_t)(p.nbins << p.log_split) * sizeof(double));
+    if (rc != QB_OK) return rc;
+    partial = (double*)h->scratch;
+  }
+  uint64_t nwarps = uint64_t(1) << (p.n_mhigh + p.log_split);
+  uint64_t grid = (nwarps + 7) / 8;
+  if (dtype == QB_C128)
+    k3_probs<double2, double><<<(unsigned)grid, 256, 0, h->stream>>>((const double2*)state, (double*)probs_out, partial, p);
+  else
+    k3_probs<float2, float><<<(unsigned)grid, 256, 0, h->stream>>>((const float2*)state, (float*)probs_out, partial, p);
+  QB_CHECK_LAUNCH("k3_probs");
+  if (p.log_split > 0) {
+    int g2 = grid_for(p.nbins, 256, h->sm_count);
+    if (dtype == QB_C128)
+      k3_finish<double><<<g2, 256, 0, h->stream>>>(partial, (double*)probs_out, p.nbins, 1 << p.log_split);
+    else
+      k3_finish<float><<<g2, 256, 0, h->stream>>>(partial, (float*)probs_out, p.nbins, 1 << p.log_split);
+    QB_CHECK_LAUNCH("k3_finish");
+  }
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4
+// ---------------------------------------------------------------------------------------------------
+static int cdf_locked(qb_context* h, const void* probs, int rdtype, uint64_t nbins, double* cdf_out, int mode,
+                      double* total_dev = nullptr) {
+  if (mode == QB_SCAN_EXACT) {
+    if (rdtype == QB_F64) k4_scan_exact<double><<<1, 256, 0, h->stream>>>((const double*)probs, cdf_out, nbins);
+    else k4_scan_exact<float><<<1, 256, 0, h->stream>>>((const float*)probs, cdf_out, nbins);
+    QB_CHECK_LAUNCH("k4_scan_exact");
+  } else {
+    uint64_t nblocks = (nbins + PSCAN_BLOCK - 1) / PSCAN_BLOCK;
+    int rc = ensure_scratch(h, (size_t)nblocks * 2 * sizeof(double));
+    if (rc != QB_OK) return rc;
+    double* tot = (double*)h->scratch;
+    double* off = tot + nblocks;
+    if (rdtype == QB_F64) {
+      k4_scan_block<double, false><<<(unsigned)nblocks, PSCAN_THREADS, 0, h->stream>>>((const double*)probs, cdf_out, tot, off, nbins);
+      k4_scan_totals<<<1, 32, 0, h->stream>>>(tot, off, nblocks);
+      k4_scan_block<double, true><<<(unsigned)nblocks, PSCAN_THREADS, 0, h->stream>>>((const double*)probs, cdf_out, tot, off, nbins);
+    } else {
+      k4_scan_block<float, false><<<(unsigned)nblocks, PSCAN_THREADS, 0, h->stream>>>((const float*)probs, cdf_out, tot, off, nbins);
+      k4_scan_totals<<<1, 32, 0, h->stream>>>(tot, off, nblocks);
+      k4_scan_block<float, true><<<(unsigned)nblocks, PSCAN_THREADS, 0, h->stream>>>((const float*)probs, cdf_out, tot, off, nbins);
+    }
+    QB_CHECK_LAUNCH("k4_scan_block");
+  }
+  if (total_dev) QB_CUDA(cudaMemcpyAsync(total_dev, cdf_out + (nbins - 1), sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  k4_normalize<<<grid_for(nbins, 256, h->sm_count), 256, 0, h->stream>>>(cdf_out, nbins);
+  k4_normalize_last<<<1, 32, 0, h->stream>>>(cdf_out, nbins);
+  QB_CHECK_LAUNCH("k4_normalize");
+  return QB_OK;
+}
+
+int qb_cdf(qb_handle h, const void* probs, int rdtype, uint64_t nbins, double* cdf_out, int mode) {
+  if (!h || !probs || !cdf_out || nbins == 0 || (rdtype != QB_F32 && rdtype != QB_F64) ||
+      (mode != QB_SCAN_EXACT && mode != QB_SCAN_PARALLEL))
+    return fail(QB_ERR_INVALID, "bad cdf arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  return cdf_locked(h, probs, rdtype, nbins, cdf_out, mode);
+}
+
+int qb_sample_cdf(qb_handle h, const double* cdf, uint64_t nbins, const double* uniforms, uint64_t nshots, int64_t* out) {
+  if (!h || !cdf || nbins == 0 || (nshots && (!uniforms || !out))) return fail(QB_ERR_INVALID, "bad sampling arguments");
+  if (nshots == 0) return QB_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  k4_search<<<grid_for(nshots, 256, h->sm_count), 256, 0, h->stream>>>(cdf, nbins, uniforms, nshots, (long long*)out);
+  QB_CHECK_LAUNCH("k4_search");
+  return QB_OK;
+}
+
+int qb_sample(qb_handle h, const void* probs, int rdtype, uint64_t nbins, const double* uniforms_host, uint64_t nshots,
+              int64_t* out_host, int mode, double* total_out) {
+  if (!h || !probs || nbins == 0 || (rdtype != QB_F32 && rdtype != QB_F64) || (nshots && (!uniforms_host || !out_host)) ||
+      (mode != QB_SCAN_EXACT && mode != QB_SCAN_PARALLEL))
+    return fail(QB_ERR_INVALID, "bad sampling arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  size_t need = nbins * sizeof(double) + nshots * 16 + 16;
+  if (h->cdf_bytes < need) {
+    if (h->cdf) {
+      QB_CUDA(cudaStreamSynchronize(h->stream));
+      cudaFree(h->cdf);
+      h->cdf = nullptr;
+      h->cdf_bytes = 0;
+    }
+    QB_CUDA(cudaMalloc((void**)&h->cdf, need));
+    h->cdf_bytes = need;
+  }
+  double* cdf = h->cdf;
+  double* u_dev = cdf + nbins;
+  long long* out_dev = (long long*)(u_dev + nshots);
+  double* total_dev = (double*)(out_dev + nshots);
+  int rc = cdf_locked(h, probs, rdtype, nbins, cdf, mode, total_dev);
+  if (rc != QB_OK) return rc;
+  if (total_out) QB_CUDA(cudaMemcpyAsync(total_out, total_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (nshots) {
+    QB_CUDA(cudaMemcpyAsync(u_dev, uniforms_host, nshots * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k4_search<<<grid_for(nshots, 256, h->sm_count), 256, 0, h->stream>>>(cdf, nbins, u_dev, nshots, out_dev);
+    QB_CHECK_LAUNCH("k4_search");
+    QB_CUDA(cudaMemcpyAsync(out_host, out_dev, nshots * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  }
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5
+// ---------------------------------------------------------------------------------------------------
+int qb_collapse(qb_handle h, void* state, int nqubits, int dtype, const int* qubits, int nmeasured, uint64_t outcome,
+                int normalize) {
+  if (!h || !valid_state_args(state, nqubits, dtype)) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (nmeasured < 1 || nmeasured > nqubits || !qubits) return fail(QB_ERR_INVALID, "bad measured qubits");
+  if (outcome >> nmeasured) return fail(QB_ERR_INVALID, "outcome out of range");
+  uint64_t mask = 0, val = 0;
+  std::vector<int> pos;
+  for (int i = 0; i < nmeasured; ++i) {
+    int q = qubits[i];
+    if (q < 0 || q >= nqubits) return fail(QB_ERR_INVALID, "measured qubit out of range");
+    int p = nqubits - 1 - q;
+    if ((mask >> p) & 1) return fail(QB_ERR_INVALID, "repeated measured qubit");
+    mask |= uint64_t(1) << p;
+    if ((outcome >> (nmeasured - 1 - i)) & 1) val |= uint64_t(1) << p;
+    pos.push_back(p);
+  }
+  std::sort(pos.begin(), pos.end());
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  double* norm_dev = nullptr;
+  if (normalize) {
+    int rc = slice_norm2_device(h, state, nqubits, dtype, pos, val, &norm_dev);
+    if (rc != QB_OK) return rc;
+  } else {
+    int rc = ensure_scratch(h, 64);
+    if (rc != QB_OK) return rc;
+    norm_dev = (double*)h->scratch;
+  }
+  uint64_t count = uint64_t(1) << nqubits;
+  int grid = grid_for(count, 256, h->sm_count);
+  if (dtype == QB_C128)
+    k5_project<double2><<<grid, 256, 0, h->stream>>>((double2*)state, count, mask, val, norm_dev, normalize);
+  else
+    k5_project<float2><<<grid, 256, 0, h->stream>>>((float2*)state, count, mask, val, norm_dev, normalize);
+  QB_CHECK_LAUNCH("k5_project");
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7 plumbing (exchange kernels live in qb_sweep.cuh)
+// ---------------------------------------------------------------------------------------------------
+int qb_pack_half(qb_handle h, const void* state, int nqubits, int dtype, int local_qubit, int bit, void* staging) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !staging) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (local_qubit < 0 || local_qubit >= nqubits || (bit != 0 && bit != 1)) return fail(QB_ERR_INVALID, "bad qubit");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int rc = launch_half_copy(h->stream, h->sm_count, (void*)state, staging, nqubits, dtype, nqubits - 1 - local_qubit, bit, 0);
+  if (rc != QB_OK) return cuda_fail(cudaGetLastError(), "pack_half");
+  return QB_OK;
+}
+
+int qb_unpack_half(qb_handle h, void* state, int nqubits, int dtype, int local_qubit, int bit, const void* staging) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !staging) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (local_qubit < 0 || local_qubit >= nqubits || (bit != 0 && bit != 1)) return fail(QB_ERR_INVALID, "bad qubit");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int rc = launch_half_copy(h->stream, h->sm_count, state, (void*)staging, nqubits, dtype, nqubits - 1 - local_qubit, bit, 1);
+  if (rc != QB_OK) return cuda_fail(cudaGetLastError(), "unpack_half");
+  return QB_OK;
+}
+
+int qb_exchange_half_p2p(qb_handle h, void* state, const void* peer_staging, int nqubits, int dtype, int local_qubit, int bit) {
+  // reading the partner's packed half through a peer-mapped pointer is the same gather as unpack_half
+  return qb_unpack_half(h, state, nqubits, dtype, local_qubit, bit, peer_staging);
+}
+
+int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes) {
+  if (!h || !dptr || !handle_out_64bytes) return fail(QB_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t hd;
+  QB_CUDA(cudaIpcGetMemHandle(&hd, dptr));
+  memcpy(handle_out_64bytes, &hd, 64);
+  return QB_OK;
+}
+
+int qb_ipc_open_handle(qb_handle h, const void* handle_64bytes, void** dptr_out) {
+  if (!h || !handle_64bytes || !dptr_out) return fail(QB_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle_64bytes, 64);
+  QB_CUDA(cudaIpcOpenMemHandle(dptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+  return QB_OK;
+}
+
+int qb_ipc_close_handle(qb_handle h, void* dptr) {
+  if (!h || !dptr) return fail(QB_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  QB_CUDA(cudaIpcCloseMemHandle(dptr));
+  return QB_OK;
+}
+

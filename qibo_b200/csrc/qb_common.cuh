@@ -1,0 +1,82 @@
+// qibo_b200: shared host/device helpers (bit-insertion index math, complex arithmetic).
+// Everything here is QB_HD so that tests/emul can compile the *same* index math for the CPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QB_HD __host__ __device__ __forceinline__
+#define QB_D __device__ __forceinline__
+#include <cuda_runtime.h>
+#else
+#define QB_HD inline
+#define QB_D inline
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+#endif
+
+namespace qb {
+
+// ---- complex helpers on float2 / double2 ---------------------------------------------------------
+template <typename R> struct cplx_of;
+template <> struct cplx_of<float> { using type = float2; };
+template <> struct cplx_of<double> { using type = double2; };
+template <typename C> struct real_of;
+template <> struct real_of<float2> { using type = float; };
+template <> struct real_of<double2> { using type = double; };
+
+template <typename C> QB_HD C cmake(typename real_of<C>::type re, typename real_of<C>::type im) {
+  C c; c.x = re; c.y = im; return c;
+}
+template <typename C> QB_HD C cmul(C a, C b) {
+  C c; c.x = a.x * b.x - a.y * b.y; c.y = a.x * b.y + a.y * b.x; return c;
+}
+template <typename C> QB_HD C cadd(C a, C b) { C c; c.x = a.x + b.x; c.y = a.y + b.y; return c; }
+// acc += a * b
+template <typename C> QB_HD void cfma(C& acc, C a, C b) {
+  acc.x += a.x * b.x; acc.x -= a.y * b.y;
+  acc.y += a.x * b.y; acc.y += a.y * b.x;
+}
+template <typename C> QB_HD typename real_of<C>::type cnorm2(C a) { return a.x * a.x + a.y * a.y; }
+
+// ---- bit utilities --------------------------------------------------------------------------------
+// insert a zero bit at position p (bits >= p move up by one)
+QB_HD uint64_t insert_zero(uint64_t x, int p) {
+  uint64_t lo = x & ((uint64_t(1) << p) - 1);
+  return ((x >> p) << (p + 1)) | lo;
+}
+// software pdep: deposit the low bits of x into the set bits of mask (ascending)
+QB_HD uint64_t deposit(uint64_t x, uint64_t mask) {
+  uint64_t r = 0;
+  int k = 0;
+  while (mask) {
+    uint64_t low = mask & (~mask + 1);
+    if ((x >> k) & 1) r |= low;
+    mask ^= low;
+    ++k;
+  }
+  return r;
+}
+// software pext
+QB_HD uint64_t extract(uint64_t x, uint64_t mask) {
+  uint64_t r = 0;
+  int k = 0;
+  while (mask) {
+    uint64_t low = mask & (~mask + 1);
+    if (x & low) r |= uint64_t(1) << k;
+    mask ^= low;
+    ++k;
+  }
+  return r;
+}
+
+// Sorted list of bit positions to insert zeros at (targets and controls of a gate).
+struct InsertList {
+  int32_t n;        // number of positions
+  uint8_t pos[48];  // ascending
+};
+QB_HD uint64_t expand(uint64_t g, const InsertList& il) {
+  for (int i = 0; i < il.n; ++i) g = insert_zero(g, il.pos[i]);
+  return g;
+}
+
+}  // namespace qb

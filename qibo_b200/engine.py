@@ -1,0 +1,211 @@
+"""Host-side engine over the C ABI: the qibo-independent half of the backend.
+
+Owns one library context per CUDA device and exposes the hot path on :class:`DeviceArray` states.
+torch is used for what the task statement calls plumbing: device allocation (the caching allocator)
+and the current stream.  All arithmetic happens inside libqibo_b200.so.
+"""
+
+import ctypes
+from collections import Counter
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from qibo_b200 import _lib
+from qibo_b200.array import DeviceArray, torch_dtype
+from qibo_b200.ops import Op, pack_ops
+
+_DT = {np.dtype("complex64"): _lib.QB_C64, np.dtype("complex128"): _lib.QB_C128}
+_RT = {np.dtype("float32"): _lib.QB_F32, np.dtype("float64"): _lib.QB_F64}
+# NumPy's exact-scan contract is kept up to this many bins; beyond it the parallel scan is used
+EXACT_SCAN_MAX_BINS = 1 << 22
+
+
+def _int_array(values):
+    arr = (ctypes.c_int * max(len(values), 1))(*[int(v) for v in values])
+    return arr
+
+
+class Engine:
+    """One context = one GPU + one stream.  Raises if there is no CUDA device (no CPU fallback)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.QiboB200Error(
+                "qibo_b200 needs a CUDA device: the hot path exists only as sm_100a kernels (no CPU fallback)"
+            )
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists before the library attaches
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.qb_create(self.device_index, ctypes.c_void_p(stream), ctypes.byref(handle)))
+        self.handle = handle
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.qb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- memory / state construction (K6) ---------------------------------------------------------
+    def empty(self, shape, dtype) -> DeviceArray:
+        return DeviceArray(torch.empty(shape, dtype=torch_dtype(dtype), device=self.device))
+
+    def basis_state(self, nqubits: int, dtype="complex128", index: int = 0) -> DeviceArray:
+        """zero_state (abstract.py:2243-2273) generalised to any basis index."""
+        out = self.empty((1 << nqubits,), dtype)
+        _lib.check(self.lib.qb_state_set_basis(self.handle, out.data_ptr(), nqubits, _DT[np.dtype(dtype)], index))
+        return out
+
+    def filled_state(self, nqubits: int, value: complex, dtype="complex128") -> DeviceArray:
+        """plus_state (abstract.py:2199-2221): every amplitude equal to ``value``."""
+        out = self.empty((1 << nqubits,), dtype)
+        value = complex(value)
+        _lib.check(self.lib.qb_state_fill(self.handle, out.data_ptr(), nqubits, _DT[np.dtype(dtype)], value.real, value.imag))
+        return out
+
+    def upload(self, array, dtype=None) -> DeviceArray:
+        """Host (or torch) array -> DeviceArray (Backend.cast for a state)."""
+        if isinstance(array, DeviceArray):
+            return array if dtype is None or np.dtype(dtype) == array.dtype else self.cast(array, dtype)
+        if isinstance(array, torch.Tensor):
+            t = array.to(self.device)
+            return DeviceArray(t if dtype is None else t.to(torch_dtype(dtype)))
+        host = np.ascontiguousarray(array) if dtype is None else np.ascontiguousarray(array, dtype=dtype)
+        return DeviceArray(torch.from_numpy(host).to(self.device))
+
+    def cast(self, array: DeviceArray, dtype) -> DeviceArray:
+        dtype = np.dtype(dtype)
+        if dtype == array.dtype:
+            return array
+        if array.dtype in _DT and dtype in _DT:
+            out = self.empty(array.shape, dtype)
+            _lib.check(
+                self.lib.qb_state_cast(self.handle, out.data_ptr(), _DT[dtype], array.data_ptr(), _DT[array.dtype], array.size)
+            )
+            return out
+        return DeviceArray(array.tensor.to(torch_dtype(dtype)))
+
+    def copy(self, array: DeviceArray) -> DeviceArray:
+        return DeviceArray(array.tensor.clone())
+
+    def synchronize(self):
+        _lib.check(self.lib.qb_sync(self.handle))
+
+    def norm2(self, state: DeviceArray) -> float:
+        n = int(state.size).bit_length() - 1
+        out = ctypes.c_double()
+        _lib.check(self.lib.qb_state_norm2(self.handle, state.data_ptr(), n, _DT[state.dtype], ctypes.byref(out)))
+        return out.value
+
+    # ---- K1: one gate ---------------------------------------------------------------------------
+    def apply_op(self, state: DeviceArray, nqubits: int, op: Op) -> DeviceArray:
+        fn = self.lib.qb_apply_diagonal if op.is_diagonal else self.lib.qb_apply_matrix
+        _lib.check(
+            fn(
+                self.handle, state.data_ptr(), nqubits, _DT[state.dtype], op.data.ctypes.data,
+                len(op.targets), _int_array(op.targets), len(op.controls), _int_array(op.controls),
+            )
+        )
+        return state
+
+    # ---- K2: a gate queue -------------------------------------------------------------------------
+    def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False):
+        """Apply ``ops`` in order, several gates per HBM sweep.  Returns the planner/timing statistics."""
+        stats = _lib.QbProgramStats()
+        if len(ops) == 0:
+            return stats
+        arr, keep = pack_ops(ops)
+        flags = (0 if fuse else _lib.QB_PROGRAM_NO_FUSE) | (_lib.QB_PROGRAM_TIME if timed else 0)
+        _lib.check(
+            self.lib.qb_apply_program(
+                self.handle, state.data_ptr(), nqubits, _DT[state.dtype], arr, len(ops), flags, ctypes.byref(stats)
+            )
+        )
+        del keep
+        self.last_stats = stats
+        return stats
+
+    def plan(self, nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
+        return plan_program(nqubits, dtype, ops, fuse)
+
+    # ---- K3: probabilities --------------------------------------------------------------------------
+    def probabilities(self, state: DeviceArray, qubits: Sequence[int], nqubits: int) -> DeviceArray:
+        rdtype = np.dtype("float64") if state.dtype == np.dtype("complex128") else np.dtype("float32")
+        out = self.empty((1 << len(qubits),), rdtype)
+        _lib.check(
+            self.lib.qb_probabilities(
+                self.handle, state.data_ptr(), nqubits, _DT[state.dtype], _int_array(qubits), len(qubits), out.data_ptr()
+            )
+        )
+        return out
+
+    # ---- K4: sampling ---------------------------------------------------------------------------------
+    def sample(self, probs: DeviceArray, uniforms: np.ndarray, mode: Optional[int] = None, return_total: bool = False):
+        """Inverse-CDF sampling: ``searchsorted(cumsum(p) / sum, u, side="right")`` as np.random.choice does."""
+        nbins = probs.size
+        if mode is None:
+            mode = _lib.QB_SCAN_EXACT if nbins <= EXACT_SCAN_MAX_BINS else _lib.QB_SCAN_PARALLEL
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.empty(uniforms.shape[0], dtype=np.int64)
+        total = ctypes.c_double()
+        _lib.check(
+            self.lib.qb_sample(
+                self.handle, probs.data_ptr(), _RT[probs.dtype], nbins, uniforms.ctypes.data, uniforms.shape[0],
+                out.ctypes.data, mode, ctypes.byref(total),
+            )
+        )
+        return (out, total.value) if return_total else out
+
+    def cdf(self, probs: DeviceArray, mode: int) -> DeviceArray:
+        out = self.empty((probs.size,), np.float64)
+        _lib.check(self.lib.qb_cdf(self.handle, probs.data_ptr(), _RT[probs.dtype], probs.size, out.data_ptr(), mode))
+        return out
+
+    def sample_cdf(self, cdf: DeviceArray, uniforms: DeviceArray) -> DeviceArray:
+        out = self.empty((uniforms.size,), np.int64)
+        _lib.check(self.lib.qb_sample_cdf(self.handle, cdf.data_ptr(), cdf.size, uniforms.data_ptr(), uniforms.size, out.data_ptr()))
+        return out
+
+    # ---- K5: collapse -----------------------------------------------------------------------------------
+    def collapse(self, state: DeviceArray, nqubits: int, qubits: Sequence[int], outcome: int, normalize: bool = True):
+        _lib.check(
+            self.lib.qb_collapse(
+                self.handle, state.data_ptr(), nqubits, _DT[state.dtype], _int_array(qubits), len(qubits), int(outcome),
+                1 if normalize else 0,
+            )
+        )
+        return state
+
+    def mem_info(self):
+        free, total = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(self.lib.qb_mem_info(self.handle, ctypes.byref(free), ctypes.byref(total)))
+        return free.value, total.value
+
+
+def plan_program(nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
+    """Host-only planner call (no GPU needed): -> (stats, sweep index of every op)."""
+    lib = _lib.load()
+    stats = _lib.QbProgramStats()
+    arr, keep = pack_ops(ops)
+    sweep_of_op = (ctypes.c_int32 * max(len(ops), 1))()
+    flags = 0 if fuse else _lib.QB_PROGRAM_NO_FUSE
+    _lib.check(lib.qb_plan_program(nqubits, _DT[np.dtype(dtype)], arr, len(ops), flags, ctypes.byref(stats), sweep_of_op))
+    del keep
+    return stats, list(sweep_of_op)[: len(ops)]
+
+
+def frequencies_from_samples(samples: np.ndarray) -> Counter:
+    """calculate_frequencies (abstract.py:2727-2732) on the host-resident sample vector (S3)."""
+    res, counts = np.unique(samples, return_counts=True)
+    return Counter(dict(zip(res.tolist(), counts.tolist())))

@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE: builds and loads the CPU emulation of the sweep data path (tests/emul/emul.cpp)."""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_emul.so")
+SRC = os.path.join(HERE, "emul.cpp")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "qibo_b200", "csrc")
+
+
+def _stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def load():
+    if _stale():
+        subprocess.run(
+            ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", SO, SRC], check=True
+        )
+    from qibo_b200 import _lib
+
+    lib = ctypes.CDLL(SO)
+    lib.emul_apply_program.restype = ctypes.c_int
+    lib.emul_apply_program.argtypes = [
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.QbOp), ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(_lib.QbProgramStats),
+    ]
+    lib.emul_last_error.restype = ctypes.c_char_p
+    lib.emul_canon_kind.restype = ctypes.c_int
+    lib.emul_canon_kind.argtypes = [
+        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+    ]
+    return lib
+
+
+def apply_program(state, nqubits, ops, fuse=True):
+    """Run ``ops`` (qibo_b200.ops.Op list) through the emulated sweep path, in place on a copy; -> (state, stats)."""
+    from qibo_b200 import _lib
+    from qibo_b200.ops import pack_ops
+
+    lib = load()
+    state = np.ascontiguousarray(state).copy()
+    dtype = _lib.QB_C128 if state.dtype == np.complex128 else _lib.QB_C64
+    arr, keep = pack_ops(ops)
+    stats = _lib.QbProgramStats()
+    rc = lib.emul_apply_program(
+        state.ctypes.data, nqubits, dtype, arr, len(ops), 0 if fuse else _lib.QB_PROGRAM_NO_FUSE, ctypes.byref(stats)
+    )
+    if rc != 0:
+        raise RuntimeError(lib.emul_last_error().decode())
+    del keep
+    return state, stats
+
+
+def canon_kind(nqubits, op):
+    lib = load()
+    kind, nt, nc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    t = (ctypes.c_int * max(1, len(op.targets)))(*op.targets)
+    c = (ctypes.c_int * max(1, len(op.controls)))(*op.controls)
+    rc = lib.emul_canon_kind(
+        nqubits, op.data.ctypes.data, int(op.is_diagonal), len(op.targets), t, len(op.controls), c,
+        ctypes.byref(kind), ctypes.byref(nt), ctypes.byref(nc),
+    )
+    if rc != 0:
+        raise ValueError(lib.emul_last_error().decode())
+    return kind.value, nt.value, nc.value

@@ -1,0 +1,93 @@
+// TEST INFRASTRUCTURE ONLY.  CPU emulation of the sweep kernel's data path: it compiles the PRODUCT's own
+// planner (qb_planner.hpp), canonicaliser (qb_canon.hpp) and shared-memory passes (qb_passes.cuh, nct = 1)
+// with g++ and walks tiles exactly as qb_sweep.cuh does (gather runs -> per-op prephase -> passes ->
+// scatter).  It lets the CPU test-suite check index math, fan tables and program serialisation without a
+// GPU.  It is never loaded by qibo_b200/ -- the product has no CPU path.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../qibo_b200/csrc/qb_passes.cuh"
+
+using namespace qb;
+
+template <typename C>
+static void run_sweep(C* state, const char* blob) {
+  const SweepHeader& hdr = *reinterpret_cast<const SweepHeader*>(blob);
+  const int T = (int)hdr.T, L = (int)hdr.L;
+  const uint32_t nruns = 1u << (T - L), run = 1u << L;
+  const DevOp* ops = reinterpret_cast<const DevOp*>(blob + hdr.ops_offset);
+  std::vector<C> tile(size_t(1) << T);
+  for (uint64_t t = 0; t < hdr.ntiles; ++t) {
+    const uint64_t base = deposit(t, hdr.other_mask);
+    for (uint32_t r = 0; r < nruns; ++r) {
+      const uint64_t off = deposit(uint64_t(r) << L, hdr.tile_mask);
+      memcpy(&tile[size_t(r) << L], state + base + off, run * sizeof(C));
+    }
+    for (uint32_t o = 0; o < hdr.nops; ++o) {
+      const DevOp& op = ops[o];
+      uint32_t flag, aux;
+      C scal;
+      op_prephase<C>(op, blob, base, flag, scal, aux);
+      if (!flag) continue;
+      const C* payload = reinterpret_cast<const C*>(blob + op.payload);
+      switch (op.type) {
+        case OP_DENSE:
+          if (op.k == 1) pass_dense<C, 1>(tile.data(), op, payload, T, 0, 1);
+          else pass_dense<C, 2>(tile.data(), op, payload, T, 0, 1);
+          break;
+        case OP_SWAP: pass_swap<C>(tile.data(), op, T, 0, 1); break;
+        case OP_FAN: pass_fan<C>(tile.data(), op, blob, scal, T, 0, 1); break;
+        case OP_DIAGK: pass_diagk<C>(tile.data(), op, blob, aux, T, 0, 1); break;
+        case OP_DENSE_BIG: {
+          const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
+          std::vector<BigAcc<C>> accs(ntasks);
+          for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, task, accs[task]);
+          for (uint32_t task = 0; task < ntasks; ++task) big_write<C>(tile.data(), op, accs[task]);
+        } break;
+        default: break;
+      }
+    }
+    for (uint32_t r = 0; r < nruns; ++r) {
+      const uint64_t off = deposit(uint64_t(r) << L, hdr.tile_mask);
+      memcpy(state + base + off, &tile[size_t(r) << L], run * sizeof(C));
+    }
+  }
+}
+
+static std::string g_err;
+
+extern "C" const char* emul_last_error() { return g_err.c_str(); }
+
+extern "C" int emul_apply_program(void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
+                                  qb_program_stats* stats) {
+  std::vector<CanonOp> canon;
+  for (int i = 0; i < nops; ++i) {
+    CanonOp c;
+    if (!canonicalize(nqubits, ops[i].data, ops[i].is_diagonal != 0, ops[i].ntargets, ops[i].targets, ops[i].ncontrols,
+                      ops[i].controls, c, g_err))
+      return QB_ERR_INVALID;
+    canon.push_back(c);
+  }
+  Plan plan;
+  if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, g_err)) return QB_ERR_UNSUPPORTED;
+  if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
+  for (auto& sd : plan.sweeps) {
+    const char* blob = plan.blob.data() + sd.blob_offset;
+    if (dtype == QB_C128) run_sweep<double2>((double2*)state, blob);
+    else run_sweep<float2>((float2*)state, blob);
+  }
+  return QB_OK;
+}
+
+// canonical form of one gate, for structural tests: kind, #targets, #controls
+extern "C" int emul_canon_kind(int nqubits, const double* data, int is_diag, int nt, const int* targets, int nc,
+                               const int* controls, int* kind, int* ntargets, int* ncontrols) {
+  CanonOp c;
+  if (!canonicalize(nqubits, data, is_diag != 0, nt, targets, nc, controls, c, g_err)) return QB_ERR_INVALID;
+  *kind = c.kind;
+  *ntargets = (int)c.tpos.size();
+  *ncontrols = (int)c.cpos.size();
+  return QB_OK;
+}

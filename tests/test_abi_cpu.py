@@ -1,0 +1,100 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/qibo_b200.h
+declares, refuses to run without a GPU (no CPU fallback), and its host-only planner works."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from qibo_b200 import _lib, circuits
+from qibo_b200.engine import plan_program
+from qibo_b200.ops import Op
+
+HAS_GPU = torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "qibo_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(qb_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 25
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.qb_version() == 100
+
+
+def test_struct_layout_matches_header():
+    # qb_op: 2 + 6 + 32 + 2 int32 then a pointer; qb_program_stats: 4 int32, double, 2 float
+    assert ctypes.sizeof(_lib.QbOp) == 4 * (2 + 6 + 32 + 2) + 8
+    assert ctypes.sizeof(_lib.QbProgramStats) == 32
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.qb_create(0, None, ctypes.byref(h))
+    assert rc == _lib.QB_ERR_CUDA
+    assert "no CPU fallback" in _lib.last_error()
+    from qibo_b200.engine import Engine
+
+    with pytest.raises(_lib.QiboB200Error):
+        Engine(0)
+
+
+def test_planner_packs_qft_into_few_sweeps():
+    for n, dtype in ((30, "complex128"), (32, "complex128"), (31, "complex64")):
+        ops = circuits.qft(n)
+        stats, sweep_of_op = plan_program(n, dtype, ops)
+        assert stats.nops == len(ops) == n * (n + 1) // 2 + n // 2
+        assert stats.nsweeps <= 20, stats.nsweeps  # gate-by-gate would be ~500 sweeps
+        assert sweep_of_op == sorted(sweep_of_op)  # program order is preserved
+        itemsize = 16 if dtype == "complex128" else 8
+        assert stats.bytes_moved == stats.nsweeps * 2 * itemsize * 2.0**n
+        stats1, _ = plan_program(n, dtype, ops, fuse=False)
+        assert stats1.nsweeps == len(ops)
+
+
+def test_planner_argument_errors():
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    with pytest.raises(ValueError):
+        plan_program(4, "complex128", [Op(h, (4,))])
+    with pytest.raises(ValueError):
+        plan_program(4, "complex128", [Op(np.eye(4), (1, 1))])
+    with pytest.raises(ValueError):
+        Op(np.eye(4), (1,))
+    with pytest.raises(NotImplementedError):
+        Op(np.eye(128), tuple(range(7)))
+
+
+def test_product_circuits_match_oracle_generators():
+    """qibo_b200.circuits (product, used by bench/smoke) describes the same circuits as the pinned oracle."""
+    from oracle import numpy_oracle as orc
+
+    def same(ops, named):
+        assert len(ops) == len(named)
+        for op, (name, qubits, params) in zip(ops, named):
+            assert op.targets == tuple(qubits)
+            np.testing.assert_array_equal(op.data, orc.gate_matrix(name, *params))
+
+    same(circuits.qft(9), orc.qft_ops(9))
+    th = np.random.default_rng(3).random(2 * 2 * 6)
+    same(circuits.variational(6, 2, th), orc.variational_ops(6, 2, th))
+    same(circuits.random_circuit(7, 25, 11), orc.random_ops(7, 25, 11))
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+
+    code = "import sys; import qibo_b200, qibo_b200.engine, qibo_b200.circuits, qibo_b200.ops; assert not any(m.startswith('oracle') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for root, _, files in os.walk(os.path.join(ROOT, "qibo_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp")):
+                assert "oracle" not in open(os.path.join(root, f)).read().replace("no oracle", ""), f

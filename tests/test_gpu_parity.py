@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via qibo_b200.engine) against the oracle and the
+reference's golden vectors.  Tolerances are the north star's: 1e-12 max-abs complex128, 1e-5 complex64;
+samples bit-exact for the same uniforms."""
+
+from collections import Counter
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import tol
+from helpers import ops_from_named, oracle_run, rand_state, random_zoo
+from oracle import numpy_oracle as orc
+from qibo_b200.ops import Op
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from qibo_b200.engine import Engine
+
+    return Engine(0)
+
+
+def run_k1(eng, psi, ops, n):
+    st = eng.upload(psi)
+    for op in ops:
+        eng.apply_op(st, n, op)
+    return st.numpy()
+
+
+def run_k2(eng, psi, ops, n, fuse=True):
+    st = eng.upload(psi)
+    eng.apply_program(st, n, ops, fuse=fuse)
+    return st.numpy()
+
+
+# ------------------------------------------------------------------------------------------ G1 / G2
+def test_golden_gates(eng, golden):
+    cases = golden.cases("gate_cases")
+    for i, c in enumerate(cases):
+        psi, ref, mat = golden[f"gate{i}_in"], golden[f"gate{i}_out"], golden[f"gate{i}_matrix"]
+        op = Op(mat, tuple(c["targets"]), tuple(c["controls"])) if c["is_controlled_by"] else Op(mat, tuple(c["qubits"]))
+        n = c["nqubits"]
+        out = run_k1(eng, psi, [op], n)
+        assert out.dtype == ref.dtype
+        assert np.abs(out - ref).max() < tol(c["dtype"]), ("k1", c["tag"])
+        for fuse in (True, False):
+            out = run_k2(eng, psi, [op], n, fuse)
+            assert np.abs(out - ref).max() < tol(c["dtype"]), ("k2", fuse, c["tag"])
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_zoo_every_bit_position(eng, dtype, seed):
+    """Every kernel family (dense k<=5, controls, diagonals, phases, swaps) on targets spanning low (vectorised /
+    in-run) and high (cross-tile) bit positions, K1 gate-by-gate and K2 fused."""
+    n = 16
+    ops = random_zoo(n, 60, seed)
+    psi = rand_state(n, seed, dtype)
+    ref = oracle_run(psi, ops, n)
+    scale = 10 if dtype == "complex64" else 1
+    assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
+    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
+    assert np.abs(run_k2(eng, psi, ops, n, fuse=False) - ref).max() < tol(dtype) * scale
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_single_qubit_gate_on_every_qubit(eng, dtype):
+    n = 18
+    psi = rand_state(n, 42, dtype)
+    rng = np.random.default_rng(5)
+    from helpers import rand_unitary
+
+    for q in range(n):
+        op = Op(rand_unitary(1, rng), (q,))
+        ref = oracle_run(psi, [op], n)
+        assert np.abs(run_k1(eng, psi, [op], n) - ref).max() < tol(dtype), q
+        assert np.abs(run_k2(eng, psi, [op], n) - ref).max() < tol(dtype), q
+    for a, b in [(0, 17), (17, 0), (16, 17), (3, 9), (0, 1), (8, 17)]:
+        op = Op(rand_unitary(2, rng), (a, b))
+        ref = oracle_run(psi, [op], n)
+        assert np.abs(run_k1(eng, psi, [op], n) - ref).max() < tol(dtype), (a, b)
+        assert np.abs(run_k2(eng, psi, [op], n) - ref).max() < tol(dtype), (a, b)
+
+
+# ------------------------------------------------------------------------------------------ circuits
+def _ops_for(tag, golden):
+    if tag.startswith("qft"):
+        return orc.qft_ops(int(tag[3:].split("_")[0]), with_swaps="noswap" not in tag)
+    if tag.startswith("var10x3"):
+        return orc.variational_ops(10, 3, golden["var_thetas"])
+    return orc.random_ops(9, 40, seed=11)
+
+
+def test_golden_circuits(eng, golden):
+    for i, c in enumerate(golden.cases("circ_cases")):
+        n, dtype = c["nqubits"], c["dtype"]
+        psi = orc.zero_state(n, dtype) if c["zero"] else golden[f"circ{i}_in"]
+        if c["queue"] is None:
+            ops = ops_from_named(_ops_for(c["tag"], golden))
+        else:  # the reference fuser's FusedGate matrices (k <= 5 dense blocks)
+            ops = [Op(golden[f"circ{i}_q{j}"], tuple(q)) for j, q in enumerate(c["queue"])]
+        ref = golden[f"circ{i}_out"]
+        assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype), c["tag"]
+        assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype), c["tag"]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [1, 2, 4, 11, 12, 13, 14, 17, 20])
+def test_qft_vs_oracle(eng, n, dtype):
+    psi = rand_state(n, 100 + n, dtype)
+    named = orc.qft_ops(n)
+    ref = orc.run_ops(psi, named, n, dtype=dtype)
+    ops = ops_from_named(named)
+    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype)
+    if n <= 17:
+        assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype)
+        assert np.abs(run_k2(eng, psi, ops, n, fuse=False) - ref).max() < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_variational_and_random_vs_oracle(eng, dtype):
+    n = 18
+    thetas = 2 * np.pi * np.random.default_rng(7).random(2 * 3 * n)
+    named = orc.variational_ops(n, 3, thetas)
+    psi = rand_state(n, 5, dtype)
+    ref = orc.run_ops(psi, named, n, dtype=dtype)
+    assert np.abs(run_k2(eng, psi, ops_from_named(named), n) - ref).max() < tol(dtype)
+    named = orc.random_ops(n, 80, seed=11)
+    ref = orc.run_ops(psi, named, n, dtype=dtype)
+    assert np.abs(run_k2(eng, psi, ops_from_named(named), n) - ref).max() < tol(dtype)
+    assert np.abs(run_k1(eng, psi, ops_from_named(named), n) - ref).max() < tol(dtype)
+
+
+@pytest.mark.parametrize("n,dtype", [(24, "complex128"), (26, "complex128"), (27, "complex64"), (30, "complex128")])
+def test_qft_full_size_properties(eng, n, dtype):
+    """BASELINE sizes where the oracle is too slow: size-independent properties.
+    QFT == inverse DFT (checked against torch.fft on the same GPU), QFT|0> is uniform, the norm is kept."""
+    from qibo_b200 import circuits
+
+    ops = circuits.qft(n)
+    st = eng.basis_state(n, dtype)
+    eng.apply_program(st, n, ops)
+    expected = 2.0 ** (-n / 2)
+    t = st.tensor
+    assert float((t.real - expected).abs().max()) < tol(dtype) and float(t.imag.abs().max()) < tol(dtype)
+    assert abs(eng.norm2(st) - 1.0) < (1e-9 if dtype == "complex128" else 1e-4)
+    if n <= 27:
+        g = torch.Generator(device="cuda").manual_seed(n)
+        x = torch.randn(2**n, dtype=torch.float64 if dtype == "complex128" else torch.float32, device="cuda", generator=g)
+        y = torch.randn(2**n, dtype=x.dtype, device="cuda", generator=g)
+        psi = torch.complex(x, y)
+        psi /= torch.linalg.vector_norm(psi)
+        from qibo_b200.array import DeviceArray
+
+        st = DeviceArray(psi.clone())
+        eng.apply_program(st, n, ops)
+        ref = torch.fft.ifft(psi, norm="ortho")
+        assert float((st.tensor - ref).abs().max()) < tol(dtype)
+        # linearity: QFT(a*psi) == a*QFT(psi)
+        st2 = DeviceArray(psi * (0.3 - 0.4j))
+        eng.apply_program(st2, n, ops)
+        assert float((st2.tensor - (0.3 - 0.4j) * st.tensor).abs().max()) < tol(dtype)
+
+
+# ------------------------------------------------------------------------------------------ P1
+def test_probabilities_golden(eng, golden):
+    for i, c in enumerate(golden.cases("prob_cases")):
+        st = eng.upload(golden[f"prob{i}_in"])
+        out = eng.probabilities(st, c["qubits"], c["nqubits"]).numpy()
+        ref = golden[f"prob{i}_out"]
+        assert out.dtype == ref.dtype and out.shape == ref.shape
+        assert np.abs(out - ref).max() < (1e-14 if c["dtype"] == "complex128" else 1e-6), c
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [3, 5, 9, 16, 20])
+def test_probabilities_vs_oracle(eng, n, dtype):
+    psi = rand_state(n, n, dtype)
+    st = eng.upload(psi)
+    rng = np.random.default_rng(n)
+    subsets = [list(range(n)), [0], [n - 1], list(range(n - 1, -1, -1))]
+    for _ in range(6):
+        m = int(rng.integers(1, n + 1))
+        subsets.append(rng.permutation(n)[:m].tolist())
+    for qubits in subsets:
+        ref = orc.calculate_probabilities(psi, qubits, n)
+        out = eng.probabilities(st, qubits, n).numpy()
+        assert out.dtype == ref.dtype
+        assert np.abs(out - ref).max() < (1e-14 if dtype == "complex128" else 2e-6), qubits
+        assert abs(out.sum() - 1) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ S1 / S2
+def test_sampling_golden_bit_exact(eng, golden):
+    from qibo_b200 import _lib
+
+    for i, c in enumerate(golden.cases("samp_cases")):
+        p = golden[f"samp{i}_probs"]
+        np.random.seed(c["seed"])
+        u = np.random.random_sample(c["nshots"])
+        out = eng.sample(eng.upload(p), u, mode=_lib.QB_SCAN_EXACT)
+        np.testing.assert_array_equal(out, golden[f"samp{i}_shots"])
+        assert out.dtype == np.int64
+        # float32 probabilities (complex64 states) follow the same contract: promoted to double, then scanned
+        p32 = p.astype(np.float32)
+        out32 = eng.sample(eng.upload(p32), u, mode=_lib.QB_SCAN_EXACT)
+        np.testing.assert_array_equal(out32, orc.choice_from_uniforms(p32, u))
+
+
+def test_sampling_search_is_exact_for_any_cdf(eng):
+    """Contract (i) of SURVEY 8a hazard 1: idx = #{k: cdf[k] <= u} bit-exactly, for both scan modes."""
+    from qibo_b200 import _lib
+
+    rng = np.random.default_rng(1)
+    for nbins in (1, 2, 5, 4096, 4097, 2**20 + 3):
+        p = rng.random(nbins)
+        p /= p.sum()
+        u = rng.random(20000)
+        u[:3] = [0.0, 0.5, np.nextafter(1.0, 0.0)]
+        for mode in (_lib.QB_SCAN_EXACT, _lib.QB_SCAN_PARALLEL):
+            dp = eng.upload(p)
+            cdf = eng.cdf(dp, mode).numpy()
+            out = eng.sample(dp, u, mode=mode)
+            np.testing.assert_array_equal(out, np.searchsorted(cdf, u, side="right"))
+            assert cdf[-1] == 1.0 and np.all(np.diff(cdf) >= -1e-15)
+            if mode == _lib.QB_SCAN_EXACT:
+                ref = np.cumsum(p)
+                ref /= ref[-1]
+                np.testing.assert_array_equal(cdf, ref)  # numpy-exact scan
+            else:
+                assert np.abs(cdf - np.cumsum(p) / p.sum()).max() < 1e-13
+    # edge of the distribution: zero-probability bins are never drawn
+    p = np.array([0.0, 0.5, 0.0, 0.5, 0.0])
+    out = eng.sample(eng.upload(p), rng.random(1000))
+    assert set(out.tolist()) <= {1, 3}
+
+
+# ------------------------------------------------------------------------------------------ C1
+def test_collapse_golden(eng, golden):
+    for i, c in enumerate(golden.cases("coll_cases")):
+        st = eng.upload(golden[f"coll{i}_in"])
+        eng.collapse(st, c["nqubits"], c["qubits"], c["shot"], c["normalize"])
+        assert np.abs(st.numpy() - golden[f"coll{i}_out"]).max() < 1e-14, c
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_collapse_vs_oracle_and_idempotence(eng, dtype):
+    n = 17
+    psi = rand_state(n, 3, dtype)
+    for qubits, shot in (([0], 1), ([16], 0), ([3, 9, 16], 5), (list(range(0, 17, 2)), 137)):
+        st = eng.upload(psi)
+        eng.collapse(st, n, qubits, shot, True)
+        ref = orc.collapse_statevector(psi, qubits, [shot], n, True)
+        assert np.abs(st.numpy() - ref).max() < (1e-13 if dtype == "complex128" else 1e-5)
+        assert abs(eng.norm2(st) - 1.0) < (1e-12 if dtype == "complex128" else 1e-5)
+        once = st.numpy().copy()
+        eng.collapse(st, n, qubits, shot, True)  # projecting twice changes nothing
+        assert np.abs(st.numpy() - once).max() < (1e-15 if dtype == "complex128" else 1e-6)
+
+
+# ------------------------------------------------------------------------------------------ K6 / misc
+def test_state_constructors_and_cast(eng):
+    for dtype in ("complex128", "complex64"):
+        st = eng.basis_state(10, dtype, 5)
+        ref = np.zeros(1024, dtype=dtype)
+        ref[5] = 1
+        np.testing.assert_array_equal(st.numpy(), ref)
+        st = eng.filled_state(10, 1 / 32.0, dtype)
+        np.testing.assert_array_equal(st.numpy(), np.full(1024, 1 / 32.0, dtype=dtype))
+    psi = rand_state(12, 1)
+    d = eng.upload(psi)
+    np.testing.assert_array_equal(eng.cast(d, "complex64").numpy(), psi.astype("complex64"))
+    np.testing.assert_array_equal(eng.cast(eng.cast(d, "complex64"), "complex128").numpy(), psi.astype("complex64").astype("complex128"))
+    assert abs(eng.norm2(d) - 1.0) < 1e-13
+    assert isinstance(d.tensor, torch.Tensor) and d.tensor.is_cuda  # the state buffer is a torch tensor too
+
+
+def test_error_mapping(eng):
+    st = eng.basis_state(4)
+    with pytest.raises(ValueError):
+        eng.apply_op(st, 4, Op(np.eye(2), (7,)))
+    with pytest.raises(ValueError):
+        eng.probabilities(st, [0, 0], 4)
+    with pytest.raises(ValueError):
+        eng.collapse(st, 4, [1], 2)

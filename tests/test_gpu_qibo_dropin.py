@@ -1,0 +1,226 @@
+"""Drop-in tests: the backend plugged into the UNMODIFIED reference package through Qibo's own loader
+(`qibo.set_backend("qibo_b200")`), compared with the reference NumpyBackend on the same circuits.
+They mirror the reference's own tests (tests/test_models_qft.py, test_models_circuit_fuse.py,
+test_measurements*.py, test_models_circuit_execution.py).  Skipped when qibo is not importable."""
+
+import numpy as np
+import pytest
+
+from conftest import have_qibo, tol
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_qibo(), reason="reference package not importable (baseline/_ref)")]
+
+
+@pytest.fixture()
+def backends():
+    import qibo
+    from qibo.backends import NumpyBackend, construct_backend
+
+    ours = construct_backend("qibo_b200")
+    ref = NumpyBackend()
+    yield ours, ref
+    qibo.backends._Global._backend = None
+
+
+def rand_state(n, seed, dtype="complex128"):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=2**n) + 1j * rng.normal(size=2**n)
+    return (x / np.linalg.norm(x)).astype(dtype)
+
+
+def test_loader_and_attributes(backends):
+    import qibo
+    from qibo.backends import list_available_backends
+
+    ours, _ = backends
+    assert ours.name == "qibo_b200" and ours.platform == "cuda-sm100a" and ours.device == "/GPU:0"
+    assert ours.supports_multigpu and ours.qubits is None and ours.connectivity is None and ours.natives is None
+    assert list_available_backends("qibo-b200")["qibo-b200"] == {"cuda-sm100a": True}
+    qibo.set_backend("qibo-b200")
+    assert qibo.get_backend().name == "qibo_b200"
+    qibo.set_backend("qibo_b200", platform="cuda-sm100a")
+    with pytest.raises(ValueError):
+        ours.set_device("/CPU:0")
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [3, 8, 15])
+def test_qft_matches_numpy_backend(backends, n, dtype):
+    from qibo.models import QFT
+
+    ours, ref = backends
+    ours.set_dtype(dtype)
+    ref.set_dtype(dtype)
+    psi = rand_state(n, n, dtype)
+    a = ours.execute_circuit(QFT(n), np.copy(psi)).state()
+    b = ref.execute_circuit(QFT(n), np.copy(psi)).state()
+    assert a.dtype == b.dtype == np.dtype(dtype)
+    assert np.abs(ours.to_numpy(a) - b).max() < tol(dtype)
+    # zero initial state, and Circuit.__call__ through the global backend
+    import qibo
+
+    qibo.set_backend("qibo_b200")
+    qibo.set_dtype(dtype)
+    c = QFT(n)
+    res = c()
+    assert np.abs(np.asarray(res.state()) - ref.execute_circuit(QFT(n)).state()).max() < tol(dtype)
+    qibo.set_dtype("complex128")
+
+
+def test_config1_qft15_with_shots(backends, golden):
+    """BASELINE config 1 (README example): QFT(15) + M(all), nshots=100, seed 1234: samples bit-exact."""
+    from qibo import gates
+    from qibo.models import QFT
+
+    ours, ref = backends
+    c = QFT(15)
+    c.add(gates.M(*range(15)))
+    ours.set_seed(1234)
+    res = ours.execute_circuit(c, nshots=100)
+    np.testing.assert_array_equal(np.asarray(res.samples(binary=False)), golden["c1_samples"])
+    assert np.abs(np.asarray(res.state())[:64] - golden["c1_state_head"]).max() < 1e-12
+    ours.set_seed(1234)
+    c2 = QFT(15)
+    c2.add(gates.M(*range(15)))
+    freq = ours.execute_circuit(c2, nshots=100).frequencies(binary=False)
+    ref.set_seed(1234)
+    c3 = QFT(15)
+    c3.add(gates.M(*range(15)))
+    assert freq == ref.execute_circuit(c3, nshots=100).frequencies(binary=False)
+
+
+def test_probabilistic_measurement_golden(backends):
+    """tests/test_measurements_probabilistic.py:11-34 (NumPy golden frequencies for seed 1234)."""
+    from qibo import Circuit, gates
+
+    ours, _ = backends
+    ours.set_seed(1234)
+    c = Circuit(2)
+    c.add(gates.H(0))
+    c.add(gates.H(1))
+    c.add(gates.M(0, 1))
+    result = ours.execute_circuit(c, nshots=1000)
+    assert dict(result.frequencies(False)) == {0: 249, 1: 231, 2: 253, 3: 267}
+
+
+@pytest.mark.parametrize("max_qubits", [2, 3, 4, 5])
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_variational_layer_fusion(backends, max_qubits, dtype):
+    """tests/test_models_circuit_fuse.py:101-118 on our backend, and against NumpyBackend."""
+    from qibo import Circuit, gates
+
+    ours, ref = backends
+    ours.set_dtype(dtype)
+    ref.set_dtype(dtype)
+    n, nlayers = 11, 2
+    theta = iter(2 * np.pi * np.random.default_rng(3).random(2 * nlayers * n))
+    c = Circuit(n)
+    for _ in range(nlayers):
+        c.add(gates.RY(i, next(theta)) for i in range(n))
+        c.add(gates.CZ(i, i + 1) for i in range(0, n - 1, 2))
+        c.add(gates.RY(i, next(theta)) for i in range(n))
+        c.add(gates.CZ(i, i + 1) for i in range(1, n - 1, 2))
+        c.add(gates.CZ(0, n - 1))
+    fused = c.fuse(max_qubits=max_qubits)
+    a = ours.to_numpy(ours.execute_circuit(fused).state())
+    b = ours.to_numpy(ours.execute_circuit(c).state())
+    r = ref.execute_circuit(c).state()
+    assert np.abs(a - r).max() < tol(dtype) and np.abs(b - r).max() < tol(dtype)
+    ours.assert_circuitclose(fused, c, atol=10 * tol(dtype))
+
+
+def test_gate_zoo_apply_gate(backends):
+    """tests/test_gates_gates.py style: backend.apply_gate on host arrays, incl. controlled_by and Unitary."""
+    from qibo import gates
+
+    ours, ref = backends
+    n = 6
+    rng = np.random.default_rng(0)
+    u3 = np.linalg.qr(rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)))[0]
+    zoo = [
+        gates.H(0), gates.X(5), gates.Y(2), gates.Z(3), gates.S(1), gates.T(4), gates.SX(0), gates.RX(1, 0.3), gates.RY(2, 0.4),
+        gates.RZ(3, 0.5), gates.U1(0, 0.1), gates.U2(1, 0.1, 0.2), gates.U3(2, 0.1, 0.2, 0.3), gates.GPI2(4, 0.3),
+        gates.CNOT(0, 5), gates.CY(5, 1), gates.CZ(2, 3), gates.CSX(1, 2), gates.CRX(0, 1, 0.2), gates.CRY(4, 2, 0.3), gates.CRZ(1, 5, 0.4),
+        gates.CU1(2, 0, 0.5), gates.CU2(3, 1, 0.1, 0.2), gates.CU3(0, 4, 0.1, 0.2, 0.3), gates.SWAP(0, 5), gates.iSWAP(1, 2),
+        gates.FSWAP(3, 4), gates.fSim(0, 3, 0.2, 0.4), gates.RXX(1, 4, 0.3), gates.RYY(2, 5, 0.3), gates.RZZ(0, 2, 0.3), gates.RZX(3, 5, 0.3),
+        gates.GIVENS(1, 3, 0.4), gates.RBS(0, 4, 0.4), gates.ECR(2, 4), gates.TOFFOLI(0, 1, 2), gates.CCZ(3, 5, 1), gates.DEUTSCH(0, 2, 4, 0.3),
+        gates.Unitary(u3, 4, 0, 2), gates.X(5).controlled_by(0, 1, 2), gates.RY(0, 0.9).controlled_by(4, 1),
+        gates.SWAP(2, 4).controlled_by(0), gates.fSim(5, 1, 0.4, 0.6).controlled_by(3), gates.Unitary(u3, 1, 3, 5).controlled_by(0, 2),
+        gates.GeneralizedfSim(1, 2, np.linalg.qr(rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)))[0], 0.3),
+    ]
+    for g in zoo:
+        psi = rand_state(n, 7)
+        a = ours.apply_gate(g, np.copy(psi), n)
+        b = ref.apply_gate(g, np.copy(psi), n)
+        assert len(a) == 2**n and a.dtype == b.dtype
+        assert np.abs(ours.to_numpy(a) - b).max() < 1e-12, g.name
+
+
+def test_density_matrix_circuit(backends):
+    from qibo import Circuit, gates
+
+    ours, ref = backends
+    c = Circuit(4, density_matrix=True)
+    c.add([gates.H(0), gates.CNOT(0, 1), gates.RY(2, 0.3), gates.CU1(3, 1, 0.5), gates.X(3).controlled_by(0, 2), gates.fSim(1, 2, 0.3, 0.1)])
+    a = ours.execute_circuit(c).state()
+    b = ref.execute_circuit(c).state()
+    assert a.shape == b.shape == (16, 16)
+    assert np.abs(ours.to_numpy(a) - b).max() < 1e-12
+
+
+def test_measurement_ordering_registers_and_collapse(backends):
+    """tests/test_measurements.py:137-156 (qubit order M(1,5,2,0)) and a collapse circuit."""
+    from qibo import Circuit, gates
+
+    ours, ref = backends
+    c = Circuit(6)
+    c.add(gates.X(0))
+    c.add(gates.X(1))
+    c.add(gates.M(1, 5, 2, 0))
+    res = ours.execute_circuit(c, nshots=100)
+    assert res.frequencies() == {"1001": 100}
+    np.testing.assert_array_equal(res.samples(binary=False), 100 * [9])
+    probs_a = np.asarray(res.probabilities([1, 5, 2, 0]))
+    c2 = Circuit(6)
+    c2.add([gates.X(0), gates.X(1)])
+    c2.add(gates.M(1, 5, 2, 0))
+    np.testing.assert_allclose(probs_a, ref.execute_circuit(c2, nshots=100).probabilities([1, 5, 2, 0]), atol=1e-14)
+
+    # mid-circuit collapse: identical RNG stream -> identical outcomes and final frequencies
+    def collapse_circuit():
+        c = Circuit(3)
+        c.add(gates.H(0))
+        c.add(gates.H(1))
+        out = c.add(gates.M(0, collapse=True))
+        c.add(gates.CNOT(0, 2))
+        c.add(gates.M(1, 2))
+        return c
+
+    ours.set_seed(123)
+    fa = ours.execute_circuit(collapse_circuit(), nshots=40).frequencies()
+    ref.set_seed(123)
+    fb = ref.execute_circuit(collapse_circuit(), nshots=40).frequencies()
+    assert fa == fb
+
+
+def test_initial_state_not_clobbered_and_errors(backends):
+    from qibo import Circuit, gates
+    from qibo.models import QFT
+
+    ours, _ = backends
+    psi = rand_state(5, 1)
+    keep = psi.copy()
+    dev = ours.cast(psi)  # host array
+    res = ours.execute_circuit(QFT(5), psi).state()
+    np.testing.assert_array_equal(psi, keep)
+    dstate = ours._to_device(psi)
+    ours.execute_circuit(QFT(5), dstate)
+    np.testing.assert_array_equal(dstate.numpy(), keep)  # device inputs are cloned too
+    with pytest.raises(ValueError):
+        ours.execute_circuit(QFT(5), np.ones(7))
+    assert res.tolist() is not None and len(res) == 32 and res.shape == (32,)
+    # tests/test_models_circuit_execution.py:54-60
+    c = Circuit(40)
+    c.add(gates.H(0))
+    with pytest.raises(RuntimeError):
+        ours.execute_circuit(c)

@@ -1,0 +1,111 @@
+"""CPU checks of the product's planner + canonicaliser + shared-memory passes through tests/emul
+(the same C++ the CUDA kernel runs, compiled for the host), against the oracle."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import tol
+from helpers import ops_from_named, oracle_run, rand_state, random_zoo
+from oracle import numpy_oracle as orc
+from qibo_b200.ops import Op
+import emul
+
+
+@pytest.fixture(params=[None, "2", "3"], ids=["L=default", "L=2", "L=3"])
+def low_bits(request, monkeypatch):
+    if request.param is not None:
+        monkeypatch.setenv("QB_SWEEP_LOW_BITS", request.param)
+    return request.param
+
+
+def test_canonical_forms():
+    CK = dict(NOOP=0, DENSE=1, DIAG=2, PHASE=3, SWAP=4)
+    g = orc.gate_matrix
+    assert emul.canon_kind(4, Op(g("CU1", 0.3), (2, 0))) == (CK["PHASE"], 0, 2)
+    assert emul.canon_kind(4, Op(g("CZ"), (1, 3))) == (CK["PHASE"], 0, 2)
+    assert emul.canon_kind(4, Op(g("Z"), (1,))) == (CK["PHASE"], 0, 1)
+    assert emul.canon_kind(4, Op(g("CNOT"), (1, 3))) == (CK["DENSE"], 1, 1)
+    assert emul.canon_kind(4, Op(g("TOFFOLI"), (1, 3, 0))) == (CK["DENSE"], 1, 2)
+    assert emul.canon_kind(4, Op(g("CCZ"), (1, 3, 0))) == (CK["PHASE"], 0, 3)
+    assert emul.canon_kind(4, Op(g("SWAP"), (1, 3))) == (CK["SWAP"], 2, 0)
+    assert emul.canon_kind(4, Op(g("SWAP"), (1, 3), (0,))) == (CK["SWAP"], 2, 1)
+    assert emul.canon_kind(4, Op(g("RZ", 0.2), (1,))) == (CK["DIAG"], 1, 0)
+    assert emul.canon_kind(4, Op(g("RZZ", 0.2), (1, 2))) == (CK["DIAG"], 2, 0)
+    assert emul.canon_kind(4, Op(g("H"), (1,))) == (CK["DENSE"], 1, 0)
+    assert emul.canon_kind(4, Op(g("fSim", 0.1, 0.2), (1, 0))) == (CK["DENSE"], 2, 0)
+    assert emul.canon_kind(4, Op(g("CRX", 0.1), (1, 0))) == (CK["DENSE"], 1, 1)
+    assert emul.canon_kind(4, Op(np.eye(4), (1, 0))) == (CK["NOOP"], 0, 0)
+    with pytest.raises(ValueError):
+        emul.canon_kind(4, Op(g("CZ"), (1, 1)))
+    with pytest.raises(ValueError):
+        emul.canon_kind(4, Op(g("H"), (4,)))
+
+
+def test_golden_gates_through_emulator(golden, low_bits):
+    for i, c in enumerate(golden.cases("gate_cases")):
+        psi, ref, mat = golden[f"gate{i}_in"], golden[f"gate{i}_out"], golden[f"gate{i}_matrix"]
+        if c["is_controlled_by"]:
+            op = Op(mat, tuple(c["targets"]), tuple(c["controls"]))
+        else:
+            op = Op(mat, tuple(c["qubits"]))
+        for fuse in (True, False):
+            out, _ = emul.apply_program(psi, c["nqubits"], [op], fuse=fuse)
+            assert np.abs(out - ref).max() < tol(c["dtype"]), c["tag"]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 12, 13, 14, 15])
+def test_qft(n, dtype, low_bits):
+    psi = rand_state(n, 100 + n, dtype)
+    ops = ops_from_named(orc.qft_ops(n))
+    ref = orc.run_ops(psi, orc.qft_ops(n), n, dtype=dtype)
+    out, stats = emul.apply_program(psi, n, ops)
+    assert np.abs(out - ref).max() < tol(dtype)
+    assert stats.nops == len(ops) and stats.nsweeps >= 1
+    if n >= 8:
+        assert stats.nsweeps < len(ops) / 4  # several gates per sweep
+    out1, stats1 = emul.apply_program(psi, n, ops, fuse=False)
+    assert np.abs(out1 - ref).max() < tol(dtype)
+    assert stats1.nsweeps == len(ops)
+    # analytic identity: QFT == ifft with ortho norm
+    if dtype == "complex128":
+        assert np.abs(out - np.fft.ifft(psi, norm="ortho")).max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_variational_and_random(dtype, low_bits):
+    n = 14
+    thetas = 2 * np.pi * np.random.default_rng(7).random(2 * 2 * n)
+    named = orc.variational_ops(n, 2, thetas)
+    psi = rand_state(n, 5, dtype)
+    out, stats = emul.apply_program(psi, n, ops_from_named(named))
+    assert np.abs(out - orc.run_ops(psi, named, n, dtype=dtype)).max() < tol(dtype)
+    named = orc.random_ops(n, 60, seed=11)
+    out, stats = emul.apply_program(psi, n, ops_from_named(named))
+    assert np.abs(out - orc.run_ops(psi, named, n, dtype=dtype)).max() < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_zoo(dtype, seed, low_bits):
+    n = 14 if dtype == "complex128" else 15
+    ops = random_zoo(n, 40, seed)
+    psi = rand_state(n, seed, dtype)
+    ref = oracle_run(psi, ops, n)
+    out, stats = emul.apply_program(psi, n, ops)
+    assert np.abs(out - ref).max() < tol(dtype) * (10 if dtype == "complex64" else 1)
+    out, stats = emul.apply_program(psi, n, ops, fuse=False)
+    assert np.abs(out - ref).max() < tol(dtype) * (10 if dtype == "complex64" else 1)
+
+
+def test_fused_reference_queue(golden):
+    """circuit.fuse() output of the reference (dense FusedGate matrices) through the sweep path."""
+    for i, c in enumerate(golden.cases("circ_cases")):
+        if c["queue"] is None:
+            continue
+        psi = golden[f"circ{i}_in"]
+        ops = [Op(golden[f"circ{i}_q{j}"], tuple(q)) for j, q in enumerate(c["queue"])]
+        out, _ = emul.apply_program(psi, c["nqubits"], ops)
+        assert np.abs(out - golden[f"circ{i}_out"]).max() < tol(c["dtype"]), c["tag"]
