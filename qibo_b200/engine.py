@@ -40,7 +40,10 @@ class Engine:
         self.device = torch.device("cuda", self.device_index)
         torch.cuda.set_device(self.device)
         torch.zeros(1, device=self.device)  # make sure the primary context exists before the library attaches
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        # torch's current stream; its default stream reports handle 0, for which the CUDA runtime's explicit
+        # name is cudaStreamLegacy (0x1) -- NULL would ask the library for a private non-blocking stream,
+        # unordered with torch's copies and clones of the same buffers.
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
         handle = ctypes.c_void_p()
         _lib.check(self.lib.qb_create(self.device_index, ctypes.c_void_p(stream), ctypes.byref(handle)))
         self.handle = handle

@@ -189,7 +189,14 @@ def test_probabilities_vs_oracle(eng, n, dtype):
         ref = orc.calculate_probabilities(psi, qubits, n)
         out = eng.probabilities(st, qubits, n).numpy()
         assert out.dtype == ref.dtype
-        assert np.abs(out - ref).max() < (1e-14 if dtype == "complex128" else 2e-6), qubits
+        if dtype == "complex128":
+            assert np.abs(out - ref).max() < 1e-14, qubits
+        else:
+            # the reference accumulates 2^(n-m) float32 terms in float32 (error ~1e-5 at n=20); the kernel accumulates
+            # in double and rounds once, so it is compared with the exactly-accumulated value, and loosely with float32
+            exact = orc.calculate_probabilities(psi.astype(np.complex128), qubits, n)
+            assert np.abs(out - exact).max() < 2e-7, qubits
+            assert np.abs(out - ref).max() < 1e-4, qubits
         assert abs(out.sum() - 1) < 1e-5
 
 
