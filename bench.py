@@ -226,11 +226,14 @@ def run_gpu(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    sweep_ms, nsweeps = 0.0, 0
+    sweep_ms, nsweeps, xch_ms, xch_bytes, nxch = 0.0, 0, 0.0, 0, 0
     for _ in range(args.steps):
         stats = step()
         sweep_ms += stats.elapsed_ms
         nsweeps += stats.nsweeps
+        xch_ms += getattr(stats, "exchange_ms", 0.0)
+        xch_bytes += getattr(stats, "exchange_bytes", 0)
+        nxch += getattr(stats, "nexchanges", 0)
     ev1.record()
     barrier()
     torch.cuda.synchronize()
@@ -241,7 +244,10 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = n_gates(n) * args.steps / (ms / 1e3)
+    # units: one gate applied to one 2^nlocal-amplitude shard; every rank applies every gate of the circuit to its
+    # shard, so N ranks process N * gates units per step (tier rule: "the units all ranks processed / that time")
+    circuit_gates_per_s = n_gates(n) * args.steps / (ms / 1e3)
+    value = world * circuit_gates_per_s
 
     # roofline of the dominant kernel (sweep_kernel): algorithmic bytes per launch = 2 * B * 2^nlocal
     bytes_per_sweep = 2.0 * itemsize * 2.0**nlocal
@@ -293,7 +299,15 @@ def run_gpu(args):
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(nsweeps), "whole_circuit_wall_s": ms_per_step / 1e3,
+            "circuit_gates_per_s": circuit_gates_per_s,
+            "value_definition": "gates applied x shards (N ranks each apply every gate to their 2^nlocal-amplitude shard) per second; equals circuit gates/s at N=1",
         }
+        if world > 1:
+            line["exchange"] = {
+                "count_per_step": nxch // args.steps, "ms_per_step_rank0": xch_ms / args.steps,
+                "GBps_per_direction_rank0": (xch_bytes / 2) / max(xch_ms, 1e-9) / 1e6,
+                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": "NCCL send/recv over NVLink, half-shard pairwise",
+            }
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

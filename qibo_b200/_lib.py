@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libqibo_b200.so")
+LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(HERE, "lib", "libqibo_b200.so")
 
 QB_C64, QB_C128 = 0, 1
 QB_F32, QB_F64 = 0, 1

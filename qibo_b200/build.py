@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libqibo_b200.so")
+# experiment variants: QB_BUILD_DEFS="-DQB_COMPUTE_THREADS=512" QB_BUILD_SUFFIX=_ct512 python -m qibo_b200.build --force
 SOURCES = [os.path.join(CSRC, "qb_api.cu")]
 
 
@@ -30,6 +31,10 @@ def needs_build():
 
 
 def build(force=False, verbose=True):
+    global LIB
+    suffix = os.environ.get("QB_BUILD_SUFFIX", "")
+    if suffix:
+        LIB = LIB.replace(".so", suffix + ".so")
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -41,7 +46,7 @@ def build(force=False, verbose=True):
         "-Xptxas", "-v" if os.environ.get("QB_PTXAS_V") else "-O3",
         "--expt-relaxed-constexpr",
         "-shared", "-o", LIB,
-    ] + SOURCES
+    ] + os.environ.get("QB_BUILD_DEFS", "").split() + SOURCES
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

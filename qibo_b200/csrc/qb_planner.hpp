@@ -22,43 +22,81 @@
 
 namespace qb {
 
-// ---- device program layout (shared with qb_sweep.cuh) ---------------------------------------------
-enum DevOpType { OP_DENSE = 1, OP_SWAP = 2, OP_FAN = 3, OP_DIAGK = 4, OP_DENSE_BIG = 5 };
+// ---- device program layout (shared with qb_passes.cuh / qb_sweep.cuh) --------------------------------
+// A sweep is a list of PASSES over the shared-memory tile.  A REGTILE pass fixes R tile-local "register
+// bits": every thread owns groups of 2^R amplitudes that differ only in those bits, loads them once,
+// applies the pass's whole list of MICRO-OPS in registers and stores them once.  A BIG pass applies one
+// dense gate on 3..6 targets (threads share a group, inputs re-read from shared memory).
+enum MicroType { MU_DENSE1 = 1, MU_DENSE2 = 2, MU_SWAP = 3, MU_FAN = 4, MU_DIAGK = 5 };
+enum PassKind { PASS_REGTILE = 1, PASS_BIG = 2 };
 
-constexpr int SWEEP_MAX_OPS = 48;
-constexpr int SWEEP_BLOB_MAX = 30 * 1024;  // program bytes resident in shared memory next to the tiles
+constexpr int SWEEP_MAX_SLOTS = 96;        // micro-ops (+ big ops) per sweep that need per-tile set-up
+constexpr int SWEEP_BLOB_MAX = 29 * 1024;  // program bytes resident in shared memory next to the tiles
 constexpr int SWEEP_TILE_BYTES_LOG2 = 16;  // 64 KiB tiles, three in flight per SM
+constexpr int MU_REAL = 1;                 // flags: the 2x2 / 4x4 matrix is real
 
-struct DevOp {
-  uint32_t type;
-  uint32_t k;          // number of target bits
-  uint32_t nins;       // DENSE/SWAP: tile-local bits to insert (targets + tile-local controls), sorted in ins[]
-  uint32_t tl_cmask;   // controls inside the tile (tile-local bit mask)
-  uint64_t ext_cmask;  // controls outside the tile (state bit positions)
-  uint32_t payload;    // byte offset inside the blob of the matrix / tables
-  uint32_t n_ext;      // FAN: number of ext tables
-  uint8_t tbit[8];     // tile-local bit of target i (tbit[0] = MSB of the matrix index); 0xFF = outside the tile (DIAGK)
-  uint8_t ins[16];
-  uint8_t chunk_lo[4];   // FAN: tile-local chunk c covers bits [chunk_lo[c], chunk_lo[c] + chunk_len[c])
-  uint8_t chunk_len[4];
-  uint32_t n_chunks;
-  uint32_t ins_mask;     // DENSE/SWAP: the same insert positions as a tile-local bit mask
-  uint64_t ext_mask[6];  // FAN: state-bit mask of ext table e; DIAGK: single-bit mask of ext target i
+struct MicroOp {
+  // ---- hot header: one 16-byte shared-memory load decodes the op ------------------------------------
+  uint8_t type;          // MicroType
+  uint8_t rb0, rb1;      // register-bit indices: DENSE1 target; DENSE2/SWAP (matrix MSB, LSB)
+  uint8_t flags;         // MU_REAL
+  uint32_t creg;         // controls that are register bits (mask over the register index j)
+  uint32_t cthr;         // controls inside the tile but outside R (tile-local mask, tested on the group base)
+  uint32_t active;       // PER TILE (written by the set-up phase): controls outside the tile are all 1
+  // ---- second 16 bytes ---------------------------------------------------------------------------------
+  uint16_t la;           // FAN: TA is indexed by the low `la` bits of the group index, TB by the rest
+  uint16_t R;            // register bits of the pass this op belongs to (table layout)
+  uint32_t k;            // DIAGK: number of target bits
+  uint32_t payload;      // byte offset in the blob: DENSE2 matrix | FAN: TA, TB, G, ext tables | DIAGK: table
+  uint32_t aux;          // PER TILE: DIAGK table-index part from the bits outside the tile
+  // ---- inline data -------------------------------------------------------------------------------------
+  double inl[8];         // DENSE1: the 2x2 matrix in the state's precision (4 x C); FAN: inl[0..1] hold the
+                         // PER TILE factor from the bits outside the tile (a C)
+  // ---- cold part -----------------------------------------------------------------------------------------
+  uint64_t ext_cmask;    // controls outside the tile (state bit positions)
+  uint32_t n_ext;        // FAN: number of ext tables
+  uint32_t slot;
+  uint8_t tbit[8];       // DIAGK: tile-local bit of target i if it is outside R, else 0xFF
+  uint8_t rsel[8];       // DIAGK: register-bit index of target i if it is in R, else 0xFF
+  uint64_t ext_mask[6];  // FAN: state-bit mask of ext table e; DIAGK: state-bit mask of target i when outside the tile
   double scalar[2];      // FAN: global factor
+};
+static_assert(sizeof(MicroOp) % 16 == 0, "MicroOp must stay 16-byte aligned");
+
+struct DevOp {           // BIG pass: one dense gate on k = 3..6 tile-local targets
+  uint32_t k;
+  uint32_t nins;         // tile-local bits to insert (targets + tile-local controls)
+  uint32_t ins_mask;
+  uint32_t tl_cmask;     // controls inside the tile
+  uint64_t ext_cmask;    // controls outside the tile
+  uint32_t payload;      // matrix
+  uint32_t slot;
+  uint8_t tbit[8];       // tile-local bit of target i (tbit[0] = MSB of the matrix index)
   uint64_t pad2;
 };
 static_assert(sizeof(DevOp) % 16 == 0, "DevOp must stay 16-byte aligned");
 
+struct PassHeader {
+  uint32_t kind;
+  uint32_t rmask;        // REGTILE: tile-local mask of the R register bits
+  uint16_t nmicro;
+  uint16_t R;            // REGTILE: number of register bits of this pass
+  uint32_t offset;       // byte offset of MicroOp[0] (REGTILE) or of the DevOp (BIG)
+};
+
 struct SweepHeader {
-  uint32_t nops;
+  uint32_t npasses;
   uint32_t T;           // log2(amplitudes per tile)
   uint32_t L;           // log2(amplitudes per contiguous run)
   uint32_t blob_bytes;
   uint64_t tile_mask;   // state bits spanned by the tile
   uint64_t other_mask;  // remaining state bits (enumerated by the tile index)
   uint64_t ntiles;
-  uint32_t ops_offset;  // byte offset of DevOp[0]
-  uint32_t pad[5];
+  uint32_t passes_offset;  // byte offset of PassHeader[0]
+  uint32_t nslots;
+  uint32_t R;              // register bits of the REGTILE passes
+  uint32_t slots_offset;   // uint32[nslots]: byte offset of the slot's MicroOp, or of its DevOp with bit 31 set
+  uint32_t pad[2];
 };
 static_assert(sizeof(SweepHeader) % 16 == 0, "SweepHeader must stay 16-byte aligned");
 
@@ -191,7 +229,7 @@ inline void merge_ops(const std::vector<CanonOp>& ops, bool no_fuse, std::vector
   }
 }
 
-// ---- step 2 + 3: pack into sweeps and serialise --------------------------------------------------------
+// ---- step 2 + 3: pack into sweeps, split sweeps into passes, serialise ------------------------------
 template <typename C> inline C to_dev(cd v);
 struct f2 { float x, y; };
 struct d2 { double x, y; };
@@ -200,145 +238,242 @@ template <> inline d2 to_dev<d2>(cd v) { return d2{v.real(), v.imag()}; }
 
 inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-template <typename C> struct BlobBuilder {
-  std::vector<char> bytes;
-  std::vector<DevOp> ops;
-  std::vector<std::vector<C>> payloads;
-  size_t payload_bytes = 0;
-  size_t size_with(size_t extra_ops, size_t extra_payload) const {
-    return sizeof(SweepHeader) + (ops.size() + extra_ops) * sizeof(DevOp) + payload_bytes + extra_payload;
-  }
-};
+inline int regtile_bits_for(int dtype) { (void)dtype; return env_int("QB_REGTILE_BITS", 4); }
 
-// bytes of payload a PlanOp needs for a given tile (upper bound, independent of the tile)
-inline size_t payload_estimate(const PlanOp& p, int csize, int T) {
+// upper bound of the blob bytes a PlanOp needs (independent of the tile)
+inline size_t blob_estimate(const PlanOp& p, int csize, int T, int R) {
   switch (p.kind) {
-    case CK_DENSE: return align16((size_t)p.data.size() * csize);
-    case CK_SWAP: return 0;
-    case CK_DIAG: return align16((size_t)p.data.size() * csize);
-    default: {  // fan: two local chunk tables + ext tables of <= 5 bits
-      size_t local = ((size_t(1) << ((T + 1) / 2)) + (size_t(1) << (T / 2))) * csize;
+    case CK_DENSE:
+      return (p.tpos.size() <= 2 ? sizeof(MicroOp) : sizeof(DevOp) + sizeof(PassHeader)) + align16(p.data.size() * csize);
+    case CK_SWAP: return sizeof(MicroOp);
+    case CK_DIAG: return sizeof(MicroOp) + align16(p.data.size() * csize);
+    default: {  // fan: TA + TB + G + ext tables of <= 5 bits
+      int gb = T - R > 0 ? T - R : 0;
+      int la = gb < 5 ? gb : 5;
+      size_t local = (size_t(1) << la) + (size_t(1) << (gb - la)) + (size_t(1) << R);
       size_t next = (p.fan.size() + 4) / 5;
-      return align16(local + next * 32 * csize);
+      return sizeof(MicroOp) + align16((local + next * 32) * csize);
     }
   }
 }
 
-template <typename C>
-inline bool emit_op(const PlanOp& p, uint64_t tile_mask, int T, const std::vector<int>& local_of_pos, BlobBuilder<C>& bb,
-                    std::string& err) {
-  DevOp d;
-  memset(&d, 0, sizeof(d));
-  memset(d.tbit, 0xFF, sizeof(d.tbit));
-  uint64_t cm = 0;
-  for (int c : p.cpos) cm |= uint64_t(1) << c;
-  d.ext_cmask = cm & ~tile_mask;
-  for (int c : p.cpos)
-    if ((tile_mask >> c) & 1) d.tl_cmask |= 1u << local_of_pos[c];
-  std::vector<C> payload;
-  if (p.kind == CK_DENSE || p.kind == CK_SWAP) {
-    int k = (int)p.tpos.size();
-    d.k = k;
-    d.type = p.kind == CK_SWAP ? OP_SWAP : (k <= 2 ? OP_DENSE : OP_DENSE_BIG);
-    std::vector<int> ins;
-    for (int i = 0; i < k; ++i) {
-      if (!((tile_mask >> p.tpos[i]) & 1)) { err = "internal: dense target outside tile"; return false; }
-      d.tbit[i] = (uint8_t)local_of_pos[p.tpos[i]];
-      ins.push_back(local_of_pos[p.tpos[i]]);
-    }
-    for (int c : p.cpos)
-      if ((tile_mask >> c) & 1) ins.push_back(local_of_pos[c]);
-    std::sort(ins.begin(), ins.end());
-    if (ins.size() > 16) { err = "too many tile-local controls"; return false; }
-    d.nins = (uint32_t)ins.size();
-    for (size_t i = 0; i < ins.size(); ++i) {
-      d.ins[i] = (uint8_t)ins[i];
-      d.ins_mask |= 1u << ins[i];
-    }
-    if (p.kind == CK_DENSE)
-      for (auto& v : p.data) payload.push_back(to_dev<C>(v));
-  } else if (p.kind == CK_DIAG) {
-    int k = (int)p.tpos.size();
-    d.type = OP_DIAGK;
-    d.k = k;
-    for (int i = 0; i < k; ++i) {
-      if ((tile_mask >> p.tpos[i]) & 1) d.tbit[i] = (uint8_t)local_of_pos[p.tpos[i]];
-      else d.ext_mask[i] = uint64_t(1) << p.tpos[i];
-    }
-    for (auto& v : p.data) payload.push_back(to_dev<C>(v));
-  } else {  // fan
-    d.type = OP_FAN;
-    d.scalar[0] = p.scalar.real();
-    d.scalar[1] = p.scalar.imag();
-    // local chunks: two contiguous ranges of tile-local bits
-    int len0 = (T + 1) / 2, len1 = T - len0;
-    int los[2] = {0, len0}, lens[2] = {len0, len1};
-    d.n_chunks = 0;
-    for (int c = 0; c < 2; ++c) {
-      if (lens[c] == 0) continue;
-      bool any = false;
-      for (auto& kv : p.fan)
-        if (((tile_mask >> kv.first) & 1) && local_of_pos[kv.first] >= los[c] && local_of_pos[kv.first] < los[c] + lens[c]) any = true;
-      if (!any) continue;
-      int ci = d.n_chunks++;
-      d.chunk_lo[ci] = (uint8_t)los[c];
-      d.chunk_len[ci] = (uint8_t)lens[c];
-      for (int v = 0; v < (1 << lens[c]); ++v) {
-        cd f(1.0, 0.0);
-        for (auto& kv : p.fan) {
-          if (!((tile_mask >> kv.first) & 1)) continue;
-          int lb = local_of_pos[kv.first];
-          if (lb < los[c] || lb >= los[c] + lens[c]) continue;
-          f *= ((v >> (lb - los[c])) & 1) ? kv.second.second : kv.second.first;
-        }
-        payload.push_back(to_dev<C>(f));
-      }
-    }
-    // ext tables: groups of <= 5 outside bits
-    std::vector<int> ext;
-    for (auto& kv : p.fan)
-      if (!((tile_mask >> kv.first) & 1)) ext.push_back(kv.first);
-    d.n_ext = 0;
-    for (size_t s = 0; s < ext.size(); s += 5) {
-      size_t e = std::min(ext.size(), s + 5);
-      if (d.n_ext >= 6) { err = "internal: too many ext tables"; return false; }
-      uint64_t mask = 0;
-      for (size_t i = s; i < e; ++i) mask |= uint64_t(1) << ext[i];
-      d.ext_mask[d.n_ext++] = mask;
-      int nb = (int)(e - s);
-      for (int v = 0; v < (1 << nb); ++v) {  // ext[] ascending == extract() order
-        cd f(1.0, 0.0);
-        for (int i = 0; i < nb; ++i) {
-          auto& pr = p.fan.at(ext[s + i]);
-          f *= ((v >> i) & 1) ? pr.second : pr.first;
-        }
-        payload.push_back(to_dev<C>(f));
-      }
-    }
-  }
-  bb.ops.push_back(d);
-  bb.payload_bytes += align16(payload.size() * sizeof(C));
-  bb.payloads.push_back(std::move(payload));
+template <typename C> struct SweepBuilder {
+  int T = 0, R = 0;
+  uint64_t tile_mask = 0;
+  std::vector<int> local_of_pos;  // state bit position -> tile-local bit
+  std::vector<PassHeader> passes;
+  std::vector<std::vector<MicroOp>> micro;   // per pass (empty for BIG)
+  std::vector<DevOp> big;                    // per pass (valid for BIG)
+  std::vector<std::vector<C>> payloads;      // one per slot
+  std::vector<std::pair<int, int>> slot_owner;  // slot -> (pass, micro index or -1)
+};
+
+inline bool is_real_matrix(const std::vector<cd>& m) {
+  for (auto& v : m)
+    if (v.imag() != 0.0) return false;
   return true;
 }
 
-template <typename C> inline void finish_blob(BlobBuilder<C>& bb, SweepHeader& hdr, std::vector<char>& out, SweepDesc& sd) {
-  size_t off = sizeof(SweepHeader);
-  hdr.ops_offset = (uint32_t)off;
-  off += bb.ops.size() * sizeof(DevOp);
-  for (size_t i = 0; i < bb.ops.size(); ++i) {
-    bb.ops[i].payload = (uint32_t)off;
-    off += align16(bb.payloads[i].size() * sizeof(C));
+// Emits the micro-ops of one REGTILE pass given its final register-bit mask.
+template <typename C>
+inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanOp*>& ops, uint32_t rmask, std::string& err) {
+  const int T = sb.T, R = __builtin_popcount(rmask);
+  std::vector<int> rbit_of_local(32, -1), gbit_of_local(32, -1);
+  {
+    int r = 0, g = 0;
+    for (int lb = 0; lb < T; ++lb) {
+      if ((rmask >> lb) & 1) rbit_of_local[lb] = r++;
+      else gbit_of_local[lb] = g++;
+    }
   }
-  hdr.nops = (uint32_t)bb.ops.size();
+  const int gb = T - R;
+  const int la = gb < 5 ? gb : 5;
+  PassHeader ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.kind = PASS_REGTILE;
+  ph.rmask = rmask;
+  ph.R = (uint16_t)R;
+  std::vector<MicroOp> mops;
+  const int pass_index = (int)sb.passes.size();
+  for (const PlanOp* pp : ops) {
+    const PlanOp& p = *pp;
+    MicroOp m;
+    memset(&m, 0, sizeof(m));
+    memset(m.tbit, 0xFF, sizeof(m.tbit));
+    memset(m.rsel, 0xFF, sizeof(m.rsel));
+    m.R = (uint16_t)R;
+    for (int c : p.cpos) {
+      if (!((sb.tile_mask >> c) & 1)) m.ext_cmask |= uint64_t(1) << c;
+      else if (rbit_of_local[sb.local_of_pos[c]] >= 0) m.creg |= 1u << rbit_of_local[sb.local_of_pos[c]];
+      else m.cthr |= 1u << sb.local_of_pos[c];
+    }
+    std::vector<C> payload;
+    if (p.kind == CK_DENSE || p.kind == CK_SWAP) {
+      int k = (int)p.tpos.size();
+      int rb[2] = {0, 0};
+      for (int i = 0; i < k; ++i) {
+        int lb = sb.local_of_pos[p.tpos[i]];
+        if (lb < 0 || rbit_of_local[lb] < 0) { err = "internal: dense target is not a register bit"; return false; }
+        rb[i] = rbit_of_local[lb];
+      }
+      m.rb0 = (uint8_t)rb[0];
+      m.rb1 = (uint8_t)rb[1];
+      if (p.kind == CK_SWAP) {
+        m.type = MU_SWAP;
+      } else {
+        m.type = k == 1 ? MU_DENSE1 : MU_DENSE2;
+        if (is_real_matrix(p.data)) m.flags |= MU_REAL;
+        if (k == 1) {  // inline 2x2
+          C* inl = reinterpret_cast<C*>(m.inl);
+          for (int e = 0; e < 4; ++e) inl[e] = to_dev<C>(p.data[e]);
+        } else {
+          for (auto& v : p.data) payload.push_back(to_dev<C>(v));
+        }
+      }
+    } else if (p.kind == CK_DIAG) {
+      m.type = MU_DIAGK;
+      int k = (int)p.tpos.size();
+      m.k = k;
+      for (int i = 0; i < k; ++i) {
+        int pos = p.tpos[i];
+        if (!((sb.tile_mask >> pos) & 1)) m.ext_mask[i] = uint64_t(1) << pos;
+        else if (rbit_of_local[sb.local_of_pos[pos]] >= 0) m.rsel[i] = (uint8_t)rbit_of_local[sb.local_of_pos[pos]];
+        else m.tbit[i] = (uint8_t)sb.local_of_pos[pos];
+      }
+      for (auto& v : p.data) payload.push_back(to_dev<C>(v));
+    } else {  // fan
+      m.type = MU_FAN;
+      m.scalar[0] = p.scalar.real();
+      m.scalar[1] = p.scalar.imag();
+      m.la = (uint16_t)la;
+      auto factor = [&](int pos, int bitval) { auto& pr = p.fan.at(pos); return bitval ? pr.second : pr.first; };
+      // TA / TB over the group-index bits, G over the register bits
+      for (int part = 0; part < 3; ++part) {
+        int nb = part == 0 ? la : part == 1 ? gb - la : R;
+        for (int v = 0; v < (1 << nb); ++v) {
+          cd f(1.0, 0.0);
+          for (auto& kv : p.fan) {
+            if (!((sb.tile_mask >> kv.first) & 1)) continue;
+            int lb = sb.local_of_pos[kv.first];
+            int idx;
+            if (part == 2) {
+              idx = rbit_of_local[lb];
+              if (idx < 0) continue;
+            } else {
+              int g = gbit_of_local[lb];
+              if (g < 0) continue;
+              if (part == 0 ? g >= la : g < la) continue;
+              idx = part == 0 ? g : g - la;
+            }
+            f *= factor(kv.first, (v >> idx) & 1);
+          }
+          payload.push_back(to_dev<C>(f));
+        }
+      }
+      std::vector<int> ext;
+      for (auto& kv : p.fan)
+        if (!((sb.tile_mask >> kv.first) & 1)) ext.push_back(kv.first);
+      for (size_t s = 0; s < ext.size(); s += 5) {
+        size_t e = std::min(ext.size(), s + 5);
+        if (m.n_ext >= 6) { err = "internal: too many ext tables"; return false; }
+        uint64_t mask = 0;
+        for (size_t i = s; i < e; ++i) mask |= uint64_t(1) << ext[i];
+        m.ext_mask[m.n_ext++] = mask;
+        int nb = (int)(e - s);
+        for (int v = 0; v < (1 << nb); ++v) {  // ext[] ascending == extract() order
+          cd f(1.0, 0.0);
+          for (int i = 0; i < nb; ++i) f *= factor(ext[s + i], (v >> i) & 1);
+          payload.push_back(to_dev<C>(f));
+        }
+      }
+    }
+    m.slot = (uint32_t)sb.payloads.size();
+    sb.slot_owner.push_back({pass_index, (int)mops.size()});
+    sb.payloads.push_back(std::move(payload));
+    mops.push_back(m);
+  }
+  ph.nmicro = (uint16_t)mops.size();
+  sb.passes.push_back(ph);
+  sb.micro.push_back(std::move(mops));
+  sb.big.push_back(DevOp());
+  return true;
+}
+
+template <typename C> inline bool emit_big_pass(SweepBuilder<C>& sb, const PlanOp& p, std::string& err) {
+  DevOp d;
+  memset(&d, 0, sizeof(d));
+  memset(d.tbit, 0xFF, sizeof(d.tbit));
+  int k = (int)p.tpos.size();
+  d.k = k;
+  std::vector<int> ins;
+  for (int i = 0; i < k; ++i) {
+    if (!((sb.tile_mask >> p.tpos[i]) & 1)) { err = "internal: dense target outside tile"; return false; }
+    d.tbit[i] = (uint8_t)sb.local_of_pos[p.tpos[i]];
+    ins.push_back(sb.local_of_pos[p.tpos[i]]);
+  }
+  for (int c : p.cpos) {
+    if ((sb.tile_mask >> c) & 1) {
+      d.tl_cmask |= 1u << sb.local_of_pos[c];
+      ins.push_back(sb.local_of_pos[c]);
+    } else {
+      d.ext_cmask |= uint64_t(1) << c;
+    }
+  }
+  d.nins = (uint32_t)ins.size();
+  for (int b : ins) d.ins_mask |= 1u << b;
+  std::vector<C> payload;
+  for (auto& v : p.data) payload.push_back(to_dev<C>(v));
+  d.slot = (uint32_t)sb.payloads.size();
+  PassHeader ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.kind = PASS_BIG;
+  sb.slot_owner.push_back({(int)sb.passes.size(), -1});
+  sb.payloads.push_back(std::move(payload));
+  sb.passes.push_back(ph);
+  sb.micro.push_back({});
+  sb.big.push_back(d);
+  return true;
+}
+
+template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& hdr, std::vector<char>& out, SweepDesc& sd) {
+  size_t off = sizeof(SweepHeader);
+  hdr.passes_offset = (uint32_t)off;
+  off += align16(sb.passes.size() * sizeof(PassHeader));
+  for (size_t p = 0; p < sb.passes.size(); ++p) {
+    sb.passes[p].offset = (uint32_t)off;
+    off += sb.passes[p].kind == PASS_BIG ? sizeof(DevOp) : sb.micro[p].size() * sizeof(MicroOp);
+  }
+  hdr.slots_offset = (uint32_t)off;
+  off += align16(sb.payloads.size() * sizeof(uint32_t));
+  for (size_t s = 0; s < sb.payloads.size(); ++s) {
+    auto own = sb.slot_owner[s];
+    if (own.second < 0) sb.big[own.first].payload = (uint32_t)off;
+    else sb.micro[own.first][own.second].payload = (uint32_t)off;
+    off += align16(sb.payloads[s].size() * sizeof(C));
+  }
+  hdr.npasses = (uint32_t)sb.passes.size();
+  hdr.nslots = (uint32_t)sb.payloads.size();
   hdr.blob_bytes = (uint32_t)off;
   size_t start = align16(out.size());
   out.resize(start + off, 0);
   char* base = out.data() + start;
   memcpy(base, &hdr, sizeof(hdr));
-  memcpy(base + hdr.ops_offset, bb.ops.data(), bb.ops.size() * sizeof(DevOp));
-  for (size_t i = 0; i < bb.ops.size(); ++i)
-    if (!bb.payloads[i].empty()) memcpy(base + bb.ops[i].payload, bb.payloads[i].data(), bb.payloads[i].size() * sizeof(C));
+  memcpy(base + hdr.passes_offset, sb.passes.data(), sb.passes.size() * sizeof(PassHeader));
+  for (size_t p = 0; p < sb.passes.size(); ++p) {
+    if (sb.passes[p].kind == PASS_BIG) memcpy(base + sb.passes[p].offset, &sb.big[p], sizeof(DevOp));
+    else if (!sb.micro[p].empty()) memcpy(base + sb.passes[p].offset, sb.micro[p].data(), sb.micro[p].size() * sizeof(MicroOp));
+  }
+  for (size_t s = 0; s < sb.payloads.size(); ++s) {
+    auto own = sb.slot_owner[s];
+    uint32_t so = own.second < 0 ? (sb.passes[own.first].offset | 0x80000000u)
+                                 : sb.passes[own.first].offset + (uint32_t)(own.second * sizeof(MicroOp));
+    memcpy(base + hdr.slots_offset + s * sizeof(uint32_t), &so, sizeof(uint32_t));
+  }
+  for (size_t s = 0; s < sb.payloads.size(); ++s) {
+    auto own = sb.slot_owner[s];
+    uint32_t po = own.second < 0 ? sb.big[own.first].payload : sb.micro[own.first][own.second].payload;
+    if (!sb.payloads[s].empty()) memcpy(base + po, sb.payloads[s].data(), sb.payloads[s].size() * sizeof(C));
+  }
   sd.blob_offset = start;
   sd.blob_bytes = off;
 }
@@ -350,8 +485,12 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
   int Lcfg = env_int("QB_SWEEP_LOW_BITS", dtype == QB_C128 ? 5 : 6);
   if (Lcfg > T) Lcfg = T;
   if (Lcfg < 1) Lcfg = 1;
+  if (T - Lcfg > 8) Lcfg = T - 8;
+  int R = regtile_bits_for(dtype);
+  if (R > T) R = T;
+  if (R < 1) R = 1;
   const int free_high = T - Lcfg;
-  const int max_passes = no_fuse ? 1 : env_int("QB_SWEEP_MAX_PASSES", 6);
+  const int max_ops = no_fuse ? 1 : env_int("QB_SWEEP_MAX_OPS", SWEEP_MAX_SLOTS);
   const uint64_t all = (uint64_t(1) << n) - 1;
   const uint64_t lowmask = (uint64_t(1) << Lcfg) - 1;
   const int csize = (int)sizeof(C);
@@ -361,8 +500,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     // ---- greedy: take ops while their dense targets fit the tile
     uint64_t high = 0;
     size_t j = i;
-    int passes = 0;
-    size_t est = sizeof(SweepHeader);
+    size_t est = sizeof(SweepHeader) + 64;
     while (j < pops.size()) {
       const PlanOp& p = pops[j];
       uint64_t need = 0;
@@ -374,22 +512,25 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
         if (j == i) { err = "gate has more target qubits outside the low bits than a tile can hold"; return false; }
         break;
       }
-      size_t add = sizeof(DevOp) + payload_estimate(p, csize, T);
-      if (j > i && (est + add > (size_t)SWEEP_BLOB_MAX || passes + 1 > max_passes || (int)(j - i) >= SWEEP_MAX_OPS)) break;
+      size_t add = blob_estimate(p, csize, T, R) + sizeof(PassHeader);
+      if (j > i && (est + add > (size_t)SWEEP_BLOB_MAX || (int)(j - i) >= max_ops)) break;
       if (est + add > (size_t)SWEEP_BLOB_MAX) { err = "single gate does not fit the sweep program buffer"; return false; }
       high = nh;
       est += add;
-      ++passes;
       ++j;
     }
     // ---- complete the tile with the lowest unused bits (longest contiguous runs)
     uint64_t tile_mask = lowmask | high;
     for (int b = 0; b < n && __builtin_popcountll(tile_mask) < T; ++b) tile_mask |= uint64_t(1) << b;
-    std::vector<int> local_of_pos(64, -1);
+    SweepBuilder<C> sb;
+    sb.T = T;
+    sb.R = R;
+    sb.tile_mask = tile_mask;
+    sb.local_of_pos.assign(64, -1);
     {
       int lb = 0;
       for (int b = 0; b < n; ++b)
-        if ((tile_mask >> b) & 1) local_of_pos[b] = lb++;
+        if ((tile_mask >> b) & 1) sb.local_of_pos[b] = lb++;
     }
     int L = 0;
     while (L < n && ((tile_mask >> L) & 1)) ++L;
@@ -397,23 +538,58 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     memset(&hdr, 0, sizeof(hdr));
     hdr.T = T;
     hdr.L = L;
+    hdr.R = R;
     hdr.tile_mask = tile_mask;
     hdr.other_mask = all & ~tile_mask;
     hdr.ntiles = uint64_t(1) << (n - T);
-    BlobBuilder<C> bb;
     SweepDesc sd;
     sd.T = T;
     sd.L = L;
     sd.tile_mask = tile_mask;
     sd.ntiles = hdr.ntiles;
+
+    // ---- split the sweep's ops into passes: a REGTILE pass holds ops whose dense targets fit R register bits
+    std::vector<const PlanOp*> cur;
+    uint32_t cur_r = 0;  // tile-local mask of the register bits demanded so far
+    auto close_pass = [&]() -> bool {
+      if (cur.empty()) return true;
+      // pad the register set to Rp bits, preferring high tile-local bits (keeps lanes on the low bits: no bank
+      // conflicts).  complex128 passes that need <= 3 register bits run with R = 3 and two groups in flight.
+      int Rp = R;
+      if (sizeof(C) == 16 && R > 3 && __builtin_popcount(cur_r) <= 3) Rp = 3;
+      uint32_t rmask = cur_r;
+      for (int lb = T - 1; lb >= 0 && __builtin_popcount(rmask) < Rp; --lb)
+        if (!((rmask >> lb) & 1)) rmask |= 1u << lb;
+      bool ok = emit_regtile_pass<C>(sb, cur, rmask, err);
+      cur.clear();
+      cur_r = 0;
+      return ok;
+    };
     for (size_t q = i; q < j; ++q) {
-      if (!emit_op<C>(pops[q], tile_mask, T, local_of_pos, bb, err)) return false;
-      if (pops[q].kind == CK_DENSE || pops[q].kind == CK_SWAP) ++sd.npasses;
-      else ++sd.ndiag;
-      for (int s : pops[q].src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
+      const PlanOp& p = pops[q];
+      for (int s : p.src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
+      if (p.kind == CK_DENSE && p.tpos.size() > 2) {
+        if (!close_pass()) return false;
+        if (!emit_big_pass<C>(sb, p, err)) return false;
+        ++sd.npasses;
+        continue;
+      }
+      uint32_t need = 0;
+      if (p.kind == CK_DENSE || p.kind == CK_SWAP)
+        for (int t : p.tpos) need |= 1u << sb.local_of_pos[t];
+      if (__builtin_popcount(cur_r | need) > R) {
+        if (!close_pass()) return false;
+      }
+      if (__builtin_popcount(need) > R) { err = "internal: gate needs more register bits than a pass has"; return false; }
+      if (cur.empty()) ++sd.npasses;
+      cur_r |= need;
+      cur.push_back(&p);
+      if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
     }
-    finish_blob<C>(bb, hdr, plan.blob, sd);
-    if (sd.blob_bytes > (size_t)SWEEP_BLOB_MAX + 2048) { err = "internal: sweep program too large"; return false; }
+    if (!close_pass()) return false;
+    if ((int)sb.payloads.size() > SWEEP_MAX_SLOTS) { err = "internal: too many ops in one sweep"; return false; }
+    finish_blob<C>(sb, hdr, plan.blob, sd);
+    if (sd.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
     plan.npasses += sd.npasses;
     plan.ndiag += sd.ndiag;
     plan.sweeps.push_back(sd);

@@ -2,7 +2,7 @@
 //
 // One persistent CTA per SM.  Warp 0 (LOADER) and warp 1 (STORER) move tiles between HBM and shared
 // memory with bulk-async copies (cp.async.bulk, the TMA engine; SASS UBLKCP) -- one copy per contiguous
-// run of the tile -- tracked by mbarriers (loads: complete_tx; stores: bulk groups).  Warps 2..15 are
+// run of the tile -- tracked by mbarriers (loads: complete_tx; stores: bulk groups).  Warps 2..9 are
 // COMPUTE warps: they apply every gate of the sweep to the resident tile in shared memory.  Three 64 KiB tiles rotate
 // through the states LOADING -> COMPUTING -> STORING, so HBM reads, shared-memory math and HBM writes of
 // three consecutive tiles overlap.  HBM traffic per sweep: 2 * B * 2^n regardless of how many gates ride.
@@ -20,12 +20,15 @@ namespace qb {
 
 constexpr int SW_NBUF = 3;
 constexpr int SW_TILE_BYTES = 1 << SWEEP_TILE_BYTES_LOG2;
-constexpr int SW_COMPUTE_THREADS = 448;  // 14 warps; 16 warps per CTA in total -> 128 registers per thread
+#ifndef QB_COMPUTE_THREADS
+#define QB_COMPUTE_THREADS 256  // 8 warps x 2 groups in flight per thread = the 512 groups of a 64 KiB tile
+#endif
+constexpr int SW_COMPUTE_THREADS = QB_COMPUTE_THREADS;
 constexpr int SW_COPY_THREADS = 64;  // warp 0: loader, warp 1: storer
 constexpr int SW_THREADS = SW_COMPUTE_THREADS + SW_COPY_THREADS;
-constexpr int SW_BLOB_REGION = 31 * 1024;
+constexpr int SW_BLOB_REGION = 30 * 1024;
 constexpr int SW_MAX_RUNS = 256;
-constexpr int SW_SMEM_BYTES = SW_NBUF * SW_TILE_BYTES + SW_BLOB_REGION + SW_MAX_RUNS * 8 + SWEEP_MAX_OPS * (16 + 4 + 4) + 128;
+constexpr int SW_SMEM_BYTES = SW_NBUF * SW_TILE_BYTES + SW_BLOB_REGION + SW_MAX_RUNS * 8 + SWEEP_MAX_SLOTS * (16 + 4 + 4) + 128;
 static_assert(SW_SMEM_BYTES <= 227 * 1024, "sweep kernel shared memory exceeds 227 KB");
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -82,9 +85,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
   char* blob = reinterpret_cast<char*>(smem + SW_NBUF * SW_TILE_BYTES);
   uint64_t* run_off = reinterpret_cast<uint64_t*>(blob + SW_BLOB_REGION);
   double2* op_scal_raw = reinterpret_cast<double2*>(run_off + SW_MAX_RUNS);
-  uint32_t* op_flag = reinterpret_cast<uint32_t*>(op_scal_raw + SWEEP_MAX_OPS);
-  uint32_t* op_aux = op_flag + SWEEP_MAX_OPS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(op_aux + SWEEP_MAX_OPS);
+  uint32_t* op_flag = reinterpret_cast<uint32_t*>(op_scal_raw + SWEEP_MAX_SLOTS);
+  uint32_t* op_aux = op_flag + SWEEP_MAX_SLOTS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(op_aux + SWEEP_MAX_SLOTS);
   uint64_t* done = full + SW_NBUF;
   uint64_t* freeb = done + SW_NBUF;
   C* op_scal = reinterpret_cast<C*>(op_scal_raw);
@@ -116,8 +119,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
 
   const uint64_t ntiles = hdr.ntiles;
   const uint64_t my_n = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const DevOp* ops = reinterpret_cast<const DevOp*>(blob + hdr.ops_offset);
-  const int nops = (int)hdr.nops;
+  const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
+  const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
+  const int npasses = (int)hdr.npasses;
+  const int nslots = (int)hdr.nslots;
 
   if (tid < 32) {
     // ================= loader warp: HBM -> shared =================
@@ -154,32 +159,30 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
       const int b = (int)(i % SW_NBUF);
       C* tile = tiles + (size_t)b * tile_elems;
       const uint64_t base = deposit(blockIdx.x + i * gridDim.x, hdr.other_mask);
-      if ((int)ctid < nops) {
-        uint32_t flag, aux;
-        C s;
-        op_prephase<C>(ops[ctid], blob, base, flag, s, aux);
-        op_flag[ctid] = flag;
-        op_aux[ctid] = aux;
-        op_scal[ctid] = s;
+      for (int sl = (int)ctid; sl < nslots; sl += SW_COMPUTE_THREADS) {
+        const uint32_t so = slot_table[sl];
+        if (so & 0x80000000u) {
+          const DevOp& bop = *reinterpret_cast<const DevOp*>(blob + (so & 0x7fffffffu));
+          op_flag[sl] = (base & bop.ext_cmask) == bop.ext_cmask ? 1u : 0u;
+        } else {
+          micro_prephase<C>(*reinterpret_cast<MicroOp*>(blob + so), blob, base, T);
+        }
       }
       mbar_wait(&full[b], (uint32_t)((i / SW_NBUF) & 1));
       compute_bar();
-      for (int o = 0; o < nops; ++o) {
-        if (!op_flag[o]) continue;
-        const DevOp& op = ops[o];
-        const C* payload = reinterpret_cast<const C*>(blob + op.payload);
-        switch (op.type) {
-          case OP_DENSE:
-            switch (op.k) {
-              case 1: pass_dense<C, 1>(tile, op, payload, T, ctid, SW_COMPUTE_THREADS); break;
-              case 2: pass_dense<C, 2>(tile, op, payload, T, ctid, SW_COMPUTE_THREADS); break;
-              default: break;
-            }
-            break;
-          case OP_SWAP: pass_swap<C>(tile, op, T, ctid, SW_COMPUTE_THREADS); break;
-          case OP_FAN: pass_fan<C>(tile, op, blob, op_scal[o], T, ctid, SW_COMPUTE_THREADS); break;
-          case OP_DIAGK: pass_diagk<C>(tile, op, blob, op_aux[o], T, ctid, SW_COMPUTE_THREADS); break;
-          case OP_DENSE_BIG: {
+      for (int pi = 0; pi < npasses; ++pi) {
+        const PassHeader& ph = passes[pi];
+        if (ph.kind == PASS_REGTILE) {
+          switch (ph.R) {
+            case 1: run_regtile<C, 1>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
+            case 2: run_regtile<C, 2>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
+            case 3: run_regtile<C, 3>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
+            default: run_regtile<C, 4>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
+          }
+        } else {
+          const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
+          if (op_flag[op.slot]) {
+            const C* payload = reinterpret_cast<const C*>(blob + op.payload);
             const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
             for (uint32_t t = 0; t < ntasks; t += SW_COMPUTE_THREADS) {
               BigAcc<C> a;
@@ -188,8 +191,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
               big_write<C>(tile, op, a);
               if (t + SW_COMPUTE_THREADS < ntasks) compute_bar();
             }
-          } break;
-          default: break;
+          }
         }
         compute_bar();
       }

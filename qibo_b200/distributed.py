@@ -1,6 +1,34 @@
-"""Global-qubit distributed execution (one process per GPU) -- see DESIGN.md section 6."""
+"""Global-qubit distributed execution: one process per GPU, ``torch.distributed`` for the plumbing.
 
+Re-implements the scheme of ``qibo.models.distcircuit`` (DistributedQubits / DistributedQueues,
+models/distcircuit.py:9-329) for an executor the reference never shipped
+(``Backend.execute_distributed_circuit`` raises NotImplementedError, backends/abstract.py:2638-2647).
+
+Layout.  W = 2^g ranks; rank r holds the 2^(n-g) amplitudes whose g most significant *physical* bits equal r
+(piece layout ``sorted(global) + local``, distcircuit.py:33-36).  Instead of relabelling the caller's gate
+objects in place (distcircuit.py:236-244) the planner keeps a logical-qubit -> physical-bit map:
+
+  * a gate needs a qubit LOCAL only if its matrix mixes that qubit's 0/1 subspaces; control qubits and every
+    qubit of a diagonal gate may stay global -- on each rank the gate is specialised to the rank's bit values
+    (the reference does the same for global controls, distcircuit.py:316-327);
+  * when a mixing target sits on a global bit it is exchanged with a high local bit whose qubit is needed
+    furthest in the future (pairwise half-shard exchange, contiguous chunks of >= 2^20 amplitudes);
+  * uncontrolled SWAP gates are applied as relabelling; the map is made canonical again at the end
+    (the reference appends reverse swaps for the same purpose, distcircuit.py:267).
+
+The local gate runs go through the same sweep kernels as the single-GPU path (``Engine.apply_program``).
+The planner and the specialisation are pure host code: ``tests/test_distributed_cpu.py`` drives them with a
+NumPy shard executor over a world_size-2/4 gloo group.
+"""
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
 import torch
+
+from qibo_b200.ops import Op
 
 
 def world_size():
@@ -9,5 +37,332 @@ def world_size():
     return 1
 
 
-def execute_circuit(backend, circuit, initial_state=None, nshots=None):  # pragma: no cover
-    raise NotImplementedError("multi-rank execution is wired up in qibo_b200.distributed (work in progress)")
+def rank():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- planning
+@dataclass
+class PhysOp:
+    """An Op with its qubits resolved to physical bit positions at planning time."""
+
+    data: np.ndarray
+    tbits: Tuple[int, ...]  # targets[0] first (MSB of the matrix index)
+    cbits: Tuple[int, ...]
+    is_diagonal: bool
+
+
+@dataclass
+class Segment:
+    kind: str  # "local" | "exchange"
+    ops: Optional[List[PhysOp]] = None
+    gbit: int = -1  # exchange: global physical bit
+    lbit: int = -1  # exchange: local physical bit
+
+
+def mixing_targets(op: Op) -> List[int]:
+    """Targets whose 0/1 subspaces the matrix mixes -- the only qubits that must be local."""
+    if op.is_diagonal:
+        return []
+    k = len(op.targets)
+    dim = 1 << k
+    m = op.data
+    rows, cols = np.nonzero(m)
+    diff = np.bitwise_xor(rows, cols)
+    mixed = 0
+    for d in np.unique(diff):
+        mixed |= int(d)
+    return [op.targets[i] for i in range(k) if (mixed >> (k - 1 - i)) & 1]
+
+
+def is_plain_swap(op: Op) -> bool:
+    if op.is_diagonal or len(op.targets) != 2 or op.controls:
+        return False
+    sw = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+    return bool(np.array_equal(op.data, sw))
+
+
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+class Plan:
+    """Host-side plan: identical on every rank (pure function of the op list, n and g)."""
+
+    def __init__(self, nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True, high_window: int = 8):
+        self.n, self.g = nqubits, nglobal
+        self.nlocal = nqubits - nglobal
+        if self.nlocal < 1:
+            raise ValueError("need at least one local qubit per rank")
+        n, nlocal = self.n, self.nlocal
+        self.segments: List[Segment] = []
+        self.nexchanges = 0
+        pos = [n - 1 - q for q in range(n)]  # logical qubit -> physical bit
+        # next dense use of every logical qubit, for the furthest-in-future eviction rule
+        needs = [mixing_targets(op) for op in ops]
+        swaps = [relabel_swaps and is_plain_swap(op) for op in ops]
+        next_use = [[] for _ in range(n)]
+        for i, (nd, sw) in enumerate(zip(needs, swaps)):
+            if sw:
+                continue
+            for q in nd:
+                next_use[q].append(i)
+        ptr = [0] * n
+        cur: List[PhysOp] = []
+        window = [b for b in range(nlocal - 1, max(nlocal - 1 - high_window, -1), -1)]
+
+        def flush():
+            if cur:
+                self.segments.append(Segment("local", ops=list(cur)))
+                cur.clear()
+
+        def exchange(gbit, lbit):
+            flush()
+            self.segments.append(Segment("exchange", gbit=gbit, lbit=lbit))
+            self.nexchanges += 1
+            qa, qb = pos.index(gbit), pos.index(lbit)
+            pos[qa], pos[qb] = lbit, gbit
+
+        for i, op in enumerate(ops):
+            for q in set(op.targets) | set(op.controls):
+                while ptr[q] < len(next_use[q]) and next_use[q][ptr[q]] < i:
+                    ptr[q] += 1
+            if swaps[i]:
+                a, b = op.targets
+                pos[a], pos[b] = pos[b], pos[a]  # the label "a" now names the amplitudes that were "b"
+                continue
+            if len(needs[i]) > nlocal:
+                raise ValueError("gate has more mixing targets than there are local qubits")
+            for q in needs[i]:
+                if pos[q] < nlocal:
+                    continue
+                best, best_use = None, -1
+                for b in window:
+                    e = pos.index(b)
+                    if e in needs[i]:
+                        continue
+                    while ptr[e] < len(next_use[e]) and next_use[e][ptr[e]] < i:
+                        ptr[e] += 1
+                    use = next_use[e][ptr[e]] if ptr[e] < len(next_use[e]) else len(ops) + 1
+                    if use > best_use:
+                        best, best_use = b, use
+                if best is None:
+                    raise ValueError("no local qubit available to exchange with")
+                exchange(pos[q], best)
+            cur.append(PhysOp(op.data, tuple(pos[q] for q in op.targets), tuple(pos[q] for q in op.controls), op.is_diagonal))
+
+        # ---- back to the canonical layout: logical qubit q on physical bit n-1-q
+        def local_swap(b1, b2):
+            cur.append(PhysOp(_SWAP, (b1, b2), (), False))
+            qa, qb = pos.index(b1), pos.index(b2)
+            pos[qa], pos[qb] = b2, b1
+
+        for gbit in range(n - 1, nlocal - 1, -1):  # fix the global bits first
+            want = n - 1 - gbit  # logical qubit that belongs here
+            if pos[want] == gbit:
+                continue
+            if pos[want] >= nlocal:  # it sits on another global bit: route through a high local bit
+                exchange(pos[want], window[0])
+            b = pos[want]
+            if b not in window:  # bring it to a high local bit first (a local sweep)
+                free = next(w for w in window if pos.index(w) != want)
+                local_swap(b, free)
+                b = free
+            exchange(gbit, b)
+        for q in range(n):  # then the local permutation, as SWAP gates for the sweep planner
+            target = n - 1 - q
+            if target < nlocal and pos[q] != target:
+                local_swap(pos[q], target)
+        flush()
+        assert pos == [n - 1 - q for q in range(n)]
+
+
+def specialise(p: PhysOp, nlocal: int, rank_: int) -> Optional[Op]:
+    """PhysOp -> the Op this rank applies to its shard (or None if a global control is 0 here)."""
+    tb, cb = list(p.tbits), []
+    for c in p.cbits:
+        if c >= nlocal:
+            if not (rank_ >> (c - nlocal)) & 1:
+                return None
+        else:
+            cb.append(c)
+    data = p.data
+    k = len(tb)
+    glob = [i for i in range(k) if tb[i] >= nlocal]
+    if glob:
+        keep = np.arange(1 << k)
+        for i in glob:
+            v = (rank_ >> (tb[i] - nlocal)) & 1
+            keep = keep[((keep >> (k - 1 - i)) & 1) == v]
+        data = data[keep] if p.is_diagonal else data[np.ix_(keep, keep)]
+        tb = [b for b in tb if b < nlocal]
+        if p.is_diagonal:
+            if np.all(data == 1):
+                return None
+        elif np.array_equal(data, np.eye(len(keep))):
+            return None
+    to_q = lambda b: nlocal - 1 - b  # noqa: E731
+    return Op(np.ascontiguousarray(data), tuple(to_q(b) for b in tb), tuple(to_q(b) for b in cb), is_diagonal=p.is_diagonal)
+
+
+# ---------------------------------------------------------------------------------------------- execution
+def exchange_half(state: torch.Tensor, nlocal: int, gbit: int, lbit: int, staging: List[torch.Tensor], group=None):
+    """Swap global physical bit ``gbit`` with local bit ``lbit``: this rank (global bit value b) sends the half of
+    its shard with local bit == 1-b to rank ^ (1 << j) and receives the partner's half with local bit == b into the
+    same place.  Contiguous chunks, double-buffered staging; NCCL send/recv over NVLink (gloo on CPU)."""
+    import torch.distributed as dist
+
+    r = dist.get_rank(group)
+    j = gbit - nlocal
+    peer = r ^ (1 << j)
+    b = (r >> j) & 1
+    view = state.view(-1, 2, 1 << lbit)[:, 1 - b, :]  # (nchunks, 2^lbit), rows are contiguous
+    nrows, row = view.shape
+    cap = staging[0].numel()
+    pending = None
+    pieces = []
+    for i in range(nrows):
+        for s in range(0, row, cap):
+            pieces.append(view[i, s : s + min(cap, row - s)])
+    for k, piece in enumerate(pieces):
+        buf = staging[k % 2][: piece.numel()]
+        ops = [dist.P2POp(dist.isend, piece, peer, group), dist.P2POp(dist.irecv, buf, peer, group)]
+        if r > peer:
+            ops.reverse()
+        reqs = dist.batch_isend_irecv(ops)
+        if pending is not None:
+            pending[0].copy_(pending[1])
+        for q in reqs:
+            q.wait()
+        pending = (piece, buf)
+    if pending is not None:
+        pending[0].copy_(pending[1])
+    return 2 * state.element_size() * (state.numel() // 2)  # bytes sent + received by this rank
+
+
+class ShardedProgram:
+    """A gate queue planned once for (n, world size) and specialised for this rank; ``run`` applies it to a shard."""
+
+    def __init__(self, engine, nqubits: int, dtype, ops: Sequence[Op], relabel_swaps: bool = True, apply=None,
+                 staging_elems: int = 1 << 26):
+        self.engine = engine
+        self.world, self.rank = world_size(), rank()
+        self.g = int(round(math.log2(self.world)))
+        if 1 << self.g != self.world:
+            raise ValueError("the number of ranks must be a power of two")
+        self.n, self.dtype = nqubits, np.dtype(dtype)
+        self.nlocal = nqubits - self.g
+        self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps)
+        self.segments = []
+        for seg in self.plan.segments:
+            if seg.kind == "local":
+                local = [o for o in (specialise(p, self.nlocal, self.rank) for p in seg.ops) if o is not None]
+                self.segments.append(("local", local))
+            else:
+                self.segments.append(("exchange", seg.gbit, seg.lbit))
+        self._apply = apply  # test hook: NumPy shard executor
+        self._staging = None
+        self._staging_elems = staging_elems
+        self.ngates = len(ops)
+
+    # ---- shard constructors --------------------------------------------------------------------
+    def basis_state(self, index: int = 0):
+        """|index> of the full register: the amplitude lives on rank index >> nlocal."""
+        st = self.engine.basis_state(self.nlocal, self.dtype, 0)
+        if (index >> self.nlocal) != self.rank:
+            st.tensor.zero_()
+        elif index & ((1 << self.nlocal) - 1):
+            st.tensor.zero_()
+            st.tensor[index & ((1 << self.nlocal) - 1)] = 1
+        return st
+
+    def scatter(self, full: np.ndarray):
+        """This rank's shard of a full host state (canonical layout)."""
+        lo = self.rank << self.nlocal
+        return self.engine.upload(np.ascontiguousarray(full[lo : lo + (1 << self.nlocal)]).astype(self.dtype))
+
+    # ---- execution ---------------------------------------------------------------------------------
+    def _stage(self, tensor):
+        if self._staging is None or self._staging[0].device != tensor.device or self._staging[0].dtype != tensor.dtype:
+            n = min(self._staging_elems, tensor.numel() // 2)
+            self._staging = [torch.empty(n, dtype=tensor.dtype, device=tensor.device) for _ in range(2)]
+        return self._staging
+
+    def run(self, state, timed: bool = True):
+        """Apply the program to this rank's shard (DeviceArray, or a torch tensor with the test hook)."""
+        tensor = state.tensor if hasattr(state, "tensor") else state
+        out = RunStats()
+        for seg in self.segments:
+            if seg[0] == "local":
+                if not seg[1]:
+                    continue
+                if self._apply is not None:
+                    self._apply(tensor, self.nlocal, seg[1])
+                else:
+                    st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed)
+                    out.nsweeps += st.nsweeps
+                    out.elapsed_ms += st.elapsed_ms
+            else:
+                t0 = None
+                if tensor.is_cuda and timed:
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record()
+                out.exchange_bytes += exchange_half(tensor, self.nlocal, seg[1], seg[2], self._stage(tensor))
+                out.nexchanges += 1
+                if t0 is not None:
+                    t1.record()
+                    t1.synchronize()
+                    out.exchange_ms += t0.elapsed_time(t1)
+        return out
+
+    def gather(self, state) -> np.ndarray:
+        """Full state on every rank (small n only)."""
+        import torch.distributed as dist
+
+        tensor = state.tensor if hasattr(state, "tensor") else state
+        parts = [torch.empty_like(tensor) for _ in range(self.world)]
+        dist.all_gather(parts, tensor)
+        return torch.cat(parts).cpu().numpy()
+
+
+class RunStats:
+    def __init__(self):
+        self.nsweeps = 0
+        self.elapsed_ms = 0.0  # CUDA-event time of the local sweeps
+        self.nexchanges = 0
+        self.exchange_ms = 0.0
+        self.exchange_bytes = 0
+
+
+def execute_circuit(backend, circuit, initial_state=None, nshots=None):
+    """``Backend.execute_distributed_circuit`` under torchrun: every rank calls it with the same circuit."""
+    from qibo.config import raise_error
+    from qibo.result import CircuitResult, QuantumState
+
+    from qibo_b200.array import DeviceArray
+
+    n = circuit.nqubits
+    ops = []
+    for gate in circuit.queue:
+        if not backend._is_plain(gate):
+            if gate.__class__.__name__ == "M" and not gate.collapse:
+                gate.result.backend = backend
+                continue
+            raise_error(NotImplementedError, "callbacks / collapsing measurements need the full state: not available across ranks")
+        ops.extend(backend._gate_ops(gate, n))
+    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops)
+    if initial_state is None:
+        shard = prog.basis_state(0)
+    else:
+        host = backend.to_numpy(initial_state) if isinstance(initial_state, DeviceArray) else np.asarray(initial_state)
+        shard = prog.scatter(host)
+    prog.run(shard, timed=False)
+    if n > 30:
+        raise_error(NotImplementedError, "gathering a state of more than 30 qubits on every rank is not supported; use ShardedProgram")
+    full = backend.engine_gpu.upload(prog.gather(shard))
+    if circuit.measurements:
+        circuit._final_state = CircuitResult(full, circuit.measurements, backend=backend, nshots=1000 if nshots is None else nshots)
+    else:
+        circuit._final_state = QuantumState(full, backend=backend)
+    return circuit._final_state

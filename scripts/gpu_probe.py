@@ -91,14 +91,19 @@ def main():
     del os.environ["QB_SWEEP_LOW_BITS"]
     out["sweep_single"] = sw
 
-    # passes per sweep: k H gates on low qubits (all inside the tile) in one sweep
+    # gates per sweep: k single-qubit gates on bits inside the tile
     pp = []
-    for k in [1, 2, 4, 6, 8, 12]:
-        os.environ["QB_SWEEP_MAX_PASSES"] = "64"
-        ops = [Op(h, (n - 1 - (i % 12),)) for i in range(k)]
-        st_, _ = plan_program(n, dtype, ops)
-        med, mn = timeit(lambda: eng.apply_program(st, n, ops))
-        pp.append({"passes": k, "sweeps": st_.nsweeps, "ms": mn, "GBs_per_sweep": st_.nsweeps * full / (mn * 1e-3) / 1e9})
+    os.environ["QB_SWEEP_MAX_OPS"] = "96"
+    ry = circuits.matrix("RY", 0.37)
+    rx = circuits.matrix("RX", 0.37)
+    for label, mat, bits in (("H mid bits 5..11", h, list(range(5, 12))), ("H low bits 0..2", h, [0, 1, 2]),
+                             ("RX(complex) mid bits", rx, list(range(5, 12))), ("H bits 3..5", h, [3, 4, 5])):
+        for k in [1, 3, 6, 12, 24]:
+            ops = [Op(mat, (n - 1 - bits[i % len(bits)],)) for i in range(k)]
+            st_, _ = plan_program(n, dtype, ops)
+            med, mn = timeit(lambda: eng.apply_program(st, n, ops))
+            pp.append({"what": label, "gates": k, "sweeps": st_.nsweeps, "passes": st_.ndense_passes, "ms": mn,
+                       "GBs_per_sweep": st_.nsweeps * full / (mn * 1e-3) / 1e9})
     for k in [1, 2, 4, 8]:
         ops = [circuits.op("CU1", (n - 1 - i, 0), 0.1 * (i + 1)) for i in range(3)] * 1
         ops = []
@@ -107,20 +112,20 @@ def main():
         st_, _ = plan_program(n, dtype, ops)
         med, mn = timeit(lambda: eng.apply_program(st, n, ops))
         pp.append({"fans": k, "sweeps": st_.nsweeps, "ms": mn, "GBs_per_sweep": st_.nsweeps * full / (mn * 1e-3) / 1e9})
-    del os.environ["QB_SWEEP_MAX_PASSES"]
+    del os.environ["QB_SWEEP_MAX_OPS"]
     out["sweep_passes"] = pp
 
     # whole circuits
     circ = []
-    for mp in ["4", "6", "8", "12"]:
-        os.environ["QB_SWEEP_MAX_PASSES"] = mp
+    for mp in ["12", "24", "96"]:
+        os.environ["QB_SWEEP_MAX_OPS"] = mp
         ops = circuits.qft(n)
         st_, _ = plan_program(n, dtype, ops)
         eng.basis_state(n, dtype)
         med, mn = timeit(lambda: eng.apply_program(st, n, ops), reps=3, warm=1)
-        circ.append({"circuit": f"QFT({n})", "max_passes": int(mp), "gates": len(ops), "sweeps": st_.nsweeps, "ms": mn,
+        circ.append({"circuit": f"QFT({n})", "max_ops": int(mp), "passes": st_.ndense_passes, "gates": len(ops), "sweeps": st_.nsweeps, "ms": mn,
                      "gates_per_s": len(ops) / (mn * 1e-3), "GBs_per_sweep": st_.nsweeps * full / (mn * 1e-3) / 1e9})
-    del os.environ["QB_SWEEP_MAX_PASSES"]
+    del os.environ["QB_SWEEP_MAX_OPS"]
     ops = circuits.qft(n)
     med, mn = timeit(lambda: eng.apply_program(st, n, ops, fuse=False), reps=2, warm=1)
     circ.append({"circuit": f"QFT({n}) one sweep per gate", "gates": len(ops), "ms": mn, "gates_per_s": len(ops) / (mn * 1e-3),

@@ -12,41 +12,52 @@
 
 using namespace qb;
 
+constexpr uint32_t EMUL_THREADS = 256;  // the kernel's compute-thread count: same group -> thread mapping
+
 template <typename C>
-static void run_sweep(C* state, const char* blob) {
+static void run_sweep(C* state, char* blob) {  // the set-up phase writes per-tile values into the ops
   const SweepHeader& hdr = *reinterpret_cast<const SweepHeader*>(blob);
   const int T = (int)hdr.T, L = (int)hdr.L;
   const uint32_t nruns = 1u << (T - L), run = 1u << L;
-  const DevOp* ops = reinterpret_cast<const DevOp*>(blob + hdr.ops_offset);
+  const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
+  const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
   std::vector<C> tile(size_t(1) << T);
+  std::vector<uint32_t> flag(hdr.nslots + 1), aux(hdr.nslots + 1);
+  std::vector<C> scal(hdr.nslots + 1);
   for (uint64_t t = 0; t < hdr.ntiles; ++t) {
     const uint64_t base = deposit(t, hdr.other_mask);
     for (uint32_t r = 0; r < nruns; ++r) {
       const uint64_t off = deposit(uint64_t(r) << L, hdr.tile_mask);
       memcpy(&tile[size_t(r) << L], state + base + off, run * sizeof(C));
     }
-    for (uint32_t o = 0; o < hdr.nops; ++o) {
-      const DevOp& op = ops[o];
-      uint32_t flag, aux;
-      C scal;
-      op_prephase<C>(op, blob, base, flag, scal, aux);
-      if (!flag) continue;
-      const C* payload = reinterpret_cast<const C*>(blob + op.payload);
-      switch (op.type) {
-        case OP_DENSE:
-          if (op.k == 1) pass_dense<C, 1>(tile.data(), op, payload, T, 0, 1);
-          else pass_dense<C, 2>(tile.data(), op, payload, T, 0, 1);
-          break;
-        case OP_SWAP: pass_swap<C>(tile.data(), op, T, 0, 1); break;
-        case OP_FAN: pass_fan<C>(tile.data(), op, blob, scal, T, 0, 1); break;
-        case OP_DIAGK: pass_diagk<C>(tile.data(), op, blob, aux, T, 0, 1); break;
-        case OP_DENSE_BIG: {
-          const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
-          std::vector<BigAcc<C>> accs(ntasks);
-          for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, task, accs[task]);
-          for (uint32_t task = 0; task < ntasks; ++task) big_write<C>(tile.data(), op, accs[task]);
-        } break;
-        default: break;
+    for (uint32_t sl = 0; sl < hdr.nslots; ++sl) {
+      const uint32_t so = slot_table[sl];
+      if (so & 0x80000000u) {
+        const DevOp& bop = *reinterpret_cast<const DevOp*>(blob + (so & 0x7fffffffu));
+        flag[sl] = (base & bop.ext_cmask) == bop.ext_cmask ? 1u : 0u;
+      } else {
+        micro_prephase<C>(*reinterpret_cast<MicroOp*>(blob + so), blob, base, T);
+      }
+    }
+    for (uint32_t pi = 0; pi < hdr.npasses; ++pi) {
+      const PassHeader& ph = passes[pi];
+      if (ph.kind == PASS_REGTILE) {
+        for (uint32_t ctid = 0; ctid < EMUL_THREADS; ++ctid) {
+          switch (ph.R) {
+            case 1: run_regtile<C, 1>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
+            case 2: run_regtile<C, 2>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
+            case 3: run_regtile<C, 3>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
+            default: run_regtile<C, 4>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
+          }
+        }
+      } else {
+        const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
+        if (!flag[op.slot]) continue;
+        const C* payload = reinterpret_cast<const C*>(blob + op.payload);
+        const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
+        std::vector<BigAcc<C>> accs(ntasks);
+        for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, task, accs[task]);
+        for (uint32_t task = 0; task < ntasks; ++task) big_write<C>(tile.data(), op, accs[task]);
       }
     }
     for (uint32_t r = 0; r < nruns; ++r) {
@@ -74,7 +85,7 @@ extern "C" int emul_apply_program(void* state, int nqubits, int dtype, const qb_
   if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, g_err)) return QB_ERR_UNSUPPORTED;
   if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
   for (auto& sd : plan.sweeps) {
-    const char* blob = plan.blob.data() + sd.blob_offset;
+    char* blob = plan.blob.data() + sd.blob_offset;
     if (dtype == QB_C128) run_sweep<double2>((double2*)state, blob);
     else run_sweep<float2>((float2*)state, blob);
   }

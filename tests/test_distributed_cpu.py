@@ -1,0 +1,131 @@
+"""World-size 2 and 4 gloo tests (CPU) of the distributed HOST logic: planning (which qubits must be local,
+exchanges, swap relabelling, canonicalisation), per-rank specialisation of gates with global controls /
+diagonal qubits, and the pairwise half-shard exchange.  The local gate runs are executed by the oracle on
+NumPy shards (a test hook); on the GPU the same plan drives the sweep kernels (tests/test_gpu_distributed.py)."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_apply(tensor, nlocal, ops):
+    from helpers import oracle_run
+
+    arr = tensor.numpy()
+    arr[:] = oracle_run(arr.copy(), ops, nlocal)
+
+
+def _worker(rank, world, port, case, n, seed, out):
+    sys.path[:0] = [ROOT, HERE]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import ops_from_named, oracle_run, rand_state, random_zoo
+        from oracle import numpy_oracle as orc
+        from qibo_b200.distributed import ShardedProgram
+
+        if case == "qft":
+            ops = ops_from_named(orc.qft_ops(n))
+        elif case == "random":
+            ops = ops_from_named(orc.random_ops(n, 30, seed=seed))
+        elif case == "variational":
+            ops = ops_from_named(orc.variational_ops(n, 2, np.random.default_rng(seed).random(4 * n) * 6))
+        else:
+            ops = random_zoo(n, 40, seed, max_dense=3)
+        psi = rand_state(n, seed)
+        prog = ShardedProgram(None, n, "complex128", ops, apply=_oracle_apply, staging_elems=8)
+        nl = prog.nlocal
+        shard = torch.from_numpy(psi[rank << nl : (rank + 1) << nl].copy())
+        stats = prog.run(shard, timed=False)
+        full = prog.gather(shard)
+        ref = oracle_run(psi, ops, n)
+        err = float(np.abs(full - ref).max())
+        if rank == 0:
+            out.put((err, stats.nexchanges, prog.plan.nexchanges))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, case, n, seed=0):
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, seed, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    return out.get()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("case", ["qft", "random", "variational", "zoo"])
+def test_sharded_program_matches_oracle(world, case):
+    err, nex, planned = _run(world, case, 7 if case != "qft" else 8, seed=3)
+    assert err < 1e-12
+    assert nex == planned
+
+
+def test_plan_properties():
+    """Device-free planner checks in the spirit of tests/test_models_distcircuit.py:95-103: no mixing target is
+    ever on a global bit inside a local segment, and the layout is canonical at the end."""
+    sys.path[:0] = [ROOT, HERE]
+    from helpers import ops_from_named
+    from oracle import numpy_oracle as orc
+    from qibo_b200.distributed import Plan
+
+    for n in (28, 31, 35):
+        ops = ops_from_named(orc.qft_ops(n))
+        for g in (1, 2, 3):
+            plan = Plan(n, g, ops)
+            nl = n - g
+            for seg in plan.segments:
+                if seg.kind == "local":
+                    for p in seg.ops:
+                        if not p.is_diagonal:
+                            rows, cols = np.nonzero(p.data)
+                            mixed = 0
+                            for d in np.unique(rows ^ cols):
+                                mixed |= int(d)
+                            k = len(p.tbits)
+                            for i, b in enumerate(p.tbits):
+                                if (mixed >> (k - 1 - i)) & 1:
+                                    assert b < nl
+                else:
+                    assert seg.gbit >= nl > seg.lbit >= nl - 8  # contiguous chunks of >= 2^(nl-8) amplitudes
+            assert plan.nexchanges <= 4 * g + 2, (n, g, plan.nexchanges)
+
+
+def test_specialise_global_control_and_diagonal():
+    sys.path[:0] = [ROOT, HERE]
+    from oracle import numpy_oracle as orc
+    from qibo_b200.distributed import PhysOp, specialise
+
+    cnot = PhysOp(orc.gate_matrix("CNOT"), (5, 1), (), False)  # control on global bit 5 (nlocal = 4), target local bit 1
+    assert specialise(cnot, 4, 0) is None  # rank bit 1 (bit 5 - 4) is 0 on rank 0
+    op = specialise(cnot, 4, 2)
+    np.testing.assert_array_equal(op.data, orc.gate_matrix("X"))
+    assert op.targets == (2,) and op.controls == ()
+    cu1 = PhysOp(orc.gate_matrix("CU1", 0.3), (4, 5), (), False)  # both qubits global
+    assert specialise(cu1, 4, 1) is None and specialise(cu1, 4, 2) is None
+    op = specialise(cu1, 4, 3)
+    assert op.targets == () and abs(op.data[0, 0] - np.exp(0.3j)) < 1e-15
+    rz = PhysOp(np.array([np.exp(-0.1j), np.exp(0.1j)]), (4,), (2,), True)
+    op = specialise(rz, 4, 1)
+    assert op.is_diagonal and op.targets == () and op.controls == (1,) and abs(op.data[0] - np.exp(0.1j)) < 1e-15
