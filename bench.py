@@ -170,7 +170,8 @@ def run_reference(args):
             break
     vals = vals[min(args.warmup, len(vals) - 1):]
     base = vals[-1]
-    v = float(np.mean([x["value"] for x in vals]))
+    # same unit as the GPU arm: gates x shards of 2^(n - log2 N) amplitudes (one host applies each gate to all N shards)
+    v = args.gpus * float(np.mean([x["value"] for x in vals]))
     base["value"] = v
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "gates/s", "n_gpus": args.gpus, "steps": len(vals),
@@ -210,7 +211,7 @@ def run_gpu(args):
         from qibo_b200 import distributed
 
         runner = distributed.ShardedProgram(eng, n, args.dtype, ops)
-        state = runner.basis_state()
+        state = runner.basis_state() if args.exchange == "nccl" else runner.peer_shard(0)
         step = lambda: runner.run(state)  # noqa: E731
         barrier = dist.barrier
     else:
@@ -306,7 +307,7 @@ def run_gpu(args):
             line["exchange"] = {
                 "count_per_step": nxch // args.steps, "ms_per_step_rank0": xch_ms / args.steps,
                 "GBps_per_direction_rank0": (xch_bytes / 2) / max(xch_ms, 1e-9) / 1e6,
-                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": "NCCL send/recv over NVLink, half-shard pairwise",
+                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": "one swap kernel over NVLink peer memory (CUDA IPC)" if args.exchange == "p2p" else "NCCL send/recv over NVLink, half-shard pairwise",
             }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -325,6 +326,7 @@ def main():
     ap.add_argument("--impl", default="qibo_b200", choices=["qibo_b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="global<->local exchange: NVLink peer-memory kernel or NCCL send/recv")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

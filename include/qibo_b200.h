@@ -150,11 +150,14 @@ int qb_collapse(qb_handle h, void* state, int nqubits, int dtype, const int* qub
  * staging buffer of 2^(nqubits-1) amplitudes (pack: state -> staging; unpack: staging -> state). */
 int qb_pack_half(qb_handle h, const void* state, int nqubits, int dtype, int local_qubit, int bit, void* staging);
 int qb_unpack_half(qb_handle h, void* state, int nqubits, int dtype, int local_qubit, int bit, const void* staging);
-/* Fused exchange over NVLink peer memory: reads the partner's half directly through a peer-mapped
- * pointer (`peer_state`) and writes it into this shard's half; both ranks must bracket it with a
- * barrier.  Swaps this rank's (local_qubit == 1 - rank_bit) half with the partner's. */
-int qb_exchange_half_p2p(qb_handle h, void* state, const void* peer_staging, int nqubits, int dtype,
-                         int local_qubit, int bit);
+/* Exchange over NVLink peer memory, no staging and no NCCL on the data path: ONE kernel swaps, element by
+ * element in registers, this rank's outgoing half (local qubit == 1 - my_bit) with the partner's outgoing half
+ * (local qubit == my_bit), reading and writing the partner's shard through a peer-mapped pointer
+ * (`peer_state`, from qb_ipc_open_handle).  The two ranks of a pair split the index range (`part` of `nparts`),
+ * so both NVLink directions carry loads and stores at once.  The caller brackets it with a stream-ordered
+ * barrier on both ranks. */
+int qb_swap_half_p2p(qb_handle h, void* state, void* peer_state, int nqubits, int dtype, int local_qubit, int my_bit,
+                     int part, int nparts);
 /* CUDA IPC plumbing so that ranks (one process per GPU) can map each other's buffers */
 int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes);
 int qb_ipc_open_handle(qb_handle h, const void* handle_64bytes, void** dptr_out);

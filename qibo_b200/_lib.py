@@ -71,7 +71,7 @@ PROTOTYPES = {
     "qb_collapse": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_uint64, c_int]),
     "qb_pack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qb_unpack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "qb_exchange_half_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "qb_swap_half_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     "qb_ipc_get_handle": (c_int, [c_void_p, c_void_p, c_void_p]),
     "qb_ipc_open_handle": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "qb_ipc_close_handle": (c_int, [c_void_p, c_void_p]),

@@ -554,6 +554,16 @@ int qb_probabilities(qb_handle h, const void* state, int nqubits, int dtype, con
 
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
+  bool identity = nmeasured == nqubits;
+  for (int i = 0; i < nmeasured && identity; ++i) identity = qubits[i] == i;
+  if (identity) {  // every qubit, ascending: a plain elementwise pass
+    uint64_t count = uint64_t(1) << nqubits;
+    int grid = grid_for((count + 1) / 2, 256, h->sm_count, 32);
+    if (dtype == QB_C128) k3_probs_full<double2, double><<<grid, 256, 0, h->stream>>>((const double2*)state, (double*)probs_out, count);
+    else k3_probs_full<float2, float><<<grid, 256, 0, h->stream>>>((const float2*)state, (float*)probs_out, count);
+    QB_CHECK_LAUNCH("k3_probs_full");
+    return QB_OK;
+  }
   double* partial = nullptr;
   if (p.log_split > 0) {
     int rc = ensure_scratch(h, (size_t)(p.nbins << p.log_split) * sizeof(double));
@@ -729,9 +739,16 @@ int qb_unpack_half(qb_handle h, void* state, int nqubits, int dtype, int local_q
   return QB_OK;
 }
 
-int qb_exchange_half_p2p(qb_handle h, void* state, const void* peer_staging, int nqubits, int dtype, int local_qubit, int bit) {
-  // reading the partner's packed half through a peer-mapped pointer is the same gather as unpack_half
-  return qb_unpack_half(h, state, nqubits, dtype, local_qubit, bit, peer_staging);
+int qb_swap_half_p2p(qb_handle h, void* state, void* peer_state, int nqubits, int dtype, int local_qubit, int my_bit, int part,
+                     int nparts) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !peer_state) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (local_qubit < 0 || local_qubit >= nqubits || (my_bit != 0 && my_bit != 1) || nparts < 1 || part < 0 || part >= nparts)
+    return fail(QB_ERR_INVALID, "bad exchange arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int rc = launch_swap_half_p2p(h->stream, h->sm_count, state, peer_state, nqubits, dtype, nqubits - 1 - local_qubit, my_bit, part, nparts);
+  if (rc != QB_OK) return cuda_fail(cudaGetLastError(), "swap_half_p2p");
+  return QB_OK;
 }
 
 int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes) {

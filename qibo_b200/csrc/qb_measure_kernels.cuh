@@ -69,17 +69,23 @@ __global__ void __launch_bounds__(256) k3_probs(const C* __restrict__ state, R* 
   const uint64_t per = uint64_t(1) << per_bits;
   const bool valid = lane < (1 << p.nlow);
   double acc = 0.0;
-  uint64_t hu = split << per_bits;
+  // walk the unmeasured high bits with a masked increment: d -> ((d | ~mask) + 1) & mask  (no pdep per row)
+  const uint64_t um = p.uhigh_mask;
+  uint64_t d = deposit(split << per_bits, um);
   uint64_t it = 0;
   for (; it + 4 <= per; it += 4) {
     C v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_stream(state + (base | deposit(hu + it + u, p.uhigh_mask) | lane));
+    for (int u = 0; u < 4; ++u) {
+      v[u] = ld_stream(state + (base | d | lane));
+      d = ((d | ~um) + 1) & um;
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc += (double)cnorm2(v[u]);
   }
   for (; it < per; ++it) {
-    if (valid) acc += (double)cnorm2(ld_stream(state + (base | deposit(hu + it, p.uhigh_mask) | lane)));
+    if (valid) acc += (double)cnorm2(ld_stream(state + (base | d | lane)));
+    d = ((d | ~um) + 1) & um;
   }
   // fold unmeasured low bits
   for (int b = 0; b < 5; ++b)
@@ -88,6 +94,22 @@ __global__ void __launch_bounds__(256) k3_probs(const C* __restrict__ state, R* 
     uint64_t bin = out_index(base | lane, p);
     if (p.log_split == 0) out[bin] = (R)acc;
     else partial[split * p.nbins + bin] = acc;
+  }
+}
+
+// all qubits measured in ascending order: out[i] = |state[i]|^2, two amplitudes per thread and iteration
+template <typename C, typename R>
+__global__ void __launch_bounds__(256) k3_probs_full(const C* __restrict__ state, R* __restrict__ out, uint64_t count) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * 2;
+  for (uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < count; i += stride) {
+    const C a = ld_stream(state + i);
+    if (i + 1 < count) {
+      const C b = ld_stream(state + i + 1);
+      out[i] = (R)cnorm2(a);
+      out[i + 1] = (R)cnorm2(b);
+    } else {
+      out[i] = (R)cnorm2(a);
+    }
   }
 }
 

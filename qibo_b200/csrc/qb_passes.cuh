@@ -210,7 +210,7 @@ QB_HD void pass_regtile(C* tile, const char* blob, const PassHeader& ph, int T, 
   const uint32_t rmask = ph.rmask;
   uint32_t off[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) off[j] = deposit32((uint32_t)j, rmask);
+  for (int j = 0; j < D; ++j) off[j] = ph.off[j];
   const MicroOp* mops = reinterpret_cast<const MicroOp*>(blob + ph.offset);
   const int nmicro = (int)ph.nmicro;
   const int gbits = T - R;

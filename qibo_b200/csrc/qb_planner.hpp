@@ -82,7 +82,9 @@ struct PassHeader {
   uint16_t nmicro;
   uint16_t R;            // REGTILE: number of register bits of this pass
   uint32_t offset;       // byte offset of MicroOp[0] (REGTILE) or of the DevOp (BIG)
+  uint16_t off[16];      // REGTILE: tile-local offset of register index j (deposit of j into rmask), precomputed
 };
+static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligned");
 
 struct SweepHeader {
   uint32_t npasses;
@@ -293,6 +295,16 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
   ph.kind = PASS_REGTILE;
   ph.rmask = rmask;
   ph.R = (uint16_t)R;
+  for (int j = 0; j < (1 << R) && j < 16; ++j) {
+    uint32_t o = 0;
+    int kbit = 0;
+    for (int lb = 0; lb < T; ++lb)
+      if ((rmask >> lb) & 1) {
+        if ((j >> kbit) & 1) o |= 1u << lb;
+        ++kbit;
+      }
+    ph.off[j] = (uint16_t)o;
+  }
   std::vector<MicroOp> mops;
   const int pass_index = (int)sb.passes.size();
   for (const PlanOp* pp : ops) {

@@ -234,6 +234,50 @@ __global__ void __launch_bounds__(256) k7_half_copy(C* __restrict__ state, C* __
   }
 }
 
+// ---- K7: pairwise half-shard swap through NVLink peer memory ------------------------------------------------
+// mine[a] <-> peer[b] for every index i of this rank's share; 4 independent pairs in flight per thread (remote
+// latency is ~2 us: bytes in flight, not arithmetic, set the rate).
+template <typename C>
+__global__ void __launch_bounds__(256) k7_swap_half_p2p(C* __restrict__ mine, C* __restrict__ peer, int pos, int mybit, uint64_t begin,
+                                                        uint64_t end) {
+  constexpr int U = 4;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  const uint64_t ma = uint64_t(1 - mybit) << pos, mb = uint64_t(mybit) << pos;
+  for (uint64_t i0 = begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < end; i0 += stride * U) {
+    C x[U], y[U];
+    uint64_t base[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * stride;
+      base[u] = insert_zero(i, pos);
+      if (i < end) {
+        x[u] = ld_stream(mine + (base[u] | ma));
+        y[u] = ld_stream(peer + (base[u] | mb));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * stride;
+      if (i < end) {
+        st_stream(mine + (base[u] | ma), y[u]);
+        st_stream(peer + (base[u] | mb), x[u]);
+      }
+    }
+  }
+}
+
+inline int launch_swap_half_p2p(cudaStream_t stream, int sm_count, void* state, void* peer, int nqubits, int dtype, int pos, int mybit,
+                                int part, int nparts) {
+  const uint64_t half = uint64_t(1) << (nqubits - 1);
+  const uint64_t begin = half / nparts * part, end = part == nparts - 1 ? half : half / nparts * (part + 1);
+  const int grid = sm_count * 8;
+  if (dtype == QB_C128)
+    k7_swap_half_p2p<double2><<<grid, 256, 0, stream>>>((double2*)state, (double2*)peer, pos, mybit, begin, end);
+  else
+    k7_swap_half_p2p<float2><<<grid, 256, 0, stream>>>((float2*)state, (float2*)peer, pos, mybit, begin, end);
+  return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
+}
+
 inline int launch_half_copy(cudaStream_t stream, int sm_count, void* state, void* staging, int nqubits, int dtype, int pos, int bit,
                             int unpack) {
   const uint64_t half = uint64_t(1) << (nqubits - 1);

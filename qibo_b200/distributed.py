@@ -241,6 +241,35 @@ def exchange_half(state: torch.Tensor, nlocal: int, gbit: int, lbit: int, stagin
     return 2 * state.element_size() * (state.numel() // 2)  # bytes sent + received by this rank
 
 
+class PeerShard:
+    """This rank's shard in a CUDA-IPC exportable buffer, with every other rank's shard mapped into this process
+    (NVLink peer memory).  Lets the exchange run as ONE kernel per rank -- loads and stores on the partner's
+    memory -- instead of NCCL send/recv through staging buffers."""
+
+    def __init__(self, engine, nlocal: int, dtype):
+        import torch.distributed as dist
+
+        self.engine = engine
+        self.array = engine.malloc_exportable((1 << nlocal,), dtype)
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, engine.ipc_handle(self.array))
+        self.peer_ptr = {}
+        for r, h in enumerate(handles):
+            if r != dist.get_rank():
+                self.peer_ptr[r] = engine.ipc_open(h)
+        self.flag = torch.zeros(1, device=self.array.tensor.device)
+
+    def fence(self):
+        """Stream-ordered barrier across ranks: kernels enqueued after it start only when every rank's stream got here."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self.flag)
+
+    @property
+    def tensor(self):
+        return self.array.tensor
+
+
 class ShardedProgram:
     """A gate queue planned once for (n, world size) and specialised for this rank; ``run`` applies it to a shard."""
 
@@ -267,6 +296,14 @@ class ShardedProgram:
         self.ngates = len(ops)
 
     # ---- shard constructors --------------------------------------------------------------------
+    def peer_shard(self, index: Optional[int] = 0):
+        """A shard in peer-mapped memory (enables the single-kernel NVLink exchange), initialised to |index>."""
+        ps = PeerShard(self.engine, self.nlocal, self.dtype)
+        ps.tensor.zero_()
+        if index is not None and (index >> self.nlocal) == self.rank:
+            ps.tensor[index & ((1 << self.nlocal) - 1)] = 1
+        return ps
+
     def basis_state(self, index: int = 0):
         """|index> of the full register: the amplitude lives on rank index >> nlocal."""
         st = self.engine.basis_state(self.nlocal, self.dtype, 0)
@@ -291,6 +328,9 @@ class ShardedProgram:
 
     def run(self, state, timed: bool = True):
         """Apply the program to this rank's shard (DeviceArray, or a torch tensor with the test hook)."""
+        peer = state if isinstance(state, PeerShard) else None
+        if peer is not None:
+            state = peer.array
         tensor = state.tensor if hasattr(state, "tensor") else state
         out = RunStats()
         for seg in self.segments:
@@ -308,7 +348,15 @@ class ShardedProgram:
                 if tensor.is_cuda and timed:
                     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     t0.record()
-                out.exchange_bytes += exchange_half(tensor, self.nlocal, seg[1], seg[2], self._stage(tensor))
+                if peer is not None:
+                    j = seg[1] - self.nlocal
+                    b = (self.rank >> j) & 1
+                    peer.fence()
+                    self.engine.swap_half_p2p(state, peer.peer_ptr[self.rank ^ (1 << j)], self.nlocal, self.nlocal - 1 - seg[2], b, b, 2)
+                    peer.fence()
+                    out.exchange_bytes += tensor.element_size() * tensor.numel()
+                else:
+                    out.exchange_bytes += exchange_half(tensor, self.nlocal, seg[1], seg[2], self._stage(tensor))
                 out.nexchanges += 1
                 if t0 is not None:
                     t1.record()
@@ -321,6 +369,7 @@ class ShardedProgram:
         import torch.distributed as dist
 
         tensor = state.tensor if hasattr(state, "tensor") else state
+        tensor = tensor.clone()
         parts = [torch.empty_like(tensor) for _ in range(self.world)]
         dist.all_gather(parts, tensor)
         return torch.cat(parts).cpu().numpy()

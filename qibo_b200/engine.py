@@ -190,10 +190,56 @@ class Engine:
         )
         return state
 
+    # ---- K7 plumbing: IPC-exportable buffers and peer mappings -------------------------------------------------
+    def malloc_exportable(self, shape, dtype):
+        """A buffer from qb_malloc (plain cudaMalloc, exportable through CUDA IPC) viewed as a DeviceArray."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = count * dtype.itemsize
+        ptr = ctypes.c_void_p()
+        _lib.check(self.lib.qb_malloc(self.handle, nbytes, ctypes.byref(ptr)))
+        owner = _RawCuda(self, ptr.value, nbytes)
+        tensor = torch.as_tensor(owner, device=self.device).view(torch_dtype(dtype)).reshape(shape)
+        arr = DeviceArray(tensor)
+        arr._owner = owner
+        return arr
+
+    def ipc_handle(self, array: DeviceArray) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.qb_ipc_get_handle(self.handle, array.data_ptr(), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        _lib.check(self.lib.qb_ipc_open_handle(self.handle, ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)))
+        return ptr.value
+
+    def swap_half_p2p(self, state: DeviceArray, peer_ptr: int, nqubits: int, local_qubit: int, my_bit: int, part: int, nparts: int):
+        _lib.check(
+            self.lib.qb_swap_half_p2p(
+                self.handle, state.data_ptr(), ctypes.c_void_p(peer_ptr), nqubits, _DT[state.dtype], local_qubit, my_bit, part, nparts
+            )
+        )
+
     def mem_info(self):
         free, total = ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(self.lib.qb_mem_info(self.handle, ctypes.byref(free), ctypes.byref(total)))
         return free.value, total.value
+
+
+class _RawCuda:
+    """Owner of a qb_malloc'ed buffer, exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, engine, ptr, nbytes):
+        self.engine, self.ptr = engine, ptr
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def __del__(self):  # pragma: no cover
+        try:
+            if self.engine.handle:
+                self.engine.lib.qb_free(self.engine.handle, ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
 
 
 def plan_program(nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):

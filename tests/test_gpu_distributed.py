@@ -53,6 +53,13 @@ def _worker(rank, world, port, case, n, dtype, out):
         zfull = prog.gather(z)
         zref = oracle_run(orc.zero_state(n, dtype), ops, n)
         err = max(err, float(np.abs(zfull - zref).max()))
+        # the single-kernel NVLink peer-memory exchange must give the same state as the NCCL path
+        ps = prog.peer_shard(None)
+        ps.tensor.copy_(prog.scatter(psi).tensor)
+        st2 = prog.run(ps)
+        pfull = prog.gather(ps)
+        err = max(err, float(np.abs(pfull - ref).max()))
+        assert st2.nexchanges == stats.nexchanges
         if rank == 0:
             out.put((err, stats.nexchanges, stats.nsweeps))
     finally:
