@@ -118,6 +118,11 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
 int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program_stats* stats,
                     int32_t* sweep_of_op /* nops entries, may be NULL */);
 
+/* ---- K8: qubit permutation, out of place, one sweep (a run of SWAP gates such as the bit reversal ending
+ * models/qft.py:55-57; gates/gates.py:1669 SWAP).  dst[.. qubit dest_of_qubit[q] ..] = src[.. qubit q ..];
+ * src and dst must not overlap. */
+int qb_permute_qubits(qb_handle h, const void* src, void* dst, int nqubits, int dtype, const int* dest_of_qubit);
+
 /* ---- K3: probabilities and marginals (abstract.py:2734-2758 + _order_probabilities :3371-3381) ----
  * out[idx] with idx bits ordered as `qubits` (caller order, qubits[0] = MSB); out is a DEVICE buffer of
  * 2^nmeasured reals of the state's real dtype (float for complex64, double for complex128). */

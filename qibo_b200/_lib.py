@@ -64,6 +64,7 @@ PROTOTYPES = {
     "qb_apply_diagonal": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     "qb_apply_program": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(QbProgramStats)]),
     "qb_plan_program": (c_int, [c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(QbProgramStats), POINTER(c_int32)]),
+    "qb_permute_qubits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
     "qb_probabilities": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p]),
     "qb_cdf": (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_int]),
     "qb_sample_cdf": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p]),

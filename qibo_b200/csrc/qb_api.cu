@@ -15,6 +15,7 @@
 #include "qb_measure_kernels.cuh"
 #include "qb_planner.hpp"
 #include "qb_sweep.cuh"
+#include "qb_permute.cuh"
 
 using namespace qb;
 
@@ -511,6 +512,30 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
     QB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (stats) stats->elapsed_ms = ms;
   }
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K8
+// ---------------------------------------------------------------------------------------------------
+int qb_permute_qubits(qb_handle h, const void* src, void* dst, int nqubits, int dtype, const int* dest_of_qubit) {
+  if (!h || !valid_state_args(src, nqubits, dtype) || !dst || !dest_of_qubit || src == dst)
+    return fail(QB_ERR_INVALID, "bad permutation arguments");
+  int pi[64];
+  uint64_t seen = 0;
+  for (int q = 0; q < nqubits; ++q) {
+    int d = dest_of_qubit[q];
+    if (d < 0 || d >= nqubits || ((seen >> d) & 1)) return fail(QB_ERR_INVALID, "dest_of_qubit is not a permutation");
+    seen |= uint64_t(1) << d;
+    pi[nqubits - 1 - q] = nqubits - 1 - d;
+  }
+  PermParams p;
+  memset(&p, 0, sizeof(p));
+  const int lowbits = dtype == QB_C128 ? 6 : 6;  // 2^6 amplitudes: 1 KiB (complex128) / 512 B (complex64) contiguous on both sides
+  perm_setup(nqubits, lowbits, lowbits, pi, p);
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  if (launch_permute(h->stream, h->sm_count, src, dst, dtype, p) != QB_OK) return cuda_fail(cudaGetLastError(), "k8_permute");
   return QB_OK;
 }
 

@@ -48,6 +48,7 @@ class Engine:
         _lib.check(self.lib.qb_create(self.device_index, ctypes.c_void_p(stream), ctypes.byref(handle)))
         self.handle = handle
         self.last_stats = None
+        self.permute_swap_runs = True
 
     def close(self):
         if getattr(self, "handle", None):
@@ -123,8 +124,7 @@ class Engine:
         return state
 
     # ---- K2: a gate queue -------------------------------------------------------------------------
-    def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False):
-        """Apply ``ops`` in order, several gates per HBM sweep.  Returns the planner/timing statistics."""
+    def _apply_sweeps(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool, timed: bool):
         stats = _lib.QbProgramStats()
         if len(ops) == 0:
             return stats
@@ -136,8 +136,59 @@ class Engine:
             )
         )
         del keep
-        self.last_stats = stats
         return stats
+
+    def permute_qubits(self, state: DeviceArray, nqubits: int, dest_of_qubit: Sequence[int], timed: bool = False):
+        """K8: out-of-place qubit permutation in one sweep; the DeviceArray is re-pointed at the result buffer
+        (buffers that other ranks have mapped through CUDA IPC are copied back instead).  Returns elapsed ms or None."""
+        scratch = torch.empty_like(state.tensor)
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(
+            self.lib.qb_permute_qubits(
+                self.handle, state.data_ptr(), scratch.data_ptr(), nqubits, _DT[state.dtype], _int_array(dest_of_qubit)
+            )
+        )
+        if getattr(state, "_owner", None) is not None:
+            state.tensor.copy_(scratch)
+        else:
+            state.tensor = scratch
+        if timed:
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+        return None
+
+    def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False):
+        """Apply ``ops`` in order, several gates per HBM sweep.  Runs of >= MIN_SWAP_RUN uncontrolled SWAP gates (the
+        bit reversal ending a QFT) become ONE out-of-place permutation sweep when a scratch buffer fits in memory.
+        Returns the planner/timing statistics."""
+        total = _lib.QbProgramStats()
+        total.nops = len(ops)
+        segments = split_swap_runs(ops, nqubits) if fuse and self.permute_swap_runs else [("ops", list(ops))]
+        for kind, payload in segments:
+            if kind == "perm":
+                try:
+                    ms = self.permute_qubits(state, nqubits, payload, timed=timed)
+                except torch.cuda.OutOfMemoryError:
+                    ms = None
+                    payload = swaps_for_permutation(payload)
+                    kind = "ops"
+                else:
+                    total.nsweeps += 1
+                    total.ndense_passes += 1
+                    total.bytes_moved += 2.0 * state.nbytes
+                    total.elapsed_ms += ms or 0.0
+                    continue
+            st = self._apply_sweeps(state, nqubits, payload, fuse, timed)
+            total.nsweeps += st.nsweeps
+            total.ndense_passes += st.ndense_passes
+            total.ndiag_ops += st.ndiag_ops
+            total.bytes_moved += st.bytes_moved
+            total.elapsed_ms += st.elapsed_ms
+        self.last_stats = total
+        return total
 
     def plan(self, nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
         return plan_program(nqubits, dtype, ops, fuse)
@@ -252,6 +303,60 @@ def plan_program(nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
     _lib.check(lib.qb_plan_program(nqubits, _DT[np.dtype(dtype)], arr, len(ops), flags, ctypes.byref(stats), sweep_of_op))
     del keep
     return stats, list(sweep_of_op)[: len(ops)]
+
+
+MIN_SWAP_RUN = 3
+_SWAP_MATRIX = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+def is_plain_swap(op: Op) -> bool:
+    return (not op.is_diagonal) and len(op.targets) == 2 and not op.controls and np.array_equal(op.data, _SWAP_MATRIX)
+
+
+def split_swap_runs(ops: Sequence[Op], nqubits: int):
+    """-> [("ops", [...]) | ("perm", dest_of_qubit)]: maximal runs of >= MIN_SWAP_RUN plain SWAPs become permutations."""
+    out, cur, run = [], [], []
+
+    def close_run():
+        if len(run) >= MIN_SWAP_RUN:
+            if cur:
+                out.append(("ops", list(cur)))
+                cur.clear()
+            dest = list(range(nqubits))
+            for op in run:
+                a, b = op.targets
+                dest = [b if d == a else a if d == b else d for d in dest]
+            if dest != list(range(nqubits)):
+                out.append(("perm", dest))
+        else:
+            cur.extend(run)
+        run.clear()
+
+    for op in ops:
+        if is_plain_swap(op):
+            run.append(op)
+        else:
+            close_run()
+            cur.append(op)
+    close_run()
+    if cur:
+        out.append(("ops", cur))
+    return out
+
+
+def swaps_for_permutation(dest_of_qubit: Sequence[int]):
+    """SWAP gates realising the permutation (fallback when no scratch buffer fits)."""
+    dest = list(dest_of_qubit)
+    ops = []
+    # data at slot q must go to slot dest[q]: cycle decomposition into transpositions
+    cur = list(range(len(dest)))  # cur[s] = original slot of the data now sitting in slot s
+    for s in range(len(dest)):
+        want = dest.index(s)  # original slot whose data belongs in s
+        at = cur.index(want)
+        if at != s:
+            ops.append(Op(_SWAP_MATRIX, (s, at)))
+            cur[s], cur[at] = cur[at], cur[s]
+    return ops
 
 
 def frequencies_from_samples(samples: np.ndarray) -> Counter:

@@ -73,3 +73,16 @@ def canon_kind(nqubits, op):
     if rc != 0:
         raise ValueError(lib.emul_last_error().decode())
     return kind.value, nt.value, nc.value
+
+
+def permute_qubits(state, nqubits, dest_of_qubit):
+    from qibo_b200 import _lib
+
+    lib = load()
+    src = np.ascontiguousarray(state)
+    dst = np.empty_like(src)
+    arr = (ctypes.c_int * nqubits)(*[int(d) for d in dest_of_qubit])
+    lib.emul_permute_qubits.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    rc = lib.emul_permute_qubits(src.ctypes.data, dst.ctypes.data, nqubits, _lib.QB_C128 if src.dtype == np.complex128 else _lib.QB_C64, arr)
+    assert rc == 0
+    return dst

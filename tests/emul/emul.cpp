@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../qibo_b200/csrc/qb_passes.cuh"
+#include "../../qibo_b200/csrc/qb_permute.cuh"
 
 using namespace qb;
 
@@ -100,5 +101,46 @@ extern "C" int emul_canon_kind(int nqubits, const double* data, int is_diag, int
   *kind = c.kind;
   *ntargets = (int)c.tpos.size();
   *ncontrols = (int)c.cpos.size();
+  return QB_OK;
+}
+
+// K8 data path: the kernel's per-thread loops (thread id = 8 low tile bits, masked increment for the rest)
+template <typename C> static void run_permute(const C* src, C* dst, const PermParams& p) {
+  const uint32_t tsize = 1u << p.tbits;
+  const uint32_t iters = tsize > PERM_THREADS ? tsize / PERM_THREADS : 1;
+  const uint64_t other = ~p.smask & ((uint64_t(1) << p.n) - 1);
+  uint64_t s_lo, s_hi, d_lo, d_hi;
+  split_mask8(p.smask, s_lo, s_hi);
+  split_mask8(p.dmask, d_lo, d_hi);
+  std::vector<C> tile(tsize);
+  for (uint64_t t = 0; t < p.ntiles; ++t) {
+    const uint64_t sbase = deposit(t, other), dbase = permute_base(sbase, p);
+    for (uint32_t tid = 0; tid < (uint32_t)PERM_THREADS && tid < tsize; ++tid) {
+      uint64_t hi = 0;
+      for (uint32_t k = 0; k < iters; ++k) {
+        tile[tid + k * PERM_THREADS] = src[sbase | deposit(tid, s_lo) | hi];
+        hi = ((hi | ~s_hi) + 1) & s_hi;
+      }
+    }
+    for (uint32_t tid = 0; tid < (uint32_t)PERM_THREADS && tid < tsize; ++tid) {
+      uint64_t hi = 0;
+      const uint32_t e_lo = perm_e_of_f(tid & (tsize - 1), p);
+      for (uint32_t k = 0; k < iters; ++k) {
+        const uint32_t e = e_lo | perm_e_of_f((k * PERM_THREADS) & (tsize - 1), p);
+        dst[dbase | deposit(tid, d_lo) | hi] = tile[e];
+        hi = ((hi | ~d_hi) + 1) & d_hi;
+      }
+    }
+  }
+}
+
+extern "C" int emul_permute_qubits(const void* src, void* dst, int nqubits, int dtype, const int* dest_of_qubit) {
+  int pi[64];
+  for (int q = 0; q < nqubits; ++q) pi[nqubits - 1 - q] = nqubits - 1 - dest_of_qubit[q];
+  PermParams p;
+  memset(&p, 0, sizeof(p));
+  perm_setup(nqubits, 6, 6, pi, p);
+  if (dtype == QB_C128) run_permute<double2>((const double2*)src, (double2*)dst, p);
+  else run_permute<float2>((const float2*)src, (float2*)dst, p);
   return QB_OK;
 }

@@ -293,3 +293,31 @@ def test_error_mapping(eng):
         eng.probabilities(st, [0, 0], 4)
     with pytest.raises(ValueError):
         eng.collapse(st, 4, [1], 2)
+
+
+# ------------------------------------------------------------------------------------------ K8
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [1, 2, 5, 12, 13, 18, 21])
+def test_permute_qubits(eng, n, dtype):
+    """Out-of-place permutation sweep == the axis transposition NumPy does; a run of SWAP gates is one such sweep."""
+    rng = np.random.default_rng(n)
+    psi = rand_state(n, n, dtype)
+    perms = [list(range(n - 1, -1, -1))] + [rng.permutation(n).tolist() for _ in range(3)]
+    for dest in perms:
+        st = eng.upload(psi)
+        eng.permute_qubits(st, n, dest)
+        ref = np.moveaxis(psi.reshape(n * (2,)), list(range(n)), dest).reshape(-1)
+        np.testing.assert_array_equal(st.numpy(), ref)
+    if n >= 6:
+        named = [("SWAP", (q, n - 1 - q), ()) for q in range(n // 2)]
+        st = eng.upload(psi)
+        stats = eng.apply_program(st, n, ops_from_named(named))
+        assert stats.nsweeps == 1
+        np.testing.assert_array_equal(st.numpy(), orc.run_ops(psi, named, n, dtype=dtype))
+        eng.permute_swap_runs = False
+        try:
+            st = eng.upload(psi)
+            eng.apply_program(st, n, ops_from_named(named))
+            np.testing.assert_array_equal(st.numpy(), orc.run_ops(psi, named, n, dtype=dtype))
+        finally:
+            eng.permute_swap_runs = True

@@ -109,3 +109,24 @@ def test_fused_reference_queue(golden):
         ops = [Op(golden[f"circ{i}_q{j}"], tuple(q)) for j, q in enumerate(c["queue"])]
         out, _ = emul.apply_program(psi, c["nqubits"], ops)
         assert np.abs(out - golden[f"circ{i}_out"]).max() < tol(c["dtype"]), c["tag"]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [1, 3, 6, 9, 13, 16])
+def test_permute_qubits(n, dtype):
+    """K8 index math: dst[.. qubit dest[q] ..] = src[.. qubit q ..] equals the transpose NumPy does."""
+    rng = np.random.default_rng(n)
+    psi = rand_state(n, n, dtype)
+    perms = [list(range(n)), list(range(n - 1, -1, -1))] + [rng.permutation(n).tolist() for _ in range(4)]
+    for dest in perms:
+        out = emul.permute_qubits(psi, n, dest)
+        # axis q of the source becomes axis dest[q] of the destination
+        ref = np.moveaxis(psi.reshape(n * (2,)), list(range(n)), dest).reshape(-1)
+        np.testing.assert_array_equal(out, ref)
+    # a run of SWAP gates is such a permutation
+    named = [("SWAP", (q, n - 1 - q), ()) for q in range(n // 2)]
+    if named:
+        dest = list(range(n))
+        for _, (a, b), _ in named:
+            dest = [b if d == a else a if d == b else d for d in dest]
+        np.testing.assert_array_equal(emul.permute_qubits(psi, n, dest), orc.run_ops(psi, named, n, dtype=dtype))
