@@ -286,6 +286,41 @@ def run_gpu(args):
         e2e = {"value": n_gates(n) * args.steps / dt, "unit": "gates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "Engine.basis_state + apply_program(host gate matrices) + probabilities(10 qubits) -> host"}
 
+    else:
+        # N > 1: fresh zero shards, host gate program in (specialised per rank), global norm out (all-reduce + D2H)
+        h2d = sum(op.data.nbytes for seg in runner.segments if seg[0] == "local" for op in seg[1]) + 176 * sum(
+            len(seg[1]) for seg in runner.segments if seg[0] == "local")
+
+        def e2e_step():
+            if args.exchange == "nccl":
+                st = runner.basis_state()
+            else:
+                st = state
+                st.tensor.zero_()
+                if rank == 0:
+                    st.tensor[0] = 1
+            runner.run(st, timed=False)
+            arr = st.array if hasattr(st, "array") else st
+            nrm = torch.tensor([eng.norm2(arr)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(nrm)
+            return float(nrm.item())
+
+        e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            nrm = e2e_step()
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        assert abs(nrm - 1.0) < 1e-9, nrm
+        e2e = {"value": world * n_gates(n) * args.steps / dt, "unit": "gates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+               "api": "zero shards + ShardedProgram.run(host gate matrices, per-rank specialisation) + global norm (all-reduce) -> host"}
+
     cpu = cpu_reference_sample(n, args.dtype, budget_s=args.cpu_budget) if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:
         line = {

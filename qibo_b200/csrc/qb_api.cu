@@ -473,6 +473,22 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
   std::vector<CanonOp> canon;
   int rc = canonicalize_program(nqubits, ops, nops, canon);
   if (rc != QB_OK) return rc;
+  if (nqubits < 3) {
+    // 2- and 4-amplitude states: nothing to tile; the K1 kernels apply the queue gate by gate
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->nops = nops;
+      stats->nsweeps = nops;
+      stats->bytes_moved = (double)nops * 2.0 * (dtype == QB_C128 ? 16.0 : 8.0) * (double)(uint64_t(1) << nqubits);
+    }
+    for (auto& c : canon) {
+      rc = dtype == QB_C128 ? apply_canon_k1<double2>(h, state, nqubits, c) : apply_canon_k1<float2>(h, state, nqubits, c);
+      if (rc != QB_OK) return rc;
+    }
+    return QB_OK;
+  }
   Plan plan;
   std::string err;
   if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, err)) return fail(QB_ERR_UNSUPPORTED, err);

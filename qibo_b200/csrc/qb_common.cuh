@@ -2,6 +2,7 @@
 // Everything here is QB_HD so that tests/emul can compile the *same* index math for the CPU.
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define QB_HD __host__ __device__ __forceinline__
@@ -37,6 +38,16 @@ template <typename C> QB_HD void cfma(C& acc, C a, C b) {
   acc.y += a.x * b.y; acc.y += a.y * b.x;
 }
 template <typename C> QB_HD typename real_of<C>::type cnorm2(C a) { return a.x * a.x + a.y * a.y; }
+
+// explicit fused multiply-add (DFMA / FFMA); std::fma on the host
+QB_HD double qfma(double a, double b, double c) { return fma(a, b, c); }
+QB_HD float qfma(float a, float b, float c) { return fmaf(a, b, c); }
+// v *= ph, written so that the results land in v's own registers (two temporaries, no register moves)
+template <typename C> QB_HD void cmul_inplace(C& v, const C ph) {
+  const typename real_of<C>::type t = v.y * ph.y, u = v.x * ph.y;
+  v.x = qfma(v.x, ph.x, -t);
+  v.y = qfma(v.y, ph.x, u);
+}
 
 // ---- bit utilities --------------------------------------------------------------------------------
 // insert a zero bit at position p (bits >= p move up by one)

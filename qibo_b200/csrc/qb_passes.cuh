@@ -52,18 +52,32 @@ QB_HD void mu_dense1_static(C* v, const C m00, const C m01, const C m10, const C
   for (int j0 = 0; j0 < D; ++j0) {
     if ((j0 & (1 << I)) || (j0 & CREG) != CREG) continue;  // compile-time
     const int j1 = j0 | (1 << I);
-    const C a = v[j0], b = v[j1];
+    // cross terms first (temporaries), then one FMA per output INTO the register that holds its own input:
+    // the results need no register moves (ncu: the naive form spent one IMAD.MOV per FP64 pair)
+    C& a = v[j0];
+    C& b = v[j1];
     if (REAL) {
       const Re r00 = m00.x, r01 = m01.x, r10 = m10.x, r11 = m11.x;
-      v[j0] = cmake<C>(r00 * a.x + r01 * b.x, r00 * a.y + r01 * b.y);
-      v[j1] = cmake<C>(r10 * a.x + r11 * b.x, r10 * a.y + r11 * b.y);
+      const Re tx = r01 * b.x, ty = r01 * b.y, ux = r10 * a.x, uy = r10 * a.y;
+      a.x = qfma(r00, a.x, tx);
+      a.y = qfma(r00, a.y, ty);
+      b.x = qfma(r11, b.x, ux);
+      b.y = qfma(r11, b.y, uy);
     } else {
-      C x = cmul(m00, a);
-      cfma(x, m01, b);
-      C y = cmul(m10, a);
-      cfma(y, m11, b);
-      v[j0] = x;
-      v[j1] = y;
+      // x = m00 a + m01 b ; y = m10 a + m11 b
+      Re xr = m01.x * b.x, xi = m01.x * b.y, yr = m10.x * a.x, yi = m10.x * a.y;
+      xr = qfma(-m01.y, b.y, xr);
+      xi = qfma(m01.y, b.x, xi);
+      yr = qfma(-m10.y, a.y, yr);
+      yi = qfma(m10.y, a.x, yi);
+      xr = qfma(-m00.y, a.y, xr);
+      xi = qfma(m00.y, a.x, xi);
+      yr = qfma(-m11.y, b.y, yr);
+      yi = qfma(m11.y, b.x, yi);
+      a.x = qfma(m00.x, a.x, xr);
+      a.y = qfma(m00.x, a.y, xi);
+      b.x = qfma(m11.x, b.x, yr);
+      b.y = qfma(m11.x, b.y, yi);
     }
   }
 }
@@ -164,14 +178,20 @@ template <typename C, int R, uint32_t CREG> QB_HD void mu_fan_static(C* v, const
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     if ((uint32_t(j) & CREG) != CREG) continue;  // compile-time
-    v[j] = cmul(v[j], cmul(p0, gt[j]));
+    cmul_inplace(v[j], cmul(p0, gt[j]));
   }
 }
-template <typename C, int R, uint32_t CREG> QB_HD void mu_fan_dispatch(C* v, const C p0, const C* gt, uint32_t creg) {
-  if constexpr (CREG < (1u << R)) {
-    if (creg == CREG) mu_fan_static<C, R, CREG>(v, p0, gt);
-    else mu_fan_dispatch<C, R, CREG + 1>(v, p0, gt, creg);
+template <typename C, int R> QB_HD void mu_fan_dispatch(C* v, const C p0, const C* gt, uint32_t creg) {
+#define QB_FAN(CR) \
+  case CR:         \
+    if constexpr ((CR) < (1 << R)) mu_fan_static<C, R, CR>(v, p0, gt); \
+    break;
+  switch (creg) {  // one jump table instead of a compare chain
+    QB_FAN(0) QB_FAN(1) QB_FAN(2) QB_FAN(3) QB_FAN(4) QB_FAN(5) QB_FAN(6) QB_FAN(7)
+    QB_FAN(8) QB_FAN(9) QB_FAN(10) QB_FAN(11) QB_FAN(12) QB_FAN(13) QB_FAN(14) QB_FAN(15)
+    default: break;
   }
+#undef QB_FAN
 }
 template <typename C, int R>
 QB_HD void mu_fan(C* v, const C* ta, uint32_t la, int gbits, C ext_factor, uint32_t creg, uint32_t g) {
@@ -179,7 +199,29 @@ QB_HD void mu_fan(C* v, const C* ta, uint32_t la, int gbits, C ext_factor, uint3
   const C* gt = tb + (1u << (gbits - (int)la));
   C p0 = cmul(ext_factor, ta[g & ((1u << la) - 1)]);
   p0 = cmul(p0, tb[g >> la]);
-  mu_fan_dispatch<C, R, 0>(v, p0, gt, creg);
+  mu_fan_dispatch<C, R>(v, p0, gt, creg);
+}
+
+// lone controlled phase: v[j] *= ph on the register indices whose control bits are set
+template <typename C, int R, uint32_t CREG> QB_HD void mu_phase_static(C* v, const C ph) {
+  constexpr int D = 1 << R;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    if ((uint32_t(j) & CREG) != CREG) continue;  // compile-time
+    cmul_inplace(v[j], ph);
+  }
+}
+template <typename C, int R> QB_HD void mu_phase(C* v, const C ph, uint32_t creg) {
+#define QB_PH(CR) \
+  case CR:        \
+    if constexpr ((CR) < (1 << R)) mu_phase_static<C, R, CR>(v, ph); \
+    break;
+  switch (creg) {
+    QB_PH(0) QB_PH(1) QB_PH(2) QB_PH(3) QB_PH(4) QB_PH(5) QB_PH(6) QB_PH(7)
+    QB_PH(8) QB_PH(9) QB_PH(10) QB_PH(11) QB_PH(12) QB_PH(13) QB_PH(14) QB_PH(15)
+    default: break;
+  }
+#undef QB_PH
 }
 
 template <typename C, int R> QB_HD void mu_diagk(C* v, const MicroOp& mo, const char* blob, uint32_t aux, uint32_t t0) {
@@ -264,6 +306,12 @@ QB_HD void pass_regtile(C* tile, const char* blob, const PassHeader& ph, int T, 
 #pragma unroll
           for (int u = 0; u < GPT; ++u)
             if (run[u]) mu_diagk<C, R>(v[u], mo, blob, mo.aux, t0[u]);
+        } break;
+        case MU_PHASE: {
+          const C ph = *reinterpret_cast<const C*>(mo.inl);
+#pragma unroll
+          for (int u = 0; u < GPT; ++u)
+            if (run[u]) mu_phase<C, R>(v[u], ph, hot.creg);
         } break;
         default: break;
       }

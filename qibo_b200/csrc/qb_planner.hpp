@@ -27,7 +27,7 @@ namespace qb {
 // bits": every thread owns groups of 2^R amplitudes that differ only in those bits, loads them once,
 // applies the pass's whole list of MICRO-OPS in registers and stores them once.  A BIG pass applies one
 // dense gate on 3..6 targets (threads share a group, inputs re-read from shared memory).
-enum MicroType { MU_DENSE1 = 1, MU_DENSE2 = 2, MU_SWAP = 3, MU_FAN = 4, MU_DIAGK = 5 };
+enum MicroType { MU_DENSE1 = 1, MU_DENSE2 = 2, MU_SWAP = 3, MU_FAN = 4, MU_DIAGK = 5, MU_PHASE = 6 };
 enum PassKind { PASS_REGTILE = 1, PASS_BIG = 2 };
 
 constexpr int SWEEP_MAX_SLOTS = 96;        // micro-ops (+ big ops) per sweep that need per-tile set-up
@@ -353,6 +353,14 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
         else m.tbit[i] = (uint8_t)sb.local_of_pos[pos];
       }
       for (auto& v : p.data) payload.push_back(to_dev<C>(v));
+    } else if (p.fan.size() == 1 && p.fan.begin()->second.first == cd(1.0, 0.0)) {
+      // a lone controlled phase (CZ, CU1, Z, T...): scalar on the slice where all of its bits are 1
+      m.type = MU_PHASE;
+      int pos = p.fan.begin()->first;
+      if (!((sb.tile_mask >> pos) & 1)) m.ext_cmask |= uint64_t(1) << pos;
+      else if (rbit_of_local[sb.local_of_pos[pos]] >= 0) m.creg |= 1u << rbit_of_local[sb.local_of_pos[pos]];
+      else m.cthr |= 1u << sb.local_of_pos[pos];
+      *reinterpret_cast<C*>(m.inl) = to_dev<C>(p.scalar * p.fan.begin()->second.second);
     } else {  // fan
       m.type = MU_FAN;
       m.scalar[0] = p.scalar.real();

@@ -61,6 +61,16 @@ QB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 20000000000LL) __trap();
   }
 }
+// for the copy warps: they wait for whole tile periods, so back off between polls instead of competing with the
+// compute warps of their scheduler for issue slots
+QB_D void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(1000);
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
 QB_D void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
     for (uint64_t i = 0; i < my_n; ++i) {
       const int b = (int)(i % SW_NBUF);
       // buffer b was last used by tile i-3: wait until the storer has drained it
-      if (i >= SW_NBUF) mbar_wait(&freeb[b], (uint32_t)(((i / SW_NBUF) - 1) & 1));
+      if (i >= SW_NBUF) mbar_wait_sleep(&freeb[b], (uint32_t)(((i / SW_NBUF) - 1) & 1));
       if (lane == 0) mbar_expect_tx(&full[b], tile_bytes);
       __syncwarp();
       const C* gbase = state + deposit(blockIdx.x + i * gridDim.x, hdr.other_mask);
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
     const int lane = tid - 32;
     for (uint64_t j = 0; j < my_n; ++j) {
       const int b = (int)(j % SW_NBUF);
-      mbar_wait(&done[b], (uint32_t)((j / SW_NBUF) & 1));
+      mbar_wait_sleep(&done[b], (uint32_t)((j / SW_NBUF) & 1));
       C* gbase = state + deposit(blockIdx.x + j * gridDim.x, hdr.other_mask);
       const C* sbase = tiles + (size_t)b * tile_elems;
       for (uint32_t r = lane; r < nruns; r += 32) bulk_s2g(gbase + run_off[r], sbase + ((size_t)r << L), run_bytes);
@@ -174,8 +184,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
         const PassHeader& ph = passes[pi];
         if (ph.kind == PASS_REGTILE) {
           switch (ph.R) {
-            case 1: run_regtile<C, 1>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
-            case 2: run_regtile<C, 2>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
+            // R < 3 only occurs for n < 3, which qb_apply_program routes to the K1 kernels
             case 3: run_regtile<C, 3>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
             default: run_regtile<C, 4>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
           }
@@ -237,10 +246,9 @@ __global__ void __launch_bounds__(256) k7_half_copy(C* __restrict__ state, C* __
 // ---- K7: pairwise half-shard swap through NVLink peer memory ------------------------------------------------
 // mine[a] <-> peer[b] for every index i of this rank's share; 4 independent pairs in flight per thread (remote
 // latency is ~2 us: bytes in flight, not arithmetic, set the rate).
-template <typename C>
+template <typename C, int U>
 __global__ void __launch_bounds__(256) k7_swap_half_p2p(C* __restrict__ mine, C* __restrict__ peer, int pos, int mybit, uint64_t begin,
                                                         uint64_t end) {
-  constexpr int U = 4;
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   const uint64_t ma = uint64_t(1 - mybit) << pos, mb = uint64_t(mybit) << pos;
   for (uint64_t i0 = begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < end; i0 += stride * U) {
@@ -270,11 +278,16 @@ inline int launch_swap_half_p2p(cudaStream_t stream, int sm_count, void* state, 
                                 int part, int nparts) {
   const uint64_t half = uint64_t(1) << (nqubits - 1);
   const uint64_t begin = half / nparts * part, end = part == nparts - 1 ? half : half / nparts * (part + 1);
-  const int grid = sm_count * 8;
-  if (dtype == QB_C128)
-    k7_swap_half_p2p<double2><<<grid, 256, 0, stream>>>((double2*)state, (double2*)peer, pos, mybit, begin, end);
-  else
-    k7_swap_half_p2p<float2><<<grid, 256, 0, stream>>>((float2*)state, (float2*)peer, pos, mybit, begin, end);
+  const int grid = sm_count * env_int("QB_P2P_BLOCKS_PER_SM", 8);
+  const int unroll = env_int("QB_P2P_UNROLL", 4);
+  if (dtype == QB_C128) {
+    if (unroll >= 8) k7_swap_half_p2p<double2, 8><<<grid, 256, 0, stream>>>((double2*)state, (double2*)peer, pos, mybit, begin, end);
+    else if (unroll >= 4) k7_swap_half_p2p<double2, 4><<<grid, 256, 0, stream>>>((double2*)state, (double2*)peer, pos, mybit, begin, end);
+    else k7_swap_half_p2p<double2, 2><<<grid, 256, 0, stream>>>((double2*)state, (double2*)peer, pos, mybit, begin, end);
+  } else {
+    if (unroll >= 8) k7_swap_half_p2p<float2, 8><<<grid, 256, 0, stream>>>((float2*)state, (float2*)peer, pos, mybit, begin, end);
+    else k7_swap_half_p2p<float2, 4><<<grid, 256, 0, stream>>>((float2*)state, (float2*)peer, pos, mybit, begin, end);
+  }
   return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
 }
 
