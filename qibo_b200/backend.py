@@ -32,6 +32,7 @@ from qibo.result import CircuitResult, MeasurementOutcomes, QuantumState
 
 from qibo_b200 import _lib
 from qibo_b200.array import DeviceArray
+from qibo_b200.array import torch_dtype as torch_dtype_of
 from qibo_b200.engine import Engine, frequencies_from_samples
 from qibo_b200.ops import Op
 
@@ -93,7 +94,12 @@ class B200Backend(NumpyBackend):
     @property
     def _cdtype(self):
         """complex dtype the state is held in (float32/float64 backends hold a complex state)."""
-        return _COMPLEX[str(np.dtype(self.dtype))] if not isinstance(self.dtype, str) else _COMPLEX[self.dtype]
+        return _COMPLEX[str(np.dtype(self.dtype))]
+
+    @property
+    def _real_dtype(self):
+        d = np.dtype(self.dtype)
+        return d if d.kind == "f" else None
 
     # ------------------------------------------------------------------ casting / interop -----------
     def is_device(self, x):
@@ -138,17 +144,20 @@ class B200Backend(NumpyBackend):
         return d if d.kind == "c" else (np.dtype("complex64") if d == np.float32 else np.dtype("complex128"))
 
     def zero_state(self, nqubits, density_matrix=False, dtype=None):
+        self._validate_nqubits(nqubits, density_matrix=density_matrix)
         n = 2 * nqubits if density_matrix else nqubits
         state = self.engine_gpu.basis_state(n, self._state_dtype(dtype), 0)
         return state.reshape(2**nqubits, 2**nqubits) if density_matrix else state
 
     def plus_state(self, nqubits, density_matrix=False, dtype=None):
+        self._validate_nqubits(nqubits, density_matrix=density_matrix)
         n = 2 * nqubits if density_matrix else nqubits
         value = 1.0 / 2**nqubits if density_matrix else 1.0 / np.sqrt(2**nqubits)
         state = self.engine_gpu.filled_state(n, value, self._state_dtype(dtype))
         return state.reshape(2**nqubits, 2**nqubits) if density_matrix else state
 
     def minus_state(self, nqubits, density_matrix=False, dtype=None):
+        self._validate_nqubits(nqubits, density_matrix=density_matrix)
         # |-> on every qubit = Z on every qubit of |+...+>
         state = self.plus_state(nqubits, density_matrix=False, dtype=dtype)
         z = np.array([1, -1], dtype=np.complex128)
@@ -210,7 +219,7 @@ class B200Backend(NumpyBackend):
         """True for gates whose apply() is Gate.apply -> backend.apply_gate (everything but M, callbacks, channels)."""
         return type(gate).apply is Gate.apply
 
-    def _run_queue(self, queue, state, nqubits, density_matrix):
+    def _run_queue(self, queue, state, nqubits, density_matrix, substitute_symbols=False):
         """The gate loop of _execute_circuit (abstract.py:3321-3322), with maximal runs of plain gates handed
         to the sweep planner in one C call."""
         flat_n = 2 * nqubits if density_matrix else nqubits
@@ -220,10 +229,15 @@ class B200Backend(NumpyBackend):
             if pending:
                 flat = st.reshape(-1) if density_matrix else st
                 self.engine_gpu.apply_program(flat, flat_n, pending)
+                if flat is not st and flat.tensor.data_ptr() != st.tensor.data_ptr():
+                    st.tensor = flat.tensor.reshape(st.shape)  # a permutation sweep re-pointed the flat view
                 pending.clear()
             return st
 
         for gate in queue:
+            if substitute_symbols and gate.symbolic_parameters:
+                # abstract.py:2590-2592: evaluated in queue order, i.e. after the collapses they depend on
+                gate.substitute_symbols()
             if self._is_plain(gate):
                 pending.extend(self._gate_ops(gate, nqubits, density_matrix))
             else:
@@ -244,6 +258,11 @@ class B200Backend(NumpyBackend):
             if state is initial_state:
                 state = state.copy()
         state = self._run_queue(circuit.queue, state, nqubits, density_matrix)
+        init_dtype = getattr(initial_state, "dtype", None) if initial_state is not None else None
+        if self._real_dtype is not None and (init_dtype is None or np.dtype(init_dtype).kind != "c"):
+            # float32/float64 backends (real-matrix circuits, abstract.py:133-179): the kernels hold a complex state of
+            # the same precision; hand back its real part in the backend's dtype (tests/test_backends_global.py:42-77)
+            state = DeviceArray(state.tensor.real.contiguous().to(torch_dtype_of(self._real_dtype)))
 
         if circuit.measurements:
             circuit._final_state = CircuitResult(state, circuit.measurements, backend=self, nshots=nshots)
@@ -314,10 +333,7 @@ class B200Backend(NumpyBackend):
 
         for _ in range(nshots):
             state = state_copy.copy()
-            for gate in circuit.queue:
-                if gate.symbolic_parameters:
-                    gate.substitute_symbols()
-            state = self._run_queue(circuit.queue, state, nqubits, density_matrix)
+            state = self._run_queue(circuit.queue, state, nqubits, density_matrix, substitute_symbols=True)
             if density_matrix:
                 final_states.append(state)
             if circuit.measurements:
@@ -354,6 +370,12 @@ class B200Backend(NumpyBackend):
         this GPU and the circuit runs as one shard -- same results, same return types."""
         from qibo_b200 import distributed
 
+        # The reference marks a distributed circuit as "planned/executed" through its queues object
+        # (models/circuit.py:357-361 refuses to reuse it as a subroutine afterwards).  Our planner never touches the
+        # caller's gate objects, so only the marker is reproduced.
+        queues = getattr(circuit, "queues", None)
+        if queues is not None and not queues.queues:
+            queues.queues = [[]]
         if distributed.world_size() > 1:
             return distributed.execute_circuit(self, circuit, initial_state, nshots)
         try:

@@ -34,6 +34,7 @@ constexpr int SWEEP_MAX_SLOTS = 96;        // micro-ops (+ big ops) per sweep th
 constexpr int SWEEP_BLOB_MAX = 29 * 1024;  // program bytes resident in shared memory next to the tiles
 constexpr int SWEEP_TILE_BYTES_LOG2 = 16;  // 64 KiB tiles, three in flight per SM
 constexpr int MU_REAL = 1;                 // flags: the 2x2 / 4x4 matrix is real
+constexpr size_t BIG_PAYLOAD_SMEM_MAX = 16 * 1024 + 64;  // larger dense matrices (6 targets) stay in global memory
 
 struct MicroOp {
   // ---- hot header: one 16-byte shared-memory load decodes the op ------------------------------------
@@ -72,7 +73,8 @@ struct DevOp {           // BIG pass: one dense gate on k = 3..6 tile-local targ
   uint32_t payload;      // matrix
   uint32_t slot;
   uint8_t tbit[8];       // tile-local bit of target i (tbit[0] = MSB of the matrix index)
-  uint64_t pad2;
+  uint32_t payload_global;  // 1: the matrix is too large for shared memory and is read from the global copy of the blob
+  uint32_t pad2;
 };
 static_assert(sizeof(DevOp) % 16 == 0, "DevOp must stay 16-byte aligned");
 
@@ -245,8 +247,11 @@ inline int regtile_bits_for(int dtype) { (void)dtype; return env_int("QB_REGTILE
 // upper bound of the blob bytes a PlanOp needs (independent of the tile)
 inline size_t blob_estimate(const PlanOp& p, int csize, int T, int R) {
   switch (p.kind) {
-    case CK_DENSE:
-      return (p.tpos.size() <= 2 ? sizeof(MicroOp) : sizeof(DevOp) + sizeof(PassHeader)) + align16(p.data.size() * csize);
+    case CK_DENSE: {
+      size_t pay = align16(p.data.size() * csize);
+      if (pay > BIG_PAYLOAD_SMEM_MAX) pay = 0;  // kept in global memory
+      return (p.tpos.size() <= 2 ? sizeof(MicroOp) : sizeof(DevOp) + sizeof(PassHeader)) + pay;
+    }
     case CK_SWAP: return sizeof(MicroOp);
     case CK_DIAG: return sizeof(MicroOp) + align16(p.data.size() * csize);
     default: {  // fan: TA + TB + G + ext tables of <= 5 bits
@@ -443,6 +448,7 @@ template <typename C> inline bool emit_big_pass(SweepBuilder<C>& sb, const PlanO
   for (int b : ins) d.ins_mask |= 1u << b;
   std::vector<C> payload;
   for (auto& v : p.data) payload.push_back(to_dev<C>(v));
+  d.payload_global = payload.size() * sizeof(C) > BIG_PAYLOAD_SMEM_MAX ? 1u : 0u;
   d.slot = (uint32_t)sb.payloads.size();
   PassHeader ph;
   memset(&ph, 0, sizeof(ph));
@@ -467,13 +473,21 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
   off += align16(sb.payloads.size() * sizeof(uint32_t));
   for (size_t s = 0; s < sb.payloads.size(); ++s) {
     auto own = sb.slot_owner[s];
+    if (own.second < 0 && sb.big[own.first].payload_global) continue;
     if (own.second < 0) sb.big[own.first].payload = (uint32_t)off;
     else sb.micro[own.first][own.second].payload = (uint32_t)off;
     off += align16(sb.payloads[s].size() * sizeof(C));
   }
   hdr.npasses = (uint32_t)sb.passes.size();
   hdr.nslots = (uint32_t)sb.payloads.size();
-  hdr.blob_bytes = (uint32_t)off;
+  hdr.blob_bytes = (uint32_t)off;  // the part the kernel copies to shared memory
+  for (size_t s = 0; s < sb.payloads.size(); ++s) {  // large matrices follow; read through the global pointer
+    auto own = sb.slot_owner[s];
+    if (own.second < 0 && sb.big[own.first].payload_global) {
+      sb.big[own.first].payload = (uint32_t)off;
+      off += align16(sb.payloads[s].size() * sizeof(C));
+    }
+  }
   size_t start = align16(out.size());
   out.resize(start + off, 0);
   char* base = out.data() + start;
@@ -609,7 +623,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     if (!close_pass()) return false;
     if ((int)sb.payloads.size() > SWEEP_MAX_SLOTS) { err = "internal: too many ops in one sweep"; return false; }
     finish_blob<C>(sb, hdr, plan.blob, sd);
-    if (sd.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
+    if (hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
     plan.npasses += sd.npasses;
     plan.ndiag += sd.ndiag;
     plan.sweeps.push_back(sd);

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
         } else {
           const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
           if (op_flag[op.slot]) {
-            const C* payload = reinterpret_cast<const C*>(blob + op.payload);
+            const C* payload = op.payload_global ? reinterpret_cast<const C*>(prog + op.payload) : reinterpret_cast<const C*>(blob + op.payload);
             const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
             for (uint32_t t = 0; t < ntasks; t += SW_COMPUTE_THREADS) {
               BigAcc<C> a;

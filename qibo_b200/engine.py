@@ -114,6 +114,10 @@ class Engine:
 
     # ---- K1: one gate ---------------------------------------------------------------------------
     def apply_op(self, state: DeviceArray, nqubits: int, op: Op) -> DeviceArray:
+        if len(op.targets) > 5 and not op.is_diagonal:
+            # the one-gate kernels hold 2^k amplitudes per thread (k <= 5); 6-qubit blocks go through the sweep kernel
+            self._apply_sweeps(state, nqubits, [op], True, False)
+            return state
         fn = self.lib.qb_apply_diagonal if op.is_diagonal else self.lib.qb_apply_matrix
         _lib.check(
             fn(

@@ -54,7 +54,7 @@ static void run_sweep(C* state, char* blob) {  // the set-up phase writes per-ti
       } else {
         const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
         if (!flag[op.slot]) continue;
-        const C* payload = reinterpret_cast<const C*>(blob + op.payload);
+        const C* payload = reinterpret_cast<const C*>(blob + op.payload);  // the emulator keeps the whole blob in one buffer
         const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
         std::vector<BigAcc<C>> accs(ntasks);
         for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, task, accs[task]);

@@ -321,3 +321,17 @@ def test_permute_qubits(eng, n, dtype):
             np.testing.assert_array_equal(st.numpy(), orc.run_ops(psi, named, n, dtype=dtype))
         finally:
             eng.permute_swap_runs = True
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_six_qubit_dense_block(eng, dtype):
+    from helpers import rand_unitary
+
+    n = 15
+    rng = np.random.default_rng(6)
+    ops = [Op(rand_unitary(6, rng), (13, 2, 7, 0, 9, 4)), Op(orc.gate_matrix("H"), (3,)), Op(rand_unitary(6, rng), (1, 5, 3, 8, 12, 6), (10,))]
+    psi = rand_state(n, 3, dtype)
+    ref = oracle_run(psi, ops, n)
+    scale = 20 if dtype == "complex64" else 1
+    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
+    assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype) * scale  # apply_op routes k = 6 to the sweep kernel

@@ -130,3 +130,17 @@ def test_permute_qubits(n, dtype):
         for _, (a, b), _ in named:
             dest = [b if d == a else a if d == b else d for d in dest]
         np.testing.assert_array_equal(emul.permute_qubits(psi, n, dest), orc.run_ops(psi, named, n, dtype=dtype))
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_six_qubit_dense_block(dtype):
+    """A 64x64 block does not fit the shared-memory program buffer: its matrix stays in the global blob."""
+    from helpers import rand_unitary
+
+    n = 14
+    rng = np.random.default_rng(6)
+    ops = [Op(rand_unitary(6, rng), (13, 2, 7, 0, 9, 4)), Op(orc.gate_matrix("H"), (3,)), Op(rand_unitary(6, rng), (1, 5, 3, 8, 12, 6), (10,))]
+    psi = rand_state(n, 3, dtype)
+    ref = oracle_run(psi, ops, n)
+    out, _ = emul.apply_program(psi, n, ops)
+    assert np.abs(out - ref).max() < tol(dtype) * (20 if dtype == "complex64" else 1)
