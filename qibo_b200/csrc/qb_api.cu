@@ -473,8 +473,9 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
   std::vector<CanonOp> canon;
   int rc = canonicalize_program(nqubits, ops, nops, canon);
   if (rc != QB_OK) return rc;
-  if (nqubits < 3) {
-    // 2- and 4-amplitude states: nothing to tile; the K1 kernels apply the queue gate by gate
+  if (nqubits < 4) {
+    // up to 8 amplitudes: nothing to tile (a register group of the sweep kernel is 2^4 amplitudes); the K1 kernels
+    // apply the queue gate by gate
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
     if (stats) {
@@ -518,7 +519,10 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
   if (flags & QB_PROGRAM_TIME) QB_CUDA(cudaEventRecord(h->ev0, h->stream));
   for (size_t s = 0; s < plan.sweeps.size(); ++s) {
     rc = launch_sweep(h->stream, h->sm_count, state, nqubits, dtype, plan.sweeps[s], (const char*)h->prog_dev);
-    if (rc != QB_OK) return fail(rc, "sweep launch failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
+    if (rc != QB_OK) {
+      const std::string what = cudaGetErrorString(cudaGetLastError());
+      return fail(rc, "sweep launch failed: " + what + " [" + sweep_resources(dtype) + "]");
+    }
   }
   QB_CUDA(cudaEventRecord(h->prog_done, h->stream));
   if (flags & QB_PROGRAM_TIME) {

@@ -30,37 +30,68 @@ namespace qb {
 enum MicroType { MU_DENSE1 = 1, MU_DENSE2 = 2, MU_SWAP = 3, MU_FAN = 4, MU_DIAGK = 5, MU_PHASE = 6 };
 enum PassKind { PASS_REGTILE = 1, PASS_BIG = 2 };
 
-constexpr int SWEEP_MAX_SLOTS = 96;        // micro-ops (+ big ops) per sweep that need per-tile set-up
-constexpr int SWEEP_BLOB_MAX = 29 * 1024;  // program bytes resident in shared memory next to the tiles
+// One handler code per micro-op: (operation, register bit(s), control mode) flattened so that the kernel needs a
+// single jump table.  "+I" = register-bit index 0..3; "+P" = register-bit pair (hi,lo): (1,0) (2,0) (2,1) (3,0) (3,1) (3,2).
+enum MicroHandler {
+  MH_NOP = 0,
+  MH_ADDSUB = 1,    // +I  (a+b, a-b): H-like gate whose scalar has been moved into another gate of the sweep
+  MH_REAL1 = 5,     // +I  real 2x2, no register-bit control
+  MH_CPLX1 = 9,     // +I  complex 2x2, no register-bit control
+  MH_CPLX1_M = 13,  // +I  complex 2x2, run-time register-bit control mask
+  MH_XPAIR = 17,    // +I  pair exchange (X, CNOT, TOFFOLI...), run-time register-bit control mask
+  MH_DENSE2 = 21,   // +P  4x4 (matrix index MSB = hi), run-time mask
+  MH_SWAP = 27,     // +P  run-time mask
+  MH_FAN_C = 33,    // +I  fan whose only register-bit control is bit I
+  MH_FAN_NC = 37,   //     fan without register-bit control
+  MH_FAN_M = 38,    //     fan, run-time mask
+  MH_PHASE_C = 39,  // +I
+  MH_PHASE_NC = 43,
+  MH_PHASE_M = 44,
+  MH_DIAGK = 45,
+  MH_STAGE_A = 46,  // +I  (a+b, a-b) on bit I, then a fan whose only control is bit I (a QFT stage in one dispatch)
+  MH_STAGE_R = 50,  // +I  real 2x2 on bit I, then that fan
+};
+
+constexpr int SWEEP_MAX_SLOTS = 48;        // ops per sweep that need per-tile set-up (controls / factors from outside the tile)
+constexpr int SWEEP_BLOB_MAX = 26 * 1024;  // program bytes resident in shared memory next to the tiles
 constexpr int SWEEP_TILE_BYTES_LOG2 = 16;  // 64 KiB tiles, three in flight per SM
-constexpr int MU_REAL = 1;                 // flags: the 2x2 / 4x4 matrix is real
+constexpr uint32_t MU_NO_SLOT = 0xFFFF;
+constexpr int FAN_EXT_CHUNK = 4;           // a fan's bits outside the tile are folded through tables of 2^4 entries (<= 8 tables: 32 bits)
 constexpr size_t BIG_PAYLOAD_SMEM_MAX = 16 * 1024 + 64;  // larger dense matrices (6 targets) stay in global memory
 
-struct MicroOp {
+// per-tile, per-team state of a slot (the program itself stays constant, so two teams of compute warps can work on
+// two tiles at once)
+struct TileSlot {
+  double ext[2];         // FAN: factor from the bits outside the tile, in the state's precision (a C)
+  uint32_t active;       // controls outside the tile are all 1
+  uint32_t aux;          // DIAGK: table-index part from the bits outside the tile
+  uint32_t pad[2];
+};
+static_assert(sizeof(TileSlot) == 32, "TileSlot layout");
+
+struct alignas(16) MicroOp {
   // ---- hot header: one 16-byte shared-memory load decodes the op ------------------------------------
+  uint8_t handler;       // MicroHandler
   uint8_t type;          // MicroType
-  uint8_t rb0, rb1;      // register-bit indices: DENSE1 target; DENSE2/SWAP (matrix MSB, LSB)
-  uint8_t flags;         // MU_REAL
+  uint16_t slot;         // TileSlot index, or MU_NO_SLOT: always active, nothing depends on the tile
   uint32_t creg;         // controls that are register bits (mask over the register index j)
   uint32_t cthr;         // controls inside the tile but outside R (tile-local mask, tested on the group base)
-  uint32_t active;       // PER TILE (written by the set-up phase): controls outside the tile are all 1
+  uint32_t payload;      // byte offset in the blob: DENSE2 matrix | FAN: TA, TB, G, ext tables | DIAGK: table
   // ---- second 16 bytes ---------------------------------------------------------------------------------
   uint16_t la;           // FAN: TA is indexed by the low `la` bits of the group index, TB by the rest
   uint16_t R;            // register bits of the pass this op belongs to (table layout)
   uint32_t k;            // DIAGK: number of target bits
-  uint32_t payload;      // byte offset in the blob: DENSE2 matrix | FAN: TA, TB, G, ext tables | DIAGK: table
-  uint32_t aux;          // PER TILE: DIAGK table-index part from the bits outside the tile
-  // ---- inline data -------------------------------------------------------------------------------------
-  double inl[8];         // DENSE1: the 2x2 matrix in the state's precision (4 x C); FAN: inl[0..1] hold the
-                         // PER TILE factor from the bits outside the tile (a C)
-  // ---- cold part -----------------------------------------------------------------------------------------
-  uint64_t ext_cmask;    // controls outside the tile (state bit positions)
   uint32_t n_ext;        // FAN: number of ext tables
-  uint32_t slot;
+  uint32_t pad0;
+  // ---- inline data -------------------------------------------------------------------------------------
+  double inl[8];         // DENSE1: the 2x2 matrix in the state's precision (4 x C); PHASE: the phase (a C)
+  // ---- cold part (per-tile set-up, DIAGK) ------------------------------------------------------------------
+  uint64_t ext_cmask;    // controls outside the tile (state bit positions)
   uint8_t tbit[8];       // DIAGK: tile-local bit of target i if it is outside R, else 0xFF
   uint8_t rsel[8];       // DIAGK: register-bit index of target i if it is in R, else 0xFF
-  uint64_t ext_mask[6];  // FAN: state-bit mask of ext table e; DIAGK: state-bit mask of target i when outside the tile
+  uint64_t ext_mask[8];  // FAN: state-bit mask of ext table e; DIAGK: state-bit mask of target i when outside the tile
   double scalar[2];      // FAN: global factor
+  uint64_t pad1;
 };
 static_assert(sizeof(MicroOp) % 16 == 0, "MicroOp must stay 16-byte aligned");
 
@@ -85,6 +116,8 @@ struct PassHeader {
   uint16_t R;            // REGTILE: number of register bits of this pass
   uint32_t offset;       // byte offset of MicroOp[0] (REGTILE) or of the DevOp (BIG)
   uint16_t off[16];      // REGTILE: tile-local offset of register index j (deposit of j into rmask), precomputed
+  uint8_t pos[8];        // REGTILE: tile-local positions of the register bits, ascending
+  uint32_t pad[2];
 };
 static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligned");
 
@@ -99,7 +132,7 @@ struct SweepHeader {
   uint32_t passes_offset;  // byte offset of PassHeader[0]
   uint32_t nslots;
   uint32_t R;              // register bits of the REGTILE passes
-  uint32_t slots_offset;   // uint32[nslots]: byte offset of the slot's MicroOp, or of its DevOp with bit 31 set
+  uint32_t slots_offset;   // uint32[nslots]: byte offset of the slot's MicroOp, or of its DevOp with bit 31 set (ops that need per-tile set-up)
   uint32_t pad[2];
 };
 static_assert(sizeof(SweepHeader) % 16 == 0, "SweepHeader must stay 16-byte aligned");
@@ -113,6 +146,7 @@ struct PlanOp {
   std::map<int, std::pair<cd, cd>> fan;  // FAN: bit position -> (factor if bit == 0, factor if bit == 1)
   cd scalar = cd(1.0, 0.0);
   std::vector<int> src;         // indices of the original ops merged into this one
+  int special = 0;              // 1: apply as (a+b, a-b); the scalar of the gate rides in another gate of the sweep
 };
 
 struct SweepDesc {
@@ -242,7 +276,14 @@ template <> inline d2 to_dev<d2>(cd v) { return d2{v.real(), v.imag()}; }
 
 inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-inline int regtile_bits_for(int dtype) { (void)dtype; return env_int("QB_REGTILE_BITS", 4); }
+// register bits per REGTILE pass, per dtype: the kernel (qb_sweep.cuh) instantiates exactly these
+#ifndef QB_R128
+#define QB_R128 4
+#endif
+#ifndef QB_R64
+#define QB_R64 4
+#endif
+inline int regtile_bits_for(int dtype) { return dtype == QB_C128 ? QB_R128 : QB_R64; }
 
 // upper bound of the blob bytes a PlanOp needs (independent of the tile)
 inline size_t blob_estimate(const PlanOp& p, int csize, int T, int R) {
@@ -254,12 +295,12 @@ inline size_t blob_estimate(const PlanOp& p, int csize, int T, int R) {
     }
     case CK_SWAP: return sizeof(MicroOp);
     case CK_DIAG: return sizeof(MicroOp) + align16(p.data.size() * csize);
-    default: {  // fan: TA + TB + G + ext tables of <= 5 bits
+    default: {  // fan: TA + TB + G + ext tables of <= FAN_EXT_CHUNK bits
       int gb = T - R > 0 ? T - R : 0;
       int la = gb < 5 ? gb : 5;
       size_t local = (size_t(1) << la) + (size_t(1) << (gb - la)) + (size_t(1) << R);
-      size_t next = (p.fan.size() + 4) / 5;
-      return sizeof(MicroOp) + align16((local + next * 32) * csize);
+      size_t next = (p.fan.size() + FAN_EXT_CHUNK - 1) / FAN_EXT_CHUNK;
+      return sizeof(MicroOp) + align16((local + next * (size_t(1) << FAN_EXT_CHUNK)) * csize);
     }
   }
 }
@@ -271,8 +312,9 @@ template <typename C> struct SweepBuilder {
   std::vector<PassHeader> passes;
   std::vector<std::vector<MicroOp>> micro;   // per pass (empty for BIG)
   std::vector<DevOp> big;                    // per pass (valid for BIG)
-  std::vector<std::vector<C>> payloads;      // one per slot
-  std::vector<std::pair<int, int>> slot_owner;  // slot -> (pass, micro index or -1)
+  std::vector<std::vector<C>> payloads;      // one per op
+  std::vector<std::pair<int, int>> payload_owner;  // payload -> (pass, micro index or -1)
+  std::vector<std::pair<int, int>> slots;    // per-tile set-up slot -> (pass, micro index or -1)
 };
 
 inline bool is_real_matrix(const std::vector<cd>& m) {
@@ -280,6 +322,15 @@ inline bool is_real_matrix(const std::vector<cd>& m) {
     if (v.imag() != 0.0) return false;
   return true;
 }
+
+// s * [[1, 1], [1, -1]] on one uncontrolled target (H): candidates for the add/sub form
+inline bool is_hadamard_like(const PlanOp& p) {
+  if (p.kind != CK_DENSE || p.tpos.size() != 1 || !p.cpos.empty() || p.data.size() != 4) return false;
+  const cd s = p.data[0];
+  return s != cd(0.0, 0.0) && p.data[1] == s && p.data[2] == s && p.data[3] == -s;
+}
+
+inline int pair_index(int hi, int lo) { return hi * (hi - 1) / 2 + lo; }
 
 // Emits the micro-ops of one REGTILE pass given its final register-bit mask.
 template <typename C>
@@ -310,6 +361,11 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       }
     ph.off[j] = (uint16_t)o;
   }
+  {
+    int kbit = 0;
+    for (int lb = 0; lb < T; ++lb)
+      if ((rmask >> lb) & 1) ph.pos[kbit++] = (uint8_t)lb;
+  }
   std::vector<MicroOp> mops;
   const int pass_index = (int)sb.passes.size();
   for (const PlanOp* pp : ops) {
@@ -319,11 +375,13 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     memset(m.tbit, 0xFF, sizeof(m.tbit));
     memset(m.rsel, 0xFF, sizeof(m.rsel));
     m.R = (uint16_t)R;
+    m.slot = (uint16_t)MU_NO_SLOT;
     for (int c : p.cpos) {
       if (!((sb.tile_mask >> c) & 1)) m.ext_cmask |= uint64_t(1) << c;
       else if (rbit_of_local[sb.local_of_pos[c]] >= 0) m.creg |= 1u << rbit_of_local[sb.local_of_pos[c]];
       else m.cthr |= 1u << sb.local_of_pos[c];
     }
+    bool needs_slot = false;
     std::vector<C> payload;
     if (p.kind == CK_DENSE || p.kind == CK_SWAP) {
       int k = (int)p.tpos.size();
@@ -333,22 +391,31 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
         if (lb < 0 || rbit_of_local[lb] < 0) { err = "internal: dense target is not a register bit"; return false; }
         rb[i] = rbit_of_local[lb];
       }
-      m.rb0 = (uint8_t)rb[0];
-      m.rb1 = (uint8_t)rb[1];
       if (p.kind == CK_SWAP) {
         m.type = MU_SWAP;
+        m.handler = (uint8_t)(MH_SWAP + pair_index(std::max(rb[0], rb[1]), std::min(rb[0], rb[1])));
+      } else if (k == 1) {
+        m.type = MU_DENSE1;
+        C* inl = reinterpret_cast<C*>(m.inl);
+        for (int e = 0; e < 4; ++e) inl[e] = to_dev<C>(p.data[e]);
+        const cd zero(0.0, 0.0), one(1.0, 0.0);
+        if (p.special == 1) m.handler = (uint8_t)(MH_ADDSUB + rb[0]);
+        else if (p.data[0] == zero && p.data[3] == zero && p.data[1] == one && p.data[2] == one) m.handler = (uint8_t)(MH_XPAIR + rb[0]);
+        else if (m.creg != 0) m.handler = (uint8_t)(MH_CPLX1_M + rb[0]);
+        else m.handler = (uint8_t)((is_real_matrix(p.data) ? MH_REAL1 : MH_CPLX1) + rb[0]);
       } else {
-        m.type = k == 1 ? MU_DENSE1 : MU_DENSE2;
-        if (is_real_matrix(p.data)) m.flags |= MU_REAL;
-        if (k == 1) {  // inline 2x2
-          C* inl = reinterpret_cast<C*>(m.inl);
-          for (int e = 0; e < 4; ++e) inl[e] = to_dev<C>(p.data[e]);
-        } else {
-          for (auto& v : p.data) payload.push_back(to_dev<C>(v));
-        }
+        m.type = MU_DENSE2;
+        const bool flip = rb[0] < rb[1];  // the handler wants the matrix-index MSB on the higher register bit
+        auto sw = [](int x) { return ((x & 1) << 1) | (x >> 1); };
+        payload.resize(16);
+        for (int r = 0; r < 4; ++r)
+          for (int c = 0; c < 4; ++c) payload[(flip ? sw(r) : r) * 4 + (flip ? sw(c) : c)] = to_dev<C>(p.data[r * 4 + c]);
+        m.handler = (uint8_t)(MH_DENSE2 + pair_index(std::max(rb[0], rb[1]), std::min(rb[0], rb[1])));
       }
     } else if (p.kind == CK_DIAG) {
       m.type = MU_DIAGK;
+      m.handler = MH_DIAGK;
+      needs_slot = true;
       int k = (int)p.tpos.size();
       m.k = k;
       for (int i = 0; i < k; ++i) {
@@ -366,8 +433,15 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       else if (rbit_of_local[sb.local_of_pos[pos]] >= 0) m.creg |= 1u << rbit_of_local[sb.local_of_pos[pos]];
       else m.cthr |= 1u << sb.local_of_pos[pos];
       *reinterpret_cast<C*>(m.inl) = to_dev<C>(p.scalar * p.fan.begin()->second.second);
+      if (m.creg == 0) m.handler = MH_PHASE_NC;
+      else if (__builtin_popcount(m.creg) == 1) m.handler = (uint8_t)(MH_PHASE_C + __builtin_ctz(m.creg));
+      else m.handler = MH_PHASE_M;
     } else {  // fan
       m.type = MU_FAN;
+      needs_slot = true;
+      if (m.creg == 0) m.handler = MH_FAN_NC;
+      else if (__builtin_popcount(m.creg) == 1) m.handler = (uint8_t)(MH_FAN_C + __builtin_ctz(m.creg));
+      else m.handler = MH_FAN_M;
       m.scalar[0] = p.scalar.real();
       m.scalar[1] = p.scalar.imag();
       m.la = (uint16_t)la;
@@ -398,9 +472,9 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       std::vector<int> ext;
       for (auto& kv : p.fan)
         if (!((sb.tile_mask >> kv.first) & 1)) ext.push_back(kv.first);
-      for (size_t s = 0; s < ext.size(); s += 5) {
-        size_t e = std::min(ext.size(), s + 5);
-        if (m.n_ext >= 6) { err = "internal: too many ext tables"; return false; }
+      for (size_t s = 0; s < ext.size(); s += FAN_EXT_CHUNK) {
+        size_t e = std::min(ext.size(), s + FAN_EXT_CHUNK);
+        if (m.n_ext >= 8) { err = "internal: too many ext tables"; return false; }
         uint64_t mask = 0;
         for (size_t i = s; i < e; ++i) mask |= uint64_t(1) << ext[i];
         m.ext_mask[m.n_ext++] = mask;
@@ -412,10 +486,47 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
         }
       }
     }
-    m.slot = (uint32_t)sb.payloads.size();
-    sb.slot_owner.push_back({pass_index, (int)mops.size()});
+    if (m.ext_cmask != 0) needs_slot = true;
+    if (needs_slot) {
+      m.slot = (uint16_t)sb.slots.size();
+      sb.slots.push_back({pass_index, (int)mops.size()});
+    }
+    sb.payload_owner.push_back({pass_index, (int)mops.size()});
     sb.payloads.push_back(std::move(payload));
     mops.push_back(m);
+  }
+  // ---- fuse "1-qubit gate on register bit I" + "fan controlled by bit I alone" into one stage op (one dispatch)
+  if (!env_int("QB_NO_STAGE", 0)) {
+    const size_t first_payload = sb.payloads.size() - mops.size(), first_slot_guard = 0;
+    (void)first_slot_guard;
+    std::vector<MicroOp> fused;
+    std::vector<int> new_index(mops.size(), -1);
+    for (size_t q = 0; q < mops.size(); ++q) {
+      const MicroOp& a = mops[q];
+      const bool dense_ok = (a.handler >= MH_ADDSUB && a.handler < MH_ADDSUB + 4) || (a.handler >= MH_REAL1 && a.handler < MH_REAL1 + 4);
+      if (dense_ok && a.cthr == 0 && a.slot == MU_NO_SLOT && q + 1 < mops.size()) {
+        const int I = a.handler >= MH_REAL1 ? a.handler - MH_REAL1 : a.handler - MH_ADDSUB;
+        const MicroOp& f = mops[q + 1];
+        if (f.handler == MH_FAN_C + I && f.cthr == 0 && f.ext_cmask == 0) {
+          MicroOp m = f;  // fan fields (tables, slot, la, ext masks) + the matrix of the dense gate
+          memcpy(m.inl, a.inl, sizeof(m.inl));
+          m.handler = (uint8_t)((a.handler >= MH_REAL1 ? MH_STAGE_R : MH_STAGE_A) + I);
+          new_index[q] = new_index[q + 1] = (int)fused.size();
+          fused.push_back(m);
+          ++q;
+          continue;
+        }
+      }
+      new_index[q] = (int)fused.size();
+      fused.push_back(a);
+    }
+    if (fused.size() != mops.size()) {
+      for (size_t q = 0; q < mops.size(); ++q) sb.payload_owner[first_payload + q].second = new_index[q];
+      for (auto& so : sb.slots)
+        if (so.first == pass_index && so.second >= 0) so.second = new_index[so.second];
+      // a fused pair owns two payload entries (the dense gate's is empty): keep the fan's payload as the op's
+      mops.swap(fused);
+    }
   }
   ph.nmicro = (uint16_t)mops.size();
   sb.passes.push_back(ph);
@@ -449,11 +560,15 @@ template <typename C> inline bool emit_big_pass(SweepBuilder<C>& sb, const PlanO
   std::vector<C> payload;
   for (auto& v : p.data) payload.push_back(to_dev<C>(v));
   d.payload_global = payload.size() * sizeof(C) > BIG_PAYLOAD_SMEM_MAX ? 1u : 0u;
-  d.slot = (uint32_t)sb.payloads.size();
+  d.slot = MU_NO_SLOT;
+  if (d.ext_cmask != 0) {
+    d.slot = (uint32_t)sb.slots.size();
+    sb.slots.push_back({(int)sb.passes.size(), -1});
+  }
   PassHeader ph;
   memset(&ph, 0, sizeof(ph));
   ph.kind = PASS_BIG;
-  sb.slot_owner.push_back({(int)sb.passes.size(), -1});
+  sb.payload_owner.push_back({(int)sb.passes.size(), -1});
   sb.payloads.push_back(std::move(payload));
   sb.passes.push_back(ph);
   sb.micro.push_back({});
@@ -470,19 +585,20 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
     off += sb.passes[p].kind == PASS_BIG ? sizeof(DevOp) : sb.micro[p].size() * sizeof(MicroOp);
   }
   hdr.slots_offset = (uint32_t)off;
-  off += align16(sb.payloads.size() * sizeof(uint32_t));
+  off += align16(sb.slots.size() * sizeof(uint32_t));
   for (size_t s = 0; s < sb.payloads.size(); ++s) {
-    auto own = sb.slot_owner[s];
+    auto own = sb.payload_owner[s];
     if (own.second < 0 && sb.big[own.first].payload_global) continue;
+    if (sb.payloads[s].empty()) continue;  // (a fused stage op owns two entries; the dense gate's is empty)
     if (own.second < 0) sb.big[own.first].payload = (uint32_t)off;
     else sb.micro[own.first][own.second].payload = (uint32_t)off;
     off += align16(sb.payloads[s].size() * sizeof(C));
   }
   hdr.npasses = (uint32_t)sb.passes.size();
-  hdr.nslots = (uint32_t)sb.payloads.size();
+  hdr.nslots = (uint32_t)sb.slots.size();
   hdr.blob_bytes = (uint32_t)off;  // the part the kernel copies to shared memory
   for (size_t s = 0; s < sb.payloads.size(); ++s) {  // large matrices follow; read through the global pointer
-    auto own = sb.slot_owner[s];
+    auto own = sb.payload_owner[s];
     if (own.second < 0 && sb.big[own.first].payload_global) {
       sb.big[own.first].payload = (uint32_t)off;
       off += align16(sb.payloads[s].size() * sizeof(C));
@@ -497,14 +613,14 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
     if (sb.passes[p].kind == PASS_BIG) memcpy(base + sb.passes[p].offset, &sb.big[p], sizeof(DevOp));
     else if (!sb.micro[p].empty()) memcpy(base + sb.passes[p].offset, sb.micro[p].data(), sb.micro[p].size() * sizeof(MicroOp));
   }
-  for (size_t s = 0; s < sb.payloads.size(); ++s) {
-    auto own = sb.slot_owner[s];
+  for (size_t s = 0; s < sb.slots.size(); ++s) {
+    auto own = sb.slots[s];
     uint32_t so = own.second < 0 ? (sb.passes[own.first].offset | 0x80000000u)
                                  : sb.passes[own.first].offset + (uint32_t)(own.second * sizeof(MicroOp));
     memcpy(base + hdr.slots_offset + s * sizeof(uint32_t), &so, sizeof(uint32_t));
   }
   for (size_t s = 0; s < sb.payloads.size(); ++s) {
-    auto own = sb.slot_owner[s];
+    auto own = sb.payload_owner[s];
     uint32_t po = own.second < 0 ? sb.big[own.first].payload : sb.micro[own.first][own.second].payload;
     if (!sb.payloads[s].empty()) memcpy(base + po, sb.payloads[s].data(), sb.payloads[s].size() * sizeof(C));
   }
@@ -524,7 +640,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
   if (R > T) R = T;
   if (R < 1) R = 1;
   const int free_high = T - Lcfg;
-  const int max_ops = no_fuse ? 1 : env_int("QB_SWEEP_MAX_OPS", SWEEP_MAX_SLOTS);
+  const int max_ops = no_fuse ? 1 : env_int("QB_SWEEP_MAX_OPS", 160);
   const uint64_t all = (uint64_t(1) << n) - 1;
   const uint64_t lowmask = (uint64_t(1) << Lcfg) - 1;
   const int csize = (int)sizeof(C);
@@ -535,6 +651,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     uint64_t high = 0;
     size_t j = i;
     size_t est = sizeof(SweepHeader) + 64;
+    int slot_est = 0;
     while (j < pops.size()) {
       const PlanOp& p = pops[j];
       uint64_t need = 0;
@@ -547,10 +664,12 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
         break;
       }
       size_t add = blob_estimate(p, csize, T, R) + sizeof(PassHeader);
-      if (j > i && (est + add > (size_t)SWEEP_BLOB_MAX || (int)(j - i) >= max_ops)) break;
+      const int slot_add = (p.kind == CK_PHASE || p.kind == CK_DIAG || !p.cpos.empty()) ? 1 : 0;  // may need per-tile set-up
+      if (j > i && (est + add > (size_t)SWEEP_BLOB_MAX || (int)(j - i) >= max_ops || slot_est + slot_add > SWEEP_MAX_SLOTS)) break;
       if (est + add > (size_t)SWEEP_BLOB_MAX) { err = "single gate does not fit the sweep program buffer"; return false; }
       high = nh;
       est += add;
+      slot_est += slot_add;
       ++j;
     }
     // ---- complete the tile with the lowest unused bits (longest contiguous runs)
@@ -582,25 +701,38 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     sd.tile_mask = tile_mask;
     sd.ntiles = hdr.ntiles;
 
+    // ---- H-like gates: all but the last one of the sweep run as (a+b, a-b); the last one carries the product of
+    // their scalars (a scalar commutes with everything).  Halves the FP work of those gates.
+    std::vector<PlanOp> sops(pops.begin() + i, pops.begin() + j);
+    if (!no_fuse && !env_int("QB_NO_ADDSUB", 0)) {
+      std::vector<size_t> cand;
+      for (size_t q = 0; q < sops.size(); ++q)
+        if (is_hadamard_like(sops[q])) cand.push_back(q);
+      if (cand.size() >= 2) {
+        cd prod(1.0, 0.0);
+        for (size_t q : cand) prod *= sops[q].data[0];
+        for (size_t c = 0; c + 1 < cand.size(); ++c) sops[cand[c]].special = 1;
+        PlanOp& last = sops[cand.back()];
+        last.data = {prod, prod, prod, -prod};
+      }
+    }
+
     // ---- split the sweep's ops into passes: a REGTILE pass holds ops whose dense targets fit R register bits
     std::vector<const PlanOp*> cur;
     uint32_t cur_r = 0;  // tile-local mask of the register bits demanded so far
     auto close_pass = [&]() -> bool {
       if (cur.empty()) return true;
-      // pad the register set to Rp bits, preferring high tile-local bits (keeps lanes on the low bits: no bank
-      // conflicts).  complex128 passes that need <= 3 register bits run with R = 3 and two groups in flight.
-      int Rp = R;
-      if (sizeof(C) == 16 && R > 3 && __builtin_popcount(cur_r) <= 3) Rp = 3;
+      // pad the register set to R bits, preferring high tile-local bits (keeps lanes on the low bits: no bank conflicts)
       uint32_t rmask = cur_r;
-      for (int lb = T - 1; lb >= 0 && __builtin_popcount(rmask) < Rp; --lb)
+      for (int lb = T - 1; lb >= 0 && __builtin_popcount(rmask) < R; --lb)
         if (!((rmask >> lb) & 1)) rmask |= 1u << lb;
       bool ok = emit_regtile_pass<C>(sb, cur, rmask, err);
       cur.clear();
       cur_r = 0;
       return ok;
     };
-    for (size_t q = i; q < j; ++q) {
-      const PlanOp& p = pops[q];
+    for (size_t q = 0; q < sops.size(); ++q) {
+      const PlanOp& p = sops[q];
       for (int s : p.src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
       if (p.kind == CK_DENSE && p.tpos.size() > 2) {
         if (!close_pass()) return false;
@@ -621,7 +753,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
       if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
     }
     if (!close_pass()) return false;
-    if ((int)sb.payloads.size() > SWEEP_MAX_SLOTS) { err = "internal: too many ops in one sweep"; return false; }
+    if ((int)sb.slots.size() > SWEEP_MAX_SLOTS) { err = "internal: too many per-tile slots in one sweep"; return false; }
     finish_blob<C>(sb, hdr, plan.blob, sd);
     if (hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
     plan.npasses += sd.npasses;

@@ -9,6 +9,7 @@
 //
 // The device program (SweepHeader + DevOp[] + payloads, qb_planner.hpp) is copied to shared memory once.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 
 #include "qb_common.cuh"
@@ -20,16 +21,59 @@ namespace qb {
 
 constexpr int SW_NBUF = 3;
 constexpr int SW_TILE_BYTES = 1 << SWEEP_TILE_BYTES_LOG2;
-#ifndef QB_COMPUTE_THREADS
-#define QB_COMPUTE_THREADS 256  // 8 warps x 2 groups in flight per thread = the 512 groups of a 64 KiB tile
+// TEAMS of 8 compute warps: each team owns one resident tile at a time (one group of 2^4 amplitudes per thread for
+// complex128, two for complex64), so with two teams two tiles are in their compute phase while the third buffer is
+// being stored / reloaded, and one team's barriers, shared-memory bursts and set-up phases hide behind the other's
+// math.  Per dtype (measured on B200, scripts/variant_bench.py): complex64 runs two teams; complex128 needs 64 data
+// registers per thread and is faster with one team and no spills (168 registers) than with two at 112.
+#ifndef QB_TEAMS128
+#define QB_TEAMS128 1
 #endif
-constexpr int SW_COMPUTE_THREADS = QB_COMPUTE_THREADS;
-constexpr int SW_COPY_THREADS = 64;  // warp 0: loader, warp 1: storer
-constexpr int SW_THREADS = SW_COMPUTE_THREADS + SW_COPY_THREADS;
-constexpr int SW_BLOB_REGION = 30 * 1024;
+#ifndef QB_TEAMS64
+#define QB_TEAMS64 2
+#endif
+// Register reallocation (setmaxnreg, sm_90a+): the copy warps live in a warpgroup of their own (warps 2-3 of it idle)
+// and hand their registers to the compute warpgroups right after start-up; 0 disables it.  Budget: the compute
+// threads can only take what the copy warpgroup released, (launch_regs - 24) * 128 registers.
+#ifndef QB_REGS128
+#define QB_REGS128 0
+#endif
+#ifndef QB_REGS64
+#define QB_REGS64 112
+#endif
+#ifndef QB_TEAM_THREADS
+#define QB_TEAM_THREADS 256
+#endif
+constexpr int SW_TEAM_THREADS = QB_TEAM_THREADS;
+constexpr int SW_MAX_TEAMS = 2;
+template <typename C> struct SweepCfg;
+template <> struct SweepCfg<double2> {
+  static constexpr int TEAMS = QB_TEAMS128, COMPUTE_REGS = QB_REGS128, RB = QB_R128;
+};
+template <> struct SweepCfg<float2> {
+  static constexpr int TEAMS = QB_TEAMS64, COMPUTE_REGS = QB_REGS64, RB = QB_R64;
+};
+template <typename C> constexpr int sw_copy_threads() { return SweepCfg<C>::COMPUTE_REGS ? 128 : 64; }  // warp 0: loader, warp 1: storer
+template <typename C> constexpr int sw_threads() { return SweepCfg<C>::TEAMS * SW_TEAM_THREADS + sw_copy_threads<C>(); }
 constexpr int SW_MAX_RUNS = 256;
-constexpr int SW_SMEM_BYTES = SW_NBUF * SW_TILE_BYTES + SW_BLOB_REGION + SW_MAX_RUNS * 8 + SWEEP_MAX_SLOTS * (16 + 4 + 4) + 128;
+constexpr int SW_FIXED_BYTES = SW_NBUF * SW_TILE_BYTES + SW_MAX_RUNS * 8 + SW_NBUF * SWEEP_MAX_SLOTS * (int)sizeof(TileSlot) + 128;
+constexpr int SW_BLOB_REGION = ((226 * 1024 - SW_FIXED_BYTES) / 16) * 16;
+constexpr int SW_SMEM_BYTES = SW_FIXED_BYTES + SW_BLOB_REGION;
 static_assert(SW_SMEM_BYTES <= 227 * 1024, "sweep kernel shared memory exceeds 227 KB");
+static_assert(SW_BLOB_REGION >= SWEEP_BLOB_MAX + 1024, "shared-memory program region is smaller than the planner's limit");
+
+// Tile <-> HBM as ONE tensor-map copy per tile (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) when the tile's bits
+// form <= 5 alternating runs of tile / non-tile bits (QFT and layered circuits do); else one bulk copy per
+// contiguous run.  ncu: the per-run form costs ~20 issue slots per 512-byte copy on the copy warps -- 18 % of all
+// instructions of a QFT sweep -- and caps a sweep at the copy-issue rate when a single lane issues them.
+struct TmaDesc {
+  CUtensorMap map;     // rank 5, 8-byte elements, dim d = d-th run of state bits (a complex128 amplitude = 2 elements)
+  int32_t shift[5];    // coordinate of dim d for a tile at state index `base`: (base >> shift[d]) & mask[d]
+  uint32_t mask[5];    // 0 for dims spanned by the tile
+  int32_t enabled;
+  int32_t pad[5];
+};
+static_assert(sizeof(TmaDesc) % 64 == 0, "CUtensorMap must stay 64-byte aligned inside the kernel parameter");
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 QB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,16 +105,29 @@ QB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 20000000000LL) __trap();
   }
 }
-// for the copy warps: they wait for whole tile periods, so back off between polls instead of competing with the
-// compute warps of their scheduler for issue slots
+// for the copy warps: they wait for whole tile periods, so let the hardware suspend the warp (time hint) instead of
+// spinning through issue slots of the scheduler they share with compute warps
+QB_D bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 QB_D void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(1000);
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (clock64() - t0 > 20000000000LL) __trap();
   }
 }
+// state index of tile t = deposit(t, other_mask); stepping t by a constant is a masked add (carries ripple through the
+// bits outside the mask), so the software pdep runs once per role instead of once per tile per warp
+QB_D uint64_t masked_add(uint64_t x, uint64_t d, uint64_t mask) { return ((x | ~mask) + d) & mask; }
 QB_D void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
@@ -80,28 +137,42 @@ QB_D void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+QB_D void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+               : "memory");
+}
+QB_D void tma_store_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem_src))
+               : "memory");
+}
 QB_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> QB_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 QB_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 QB_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 QB_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-QB_D void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SW_COMPUTE_THREADS) : "memory"); }
+// literal barrier ids: with a register operand ptxas reserves all 16 hardware barriers
+QB_D void team_bar(int team) {
+  if (team == 0) asm volatile("bar.sync 1, %0;" ::"n"(SW_TEAM_THREADS) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"n"(SW_TEAM_THREADS) : "memory");
+}
 
 // ---- the kernel -----------------------------------------------------------------------------------------
 template <typename C>
-__global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ state, const char* __restrict__ prog) {
+__global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict__ state, const char* __restrict__ prog, const __grid_constant__ TmaDesc tma) {
   extern __shared__ __align__(1024) unsigned char smem[];
   C* tiles = reinterpret_cast<C*>(smem);
   char* blob = reinterpret_cast<char*>(smem + SW_NBUF * SW_TILE_BYTES);
   uint64_t* run_off = reinterpret_cast<uint64_t*>(blob + SW_BLOB_REGION);
-  double2* op_scal_raw = reinterpret_cast<double2*>(run_off + SW_MAX_RUNS);
-  uint32_t* op_flag = reinterpret_cast<uint32_t*>(op_scal_raw + SWEEP_MAX_SLOTS);
-  uint32_t* op_aux = op_flag + SWEEP_MAX_SLOTS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(op_aux + SWEEP_MAX_SLOTS);
+  TileSlot* tslots = reinterpret_cast<TileSlot*>(run_off + SW_MAX_RUNS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tslots + SW_NBUF * SWEEP_MAX_SLOTS);
   uint64_t* done = full + SW_NBUF;
   uint64_t* freeb = done + SW_NBUF;
-  C* op_scal = reinterpret_cast<C*>(op_scal_raw);
 
+  constexpr int SW_TEAMS = SweepCfg<C>::TEAMS, SW_COPY_THREADS = sw_copy_threads<C>(), SW_THREADS = sw_threads<C>();
   const int tid = threadIdx.x;
   {
     const uint32_t nbytes = reinterpret_cast<const SweepHeader*>(prog)->blob_bytes;
@@ -115,7 +186,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
   const uint32_t run_bytes = (uint32_t)sizeof(C) << L;
   const uint32_t tile_bytes = (uint32_t)sizeof(C) << T;
   const uint32_t tile_elems = 1u << T;
-  for (uint32_t r = tid; r < nruns; r += SW_THREADS) run_off[r] = deposit(uint64_t(r) << L, hdr.tile_mask);
+  for (uint32_t r = tid; r < nruns; r += SW_THREADS) run_off[r] = deposit(uint64_t(r) << L, hdr.tile_mask) * sizeof(C);
   if (tid == 0) {
     for (int b = 0; b < SW_NBUF; ++b) {
       mbar_init(&full[b], 1);
@@ -127,85 +198,120 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(C* __restrict__ st
   }
   __syncthreads();
 
+  const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
+  const int nslots = (int)hdr.nslots;
   const uint64_t ntiles = hdr.ntiles;
   const uint64_t my_n = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
-  const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
-  const int npasses = (int)hdr.npasses;
-  const int nslots = (int)hdr.nslots;
+  if constexpr (SweepCfg<C>::COMPUTE_REGS != 0) {
+    if (tid < SW_COPY_THREADS) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SweepCfg<C>::COMPUTE_REGS));
+  }
 
   if (tid < 32) {
     // ================= loader warp: HBM -> shared =================
     const int lane = tid;
-    for (uint64_t i = 0; i < my_n; ++i) {
+    uint64_t base = deposit(blockIdx.x, hdr.other_mask);
+    const uint64_t dstep = deposit(gridDim.x, hdr.other_mask);
+    for (uint64_t i = 0; i < my_n; ++i, base = masked_add(base, dstep, hdr.other_mask)) {
       const int b = (int)(i % SW_NBUF);
       // buffer b was last used by tile i-3: wait until the storer has drained it
       if (i >= SW_NBUF) mbar_wait_sleep(&freeb[b], (uint32_t)(((i / SW_NBUF) - 1) & 1));
-      if (lane == 0) mbar_expect_tx(&full[b], tile_bytes);
-      __syncwarp();
-      const C* gbase = state + deposit(blockIdx.x + i * gridDim.x, hdr.other_mask);
-      C* sbase = tiles + (size_t)b * tile_elems;
-      for (uint32_t r = lane; r < nruns; r += 32) bulk_g2s(sbase + ((size_t)r << L), gbase + run_off[r], run_bytes, &full[b]);
+      // per-tile set-up of the ops that depend on bits outside the tile (control predicates, fan factors), by the
+      // otherwise idle lanes of this warp: off the compute warps' critical path.  Published by the mbarrier
+      // arrive below (release) -> the compute threads' wait on `full` (acquire).
+      {
+        TileSlot* ts = tslots + b * SWEEP_MAX_SLOTS;
+        for (int sl = lane; sl < nslots; sl += 32) {
+          const uint32_t so = slot_table[sl];
+          if (so & 0x80000000u) {
+            const DevOp& bop = *reinterpret_cast<const DevOp*>(blob + (so & 0x7fffffffu));
+            ts[sl].active = (base & bop.ext_cmask) == bop.ext_cmask ? 1u : 0u;
+          } else {
+            micro_prephase<C>(*reinterpret_cast<const MicroOp*>(blob + so), blob, base, T, ts[sl]);
+          }
+        }
+        __syncwarp();
+      }
+      char* sbase = reinterpret_cast<char*>(tiles + (size_t)b * tile_elems);
+      if (tma.enabled) {
+        if (lane == 0) {
+          mbar_expect_tx(&full[b], tile_bytes);
+          tma_load_5d(sbase, &tma.map, (int)((base >> tma.shift[0]) & tma.mask[0]), (int)((base >> tma.shift[1]) & tma.mask[1]),
+                      (int)((base >> tma.shift[2]) & tma.mask[2]), (int)((base >> tma.shift[3]) & tma.mask[3]),
+                      (int)((base >> tma.shift[4]) & tma.mask[4]), &full[b]);
+        }
+      } else {
+        if (lane == 0) mbar_expect_tx(&full[b], tile_bytes);
+        __syncwarp();
+        const char* gbase = reinterpret_cast<const char*>(state + base);
+        for (uint32_t r = lane; r < nruns; r += 32) bulk_g2s(sbase + r * run_bytes, gbase + run_off[r], run_bytes, &full[b]);
+      }
     }
   } else if (tid < 64) {
     // ================= storer warp: shared -> HBM =================
     const int lane = tid - 32;
-    for (uint64_t j = 0; j < my_n; ++j) {
+    uint64_t base = deposit(blockIdx.x, hdr.other_mask);
+    const uint64_t dstep = deposit(gridDim.x, hdr.other_mask);
+    for (uint64_t j = 0; j < my_n; ++j, base = masked_add(base, dstep, hdr.other_mask)) {
       const int b = (int)(j % SW_NBUF);
       mbar_wait_sleep(&done[b], (uint32_t)((j / SW_NBUF) & 1));
-      C* gbase = state + deposit(blockIdx.x + j * gridDim.x, hdr.other_mask);
-      const C* sbase = tiles + (size_t)b * tile_elems;
-      for (uint32_t r = lane; r < nruns; r += 32) bulk_s2g(gbase + run_off[r], sbase + ((size_t)r << L), run_bytes);
-      bulk_commit();
-      bulk_wait_read<0>();  // shared memory of this tile has been read out: the loader may refill it
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&freeb[b]);
+      const char* sbase = reinterpret_cast<const char*>(tiles + (size_t)b * tile_elems);
+      if (tma.enabled) {
+        if (lane == 0) {
+          tma_store_5d(&tma.map, (int)((base >> tma.shift[0]) & tma.mask[0]), (int)((base >> tma.shift[1]) & tma.mask[1]),
+                       (int)((base >> tma.shift[2]) & tma.mask[2]), (int)((base >> tma.shift[3]) & tma.mask[3]),
+                       (int)((base >> tma.shift[4]) & tma.mask[4]), sbase);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(&freeb[b]);
+        }
+      } else {
+        char* gbase = reinterpret_cast<char*>(state + base);
+        for (uint32_t r = lane; r < nruns; r += 32) bulk_s2g(gbase + run_off[r], sbase + r * run_bytes, run_bytes);
+        bulk_commit();
+        bulk_wait_read<0>();  // shared memory of this tile has been read out: the loader may refill it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&freeb[b]);
+      }
     }
     bulk_wait_all();
-  } else {
-    // ================= compute warps =================
-    const uint32_t ctid = tid - SW_COPY_THREADS;
-    for (uint64_t i = 0; i < my_n; ++i) {
+  } else if (tid >= SW_COPY_THREADS) {
+    // ================= compute teams =================
+    const int team = (tid - SW_COPY_THREADS) / SW_TEAM_THREADS;
+    const uint32_t ctid = (uint32_t)(tid - SW_COPY_THREADS) % SW_TEAM_THREADS;
+    const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
+    const int npasses = (int)hdr.npasses;
+    constexpr int RB = SweepCfg<C>::RB;                                     // register bits of a REGTILE pass
+    constexpr int TB = SWEEP_TILE_BYTES_LOG2 - (sizeof(C) == 16 ? 4 : 3);  // tile bits of a full tile
+    constexpr int GPT = ((1 << (TB - RB)) + SW_TEAM_THREADS - 1) / SW_TEAM_THREADS;  // groups per thread
+    for (uint64_t i = team; i < my_n; i += SW_TEAMS) {
       const int b = (int)(i % SW_NBUF);
       C* tile = tiles + (size_t)b * tile_elems;
-      const uint64_t base = deposit(blockIdx.x + i * gridDim.x, hdr.other_mask);
-      for (int sl = (int)ctid; sl < nslots; sl += SW_COMPUTE_THREADS) {
-        const uint32_t so = slot_table[sl];
-        if (so & 0x80000000u) {
-          const DevOp& bop = *reinterpret_cast<const DevOp*>(blob + (so & 0x7fffffffu));
-          op_flag[sl] = (base & bop.ext_cmask) == bop.ext_cmask ? 1u : 0u;
-        } else {
-          micro_prephase<C>(*reinterpret_cast<MicroOp*>(blob + so), blob, base, T);
-        }
-      }
-      mbar_wait(&full[b], (uint32_t)((i / SW_NBUF) & 1));
-      compute_bar();
+      const TileSlot* ts = tslots + b * SWEEP_MAX_SLOTS;
+      mbar_wait(&full[b], (uint32_t)((i / SW_NBUF) & 1));  // tile data (async proxy) + slot states (loader warp) are visible
       for (int pi = 0; pi < npasses; ++pi) {
         const PassHeader& ph = passes[pi];
+        if (pi) team_bar(team);
         if (ph.kind == PASS_REGTILE) {
-          switch (ph.R) {
-            // R < 3 only occurs for n < 3, which qb_apply_program routes to the K1 kernels
-            case 3: run_regtile<C, 3>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
-            default: run_regtile<C, 4>(tile, blob, ph, T, ctid, SW_COMPUTE_THREADS); break;
-          }
+          // R < RB only occurs for n < 4, which qb_apply_program routes to the K1 kernels
+          run_pass<C, RB, GPT>(tile, blob, ts, ph, T, ctid, SW_TEAM_THREADS);
         } else {
           const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
-          if (op_flag[op.slot]) {
+          if (op.slot == MU_NO_SLOT || ts[op.slot].active) {
             const C* payload = op.payload_global ? reinterpret_cast<const C*>(prog + op.payload) : reinterpret_cast<const C*>(blob + op.payload);
             const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
-            for (uint32_t t = 0; t < ntasks; t += SW_COMPUTE_THREADS) {
+            for (uint32_t t = 0; t < ntasks; t += SW_TEAM_THREADS) {
               BigAcc<C> a;
               big_read<C>(tile, op, payload, T, t + ctid, a);
-              compute_bar();
+              team_bar(team);
               big_write<C>(tile, op, a);
-              if (t + SW_COMPUTE_THREADS < ntasks) compute_bar();
+              if (t + SW_TEAM_THREADS < ntasks) team_bar(team);
             }
           }
         }
-        compute_bar();
       }
       fence_proxy_async();
-      compute_bar();
+      team_bar(team);
       if (ctid == 0) mbar_arrive(&done[b]);
     }
   }
@@ -220,15 +326,90 @@ inline int sweep_configure(const cudaDeviceProp& prop) {
   return QB_OK;
 }
 
+// ---- host: tensor map of one sweep ---------------------------------------------------------------------------
+typedef CUresult (*qb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline qb_encode_tiled_fn tma_encoder() {
+  static qb_encode_tiled_fn fn = []() -> qb_encode_tiled_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<qb_encode_tiled_fn>(p);
+  }();
+  return fn;
+}
+
+// Runs of consecutive state bits that are all inside / all outside the tile become tensor dimensions; a run of tile
+// bits is cut so that a box edge stays <= 256 elements.  Returns false (per-run copies) when more than 5 are needed.
+inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask, TmaDesc& d) {
+  memset(&d, 0, sizeof(d));
+  if (env_int("QB_NO_TMA", 0)) return false;
+  qb_encode_tiled_fn enc = tma_encoder();
+  if (!enc) return false;
+  const int epa = dtype == QB_C128 ? 2 : 1;  // 8-byte elements per amplitude
+  struct Seg { int start, len; bool tile; };
+  std::vector<Seg> segs;
+  for (int b = 0; b < nqubits;) {
+    const bool t = (tile_mask >> b) & 1;
+    int e = b;
+    const int cap = t ? (segs.empty() ? (epa == 2 ? 7 : 8) : 8) : 31;
+    while (e < nqubits && (((tile_mask >> e) & 1) != 0) == t && e - b < cap) ++e;
+    segs.push_back({b, e - b, t});
+    b = e;
+  }
+  if (segs.empty() || !segs[0].tile || segs.size() > 5) return false;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5], estr[5];
+  for (int i = 0; i < 5; ++i) {
+    estr[i] = 1;
+    if (i < (int)segs.size()) {
+      gdim[i] = (cuuint64_t(1) << segs[i].len) * (i == 0 ? epa : 1);
+      box[i] = segs[i].tile ? (cuuint32_t)gdim[i] : 1;
+      d.shift[i] = segs[i].start;
+      d.mask[i] = segs[i].tile ? 0u : (uint32_t)((uint64_t(1) << segs[i].len) - 1);
+    } else {
+      gdim[i] = 1;
+      box[i] = 1;
+      d.shift[i] = 0;
+      d.mask[i] = 0;
+    }
+  }
+  // the runs tile the index bits in order, so every stride is the natural one: the byte size of all lower dimensions
+  cuuint64_t bytes = 8;
+  for (int i = 0; i < 4; ++i) {
+    bytes *= gdim[i];
+    if (bytes >= (cuuint64_t(1) << 40)) return false;
+    gstride[i] = bytes;
+  }
+  if (enc(&d.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, state, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  d.enabled = 1;
+  return true;
+}
+
 inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqubits, int dtype, const SweepDesc& sd,
                         const char* prog_dev) {
-  (void)nqubits;
   uint64_t grid = sd.ntiles < (uint64_t)sm_count ? sd.ntiles : (uint64_t)sm_count;
+  TmaDesc tma;
+  tma_describe(state, nqubits, dtype, sd.tile_mask, tma);
   if (dtype == QB_C128)
-    sweep_kernel<double2><<<(unsigned)grid, SW_THREADS, SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset);
+    sweep_kernel<double2><<<(unsigned)grid, sw_threads<double2>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
   else
-    sweep_kernel<float2><<<(unsigned)grid, SW_THREADS, SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset);
+    sweep_kernel<float2><<<(unsigned)grid, sw_threads<float2>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma);
   return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
+}
+
+// resources of the compiled kernel, for launch-failure messages
+inline std::string sweep_resources(int dtype) {
+  cudaFuncAttributes a;
+  cudaError_t e = dtype == QB_C128 ? cudaFuncGetAttributes(&a, sweep_kernel<double2>) : cudaFuncGetAttributes(&a, sweep_kernel<float2>);
+  if (e != cudaSuccess) return "(no attributes)";
+  return "threads=" + std::to_string(dtype == QB_C128 ? sw_threads<double2>() : sw_threads<float2>()) + " regs=" + std::to_string(a.numRegs) + " maxThreadsPerBlock=" + std::to_string(a.maxThreadsPerBlock) +
+         " static_smem=" + std::to_string(a.sharedSizeBytes) + " dyn_smem=" + std::to_string(SW_SMEM_BYTES) +
+         " max_dyn_smem=" + std::to_string(a.maxDynamicSharedSizeBytes) + " local=" + std::to_string(a.localSizeBytes);
 }
 
 // ---- K7 helper: gather / scatter the half of the shard with bit `pos` == `bit` ----------------------------

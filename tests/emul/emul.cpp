@@ -16,15 +16,15 @@ using namespace qb;
 constexpr uint32_t EMUL_THREADS = 256;  // the kernel's compute-thread count: same group -> thread mapping
 
 template <typename C>
-static void run_sweep(C* state, char* blob) {  // the set-up phase writes per-tile values into the ops
+static void run_sweep(C* state, const char* blob) {
   const SweepHeader& hdr = *reinterpret_cast<const SweepHeader*>(blob);
   const int T = (int)hdr.T, L = (int)hdr.L;
   const uint32_t nruns = 1u << (T - L), run = 1u << L;
   const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
   const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
   std::vector<C> tile(size_t(1) << T);
-  std::vector<uint32_t> flag(hdr.nslots + 1), aux(hdr.nslots + 1);
-  std::vector<C> scal(hdr.nslots + 1);
+  std::vector<TileSlot> ts(hdr.nslots + 1);
+  const int GPT = sizeof(C) == 16 ? 1 : 2;  // both group counts the kernel variants use are exercised
   for (uint64_t t = 0; t < hdr.ntiles; ++t) {
     const uint64_t base = deposit(t, hdr.other_mask);
     for (uint32_t r = 0; r < nruns; ++r) {
@@ -35,25 +35,34 @@ static void run_sweep(C* state, char* blob) {  // the set-up phase writes per-ti
       const uint32_t so = slot_table[sl];
       if (so & 0x80000000u) {
         const DevOp& bop = *reinterpret_cast<const DevOp*>(blob + (so & 0x7fffffffu));
-        flag[sl] = (base & bop.ext_cmask) == bop.ext_cmask ? 1u : 0u;
+        ts[sl].active = (base & bop.ext_cmask) == bop.ext_cmask ? 1u : 0u;
       } else {
-        micro_prephase<C>(*reinterpret_cast<MicroOp*>(blob + so), blob, base, T);
+        micro_prephase<C>(*reinterpret_cast<const MicroOp*>(blob + so), blob, base, T, ts[sl]);
       }
     }
     for (uint32_t pi = 0; pi < hdr.npasses; ++pi) {
       const PassHeader& ph = passes[pi];
       if (ph.kind == PASS_REGTILE) {
         for (uint32_t ctid = 0; ctid < EMUL_THREADS; ++ctid) {
-          switch (ph.R) {
-            case 1: run_regtile<C, 1>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
-            case 2: run_regtile<C, 2>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
-            case 3: run_regtile<C, 3>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
-            default: run_regtile<C, 4>(tile.data(), blob, ph, T, ctid, EMUL_THREADS); break;
+          if (GPT == 1) {
+            switch (ph.R) {
+              case 1: run_pass<C, 1, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              case 2: run_pass<C, 2, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              case 3: run_pass<C, 3, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              default: run_pass<C, 4, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+            }
+          } else {
+            switch (ph.R) {
+              case 1: run_pass<C, 1, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              case 2: run_pass<C, 2, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              case 3: run_pass<C, 3, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              default: run_pass<C, 4, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+            }
           }
         }
       } else {
         const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
-        if (!flag[op.slot]) continue;
+        if (op.slot != MU_NO_SLOT && !ts[op.slot].active) continue;
         const C* payload = reinterpret_cast<const C*>(blob + op.payload);  // the emulator keeps the whole blob in one buffer
         const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
         std::vector<BigAcc<C>> accs(ntasks);
