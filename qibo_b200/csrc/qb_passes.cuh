@@ -36,6 +36,14 @@ QB_HD uint32_t expand_mask(uint32_t g, uint32_t mask) {
   return g;
 }
 
+// Shared-memory layout of a tile: linear, or the TMA 128-byte swizzle (the 16-byte chunk index inside a 128-byte row
+// is XORed with the row index mod 8), which spreads amplitudes that differ only in bits >= 3 over the banks -- without
+// it a pass whose register bits are the lowest tile bits is an 8-way bank conflict.  `on` is 7 (swizzled) or 0.
+// swz is linear over XOR, so swz(t0 | off) = swz(t0) ^ swz(off) for disjoint t0 / off.
+template <typename C> QB_HD uint32_t swz(uint32_t x, uint32_t on) {
+  return sizeof(C) == 16 ? x ^ ((x >> 3) & on) : x ^ (((x >> 4) & on) << 1);
+}
+
 template <typename C> QB_HD C slot_ext(const TileSlot& s) { return *reinterpret_cast<const C*>(s.ext); }
 
 // ---- micro-op bodies on a register tile v[2^R] --------------------------------------------------------------
@@ -204,15 +212,15 @@ struct alignas(16) MicroHot { uint32_t w0, creg, cthr, payload; };  // first 16 
 // One REGTILE pass over the tile.  Each thread keeps GPT groups in registers at once, so that the decode of a
 // micro-op is paid once per GPT * 2^R amplitudes.  `ts` = this team's per-tile slot states.
 template <typename C, int R, int GPT>
-QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t ctid, uint32_t nct) {
+QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t swz_on, uint32_t ctid, uint32_t nct) {
   constexpr int D = 1 << R;
   const int gbits = T - R;
   const uint32_t ngroups = 1u << gbits;
-  uint32_t stride[R > 0 ? R : 1];
+  uint32_t stride[R > 0 ? R : 1];  // physical (swizzled) offset of register bit i
 #pragma unroll
-  for (int i = 0; i < R; ++i) stride[i] = 1u << ph.pos[i];
+  for (int i = 0; i < R; ++i) stride[i] = swz<C>(1u << ph.pos[i], swz_on);
   C v[GPT][D];
-  uint32_t g[GPT], t0[GPT];
+  uint32_t g[GPT], t0[GPT], p0[GPT];  // group index, logical tile index of the group base, its physical index
   bool valid[GPT];
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {
@@ -222,13 +230,14 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
 #pragma unroll
     for (int i = 0; i < R; ++i) t = insert_zero32(t, ph.pos[i]);
     t0[u] = t;
+    p0[u] = swz<C>(t, swz_on);
     if (valid[u]) {
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        uint32_t o = t0[u];
+        uint32_t o = p0[u];
 #pragma unroll
         for (int i = 0; i < R; ++i)
-          if ((j >> i) & 1) o += stride[i];
+          if ((j >> i) & 1) o ^= stride[i];
         v[u][j] = tile[o];
       }
     }
@@ -275,9 +284,9 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
     const C* gt = tb + (1u << (gbits - (int)la));                                    \
     const C ext = slot_ext<C>(ts[slot]);                                             \
     QB_EACH({                                                                        \
-      C p0 = cmul(ext, ta[g[u] & ((1u << la) - 1)]);                                 \
-      p0 = cmul(p0, tb[g[u] >> la]);                                                 \
-      mu_fan<C, R, CB>(v[u], p0, gt, hot.creg);                                      \
+      C ph0 = cmul(ext, ta[g[u] & ((1u << la) - 1)]);                                \
+      ph0 = cmul(ph0, tb[g[u] >> la]);                                               \
+      mu_fan<C, R, CB>(v[u], ph0, gt, hot.creg);                                     \
     })                                                                               \
   }
       QB_CASE_BIT(MH_FAN_C, QB_FAN_BODY(I))
@@ -302,10 +311,10 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
     if (valid[u]) {
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        uint32_t o = t0[u];
+        uint32_t o = p0[u];
 #pragma unroll
         for (int i = 0; i < R; ++i)
-          if ((j >> i) & 1) o += stride[i];
+          if ((j >> i) & 1) o ^= stride[i];
         tile[o] = v[u][j];
       }
     }
@@ -325,7 +334,7 @@ QB_HD uint32_t big_offset(const DevOp& op, int k, int j) {
 }
 
 template <typename C>
-QB_HD void big_read(const C* tile, const DevOp& op, const C* m, int T, uint32_t task, BigAcc<C>& a) {
+QB_HD void big_read(const C* tile, const DevOp& op, const C* m, int T, uint32_t swz_on, uint32_t task, BigAcc<C>& a) {
   const int k = (int)op.k, D = 1 << k, lt = k - 3;
   const uint32_t ntasks = (1u << (T - (int)op.nins)) << lt;
   a.valid = task < ntasks;
@@ -335,16 +344,16 @@ QB_HD void big_read(const C* tile, const DevOp& op, const C* m, int T, uint32_t 
 #pragma unroll
   for (int r = 0; r < 8; ++r) a.acc[r] = cmake<C>(0, 0);
   for (int j = 0; j < D; ++j) {
-    const C x = tile[a.t0 | big_offset(op, k, j)];
+    const C x = tile[swz<C>(a.t0 | big_offset(op, k, j), swz_on)];
 #pragma unroll
     for (int r = 0; r < 8; ++r) cfma(a.acc[r], m[(a.sub * 8 + r) * D + j], x);
   }
 }
-template <typename C> QB_HD void big_write(C* tile, const DevOp& op, const BigAcc<C>& a) {
+template <typename C> QB_HD void big_write(C* tile, const DevOp& op, uint32_t swz_on, const BigAcc<C>& a) {
   if (!a.valid) return;
   const int k = (int)op.k;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) tile[a.t0 | big_offset(op, k, (int)(a.sub * 8 + r))] = a.acc[r];
+  for (int r = 0; r < 8; ++r) tile[swz<C>(a.t0 | big_offset(op, k, (int)(a.sub * 8 + r)), swz_on)] = a.acc[r];
 }
 
 // ---- per-tile set-up of one slot (written into the calling team's TileSlot) ---------------------------------

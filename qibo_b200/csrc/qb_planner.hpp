@@ -133,7 +133,8 @@ struct SweepHeader {
   uint32_t nslots;
   uint32_t R;              // register bits of the REGTILE passes
   uint32_t slots_offset;   // uint32[nslots]: byte offset of the slot's MicroOp, or of its DevOp with bit 31 set (ops that need per-tile set-up)
-  uint32_t pad[2];
+  uint32_t swizzle;        // 1: the tile sits in shared memory in the TMA 128-byte swizzle (qb_passes.cuh swz); needs the tensor-map copy
+  uint32_t pad[1];
 };
 static_assert(sizeof(SweepHeader) % 16 == 0, "SweepHeader must stay 16-byte aligned");
 
@@ -150,6 +151,7 @@ struct PlanOp {
 };
 
 struct SweepDesc {
+  int swizzle = 0;
   int T = 0, L = 0;
   uint64_t tile_mask = 0;
   size_t blob_offset = 0, blob_bytes = 0;
@@ -628,6 +630,31 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
   sd.blob_bytes = off;
 }
 
+// Runs of consecutive state bits that are all inside / all outside the tile: the dimensions of the tensor map that
+// moves a tile with one TMA copy (qb_sweep.cuh).  A run of tile bits is cut so that a box edge stays <= 256 8-byte
+// elements; with the 128-byte swizzle the innermost run is exactly one 128-byte row.  More than 5 runs: no tensor map.
+struct TileSeg { int start, len; bool tile; };
+inline std::vector<TileSeg> tile_segments(int nqubits, int dtype, uint64_t tile_mask, bool swizzle) {
+  const int row_bits = dtype == QB_C128 ? 3 : 4;  // amplitudes per 128-byte row
+  std::vector<TileSeg> segs;
+  for (int b = 0; b < nqubits;) {
+    const bool t = (tile_mask >> b) & 1;
+    int e = b;
+    const int cap = !t ? 31 : (segs.empty() ? (swizzle ? row_bits : row_bits + 4) : 8);
+    while (e < nqubits && (((tile_mask >> e) & 1) != 0) == t && e - b < cap) ++e;
+    segs.push_back({b, e - b, t});
+    b = e;
+  }
+  return segs;
+}
+inline bool tile_swizzle_ok(int nqubits, int dtype, uint64_t tile_mask) {
+  if (env_int("QB_NO_TMA", 0) || env_int("QB_NO_SWIZZLE", 0)) return false;
+  const int row_bits = dtype == QB_C128 ? 3 : 4;
+  if ((int)__builtin_popcountll(tile_mask) < row_bits + 3) return false;  // at least eight full rows
+  if ((tile_mask & ((uint64_t(1) << row_bits) - 1)) != ((uint64_t(1) << row_bits) - 1)) return false;
+  return tile_segments(nqubits, dtype, tile_mask, true).size() <= 5;
+}
+
 template <typename C>
 inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool no_fuse, Plan& plan, std::string& err) {
   const int Tfull = tile_bits_for(dtype);
@@ -695,7 +722,9 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     hdr.tile_mask = tile_mask;
     hdr.other_mask = all & ~tile_mask;
     hdr.ntiles = uint64_t(1) << (n - T);
+    hdr.swizzle = tile_swizzle_ok(n, dtype, tile_mask) ? 1u : 0u;
     SweepDesc sd;
+    sd.swizzle = (int)hdr.swizzle;
     sd.T = T;
     sd.L = L;
     sd.tile_mask = tile_mask;

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
     const uint32_t ctid = (uint32_t)(tid - SW_COPY_THREADS) % SW_TEAM_THREADS;
     const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
     const int npasses = (int)hdr.npasses;
+    const uint32_t swz_on = hdr.swizzle ? 7u : 0u;
     constexpr int RB = SweepCfg<C>::RB;                                     // register bits of a REGTILE pass
     constexpr int TB = SWEEP_TILE_BYTES_LOG2 - (sizeof(C) == 16 ? 4 : 3);  // tile bits of a full tile
     constexpr int GPT = ((1 << (TB - RB)) + SW_TEAM_THREADS - 1) / SW_TEAM_THREADS;  // groups per thread
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
         if (pi) team_bar(team);
         if (ph.kind == PASS_REGTILE) {
           // R < RB only occurs for n < 4, which qb_apply_program routes to the K1 kernels
-          run_pass<C, RB, GPT>(tile, blob, ts, ph, T, ctid, SW_TEAM_THREADS);
+          run_pass<C, RB, GPT>(tile, blob, ts, ph, T, swz_on, ctid, SW_TEAM_THREADS);
         } else {
           const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
           if (op.slot == MU_NO_SLOT || ts[op.slot].active) {
@@ -302,9 +303,9 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
             const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
             for (uint32_t t = 0; t < ntasks; t += SW_TEAM_THREADS) {
               BigAcc<C> a;
-              big_read<C>(tile, op, payload, T, t + ctid, a);
+              big_read<C>(tile, op, payload, T, swz_on, t + ctid, a);
               team_bar(team);
-              big_write<C>(tile, op, a);
+              big_write<C>(tile, op, swz_on, a);
               if (t + SW_TEAM_THREADS < ntasks) team_bar(team);
             }
           }
@@ -341,24 +342,15 @@ inline qb_encode_tiled_fn tma_encoder() {
   return fn;
 }
 
-// Runs of consecutive state bits that are all inside / all outside the tile become tensor dimensions; a run of tile
-// bits is cut so that a box edge stays <= 256 elements.  Returns false (per-run copies) when more than 5 are needed.
-inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask, TmaDesc& d) {
+// One tensor dimension per run of state bits (tile_segments, qb_planner.hpp).  Returns false (per-run copies) when the
+// tile needs more than 5 dimensions or the driver entry point is missing.
+inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask, bool swizzle, TmaDesc& d) {
   memset(&d, 0, sizeof(d));
   if (env_int("QB_NO_TMA", 0)) return false;
   qb_encode_tiled_fn enc = tma_encoder();
   if (!enc) return false;
   const int epa = dtype == QB_C128 ? 2 : 1;  // 8-byte elements per amplitude
-  struct Seg { int start, len; bool tile; };
-  std::vector<Seg> segs;
-  for (int b = 0; b < nqubits;) {
-    const bool t = (tile_mask >> b) & 1;
-    int e = b;
-    const int cap = t ? (segs.empty() ? (epa == 2 ? 7 : 8) : 8) : 31;
-    while (e < nqubits && (((tile_mask >> e) & 1) != 0) == t && e - b < cap) ++e;
-    segs.push_back({b, e - b, t});
-    b = e;
-  }
+  std::vector<TileSeg> segs = tile_segments(nqubits, dtype, tile_mask, swizzle);
   if (segs.empty() || !segs[0].tile || segs.size() > 5) return false;
   cuuint64_t gdim[5], gstride[4];
   cuuint32_t box[5], estr[5];
@@ -383,7 +375,8 @@ inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask
     if (bytes >= (cuuint64_t(1) << 40)) return false;
     gstride[i] = bytes;
   }
-  if (enc(&d.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, state, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+  if (enc(&d.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, state, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   d.enabled = 1;
@@ -394,7 +387,7 @@ inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqub
                         const char* prog_dev) {
   uint64_t grid = sd.ntiles < (uint64_t)sm_count ? sd.ntiles : (uint64_t)sm_count;
   TmaDesc tma;
-  tma_describe(state, nqubits, dtype, sd.tile_mask, tma);
+  if (!tma_describe(state, nqubits, dtype, sd.tile_mask, sd.swizzle != 0, tma) && sd.swizzle) return QB_ERR_UNSUPPORTED;  // planned for a swizzled tile
   if (dtype == QB_C128)
     sweep_kernel<double2><<<(unsigned)grid, sw_threads<double2>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
   else

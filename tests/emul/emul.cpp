@@ -24,12 +24,13 @@ static void run_sweep(C* state, const char* blob) {
   const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
   std::vector<C> tile(size_t(1) << T);
   std::vector<TileSlot> ts(hdr.nslots + 1);
+  const uint32_t swz_on = hdr.swizzle ? 7u : 0u;
   const int GPT = sizeof(C) == 16 ? 1 : 2;  // both group counts the kernel variants use are exercised
   for (uint64_t t = 0; t < hdr.ntiles; ++t) {
     const uint64_t base = deposit(t, hdr.other_mask);
     for (uint32_t r = 0; r < nruns; ++r) {
       const uint64_t off = deposit(uint64_t(r) << L, hdr.tile_mask);
-      memcpy(&tile[size_t(r) << L], state + base + off, run * sizeof(C));
+      for (uint32_t e = 0; e < run; ++e) tile[swz<C>((r << L) + e, swz_on)] = state[base + off + e];  // TMA swizzle when planned
     }
     for (uint32_t sl = 0; sl < hdr.nslots; ++sl) {
       const uint32_t so = slot_table[sl];
@@ -46,17 +47,17 @@ static void run_sweep(C* state, const char* blob) {
         for (uint32_t ctid = 0; ctid < EMUL_THREADS; ++ctid) {
           if (GPT == 1) {
             switch (ph.R) {
-              case 1: run_pass<C, 1, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
-              case 2: run_pass<C, 2, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
-              case 3: run_pass<C, 3, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
-              default: run_pass<C, 4, 1>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              case 1: run_pass<C, 1, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+              case 2: run_pass<C, 2, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+              case 3: run_pass<C, 3, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+              default: run_pass<C, 4, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
             }
           } else {
             switch (ph.R) {
-              case 1: run_pass<C, 1, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
-              case 2: run_pass<C, 2, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
-              case 3: run_pass<C, 3, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
-              default: run_pass<C, 4, 2>(tile.data(), blob, ts.data(), ph, T, ctid, EMUL_THREADS); break;
+              case 1: run_pass<C, 1, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+              case 2: run_pass<C, 2, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+              case 3: run_pass<C, 3, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+              default: run_pass<C, 4, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
             }
           }
         }
@@ -66,13 +67,13 @@ static void run_sweep(C* state, const char* blob) {
         const C* payload = reinterpret_cast<const C*>(blob + op.payload);  // the emulator keeps the whole blob in one buffer
         const uint32_t ntasks = (1u << (T - (int)op.nins)) << (op.k - 3);
         std::vector<BigAcc<C>> accs(ntasks);
-        for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, task, accs[task]);
-        for (uint32_t task = 0; task < ntasks; ++task) big_write<C>(tile.data(), op, accs[task]);
+        for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, swz_on, task, accs[task]);
+        for (uint32_t task = 0; task < ntasks; ++task) big_write<C>(tile.data(), op, swz_on, accs[task]);
       }
     }
     for (uint32_t r = 0; r < nruns; ++r) {
       const uint64_t off = deposit(uint64_t(r) << L, hdr.tile_mask);
-      memcpy(state + base + off, &tile[size_t(r) << L], run * sizeof(C));
+      for (uint32_t e = 0; e < run; ++e) state[base + off + e] = tile[swz<C>((r << L) + e, swz_on)];
     }
   }
 }
