@@ -672,33 +672,98 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
   const uint64_t lowmask = (uint64_t(1) << Lcfg) - 1;
   const int csize = (int)sizeof(C);
 
-  size_t i = 0;
-  while (i < pops.size()) {
-    // ---- greedy: take ops while their dense targets fit the tile
+  // ---- commutation bookkeeping: X = bits an op mixes (dense / swap targets), D = bits it only reads or multiplies
+  // (controls, diagonal targets, fan bits).  Two ops commute iff neither one's X meets the other's X or D.
+  const size_t N = pops.size();
+  std::vector<uint64_t> xset(N, 0), dset(N, 0);
+  for (size_t q = 0; q < N; ++q) {
+    const PlanOp& p = pops[q];
+    for (int c : p.cpos) dset[q] |= uint64_t(1) << c;
+    if (p.kind == CK_DENSE || p.kind == CK_SWAP)
+      for (int t : p.tpos) xset[q] |= uint64_t(1) << t;
+    else if (p.kind == CK_DIAG)
+      for (int t : p.tpos) dset[q] |= uint64_t(1) << t;
+    else
+      for (auto& kv : p.fan) dset[q] |= uint64_t(1) << kv.first;
+  }
+  const bool reorder = !no_fuse && !env_int("QB_NO_REORDER", 0);
+  const size_t window = (size_t)env_int("QB_REORDER_WINDOW", 4096);
+  std::vector<char> done(N, 0);
+  size_t ndone = 0, first = 0;
+  while (ndone < N) {
+    while (first < N && done[first]) ++first;
+    // ---- list scheduling: walk the remaining ops in program order; an op joins this sweep when it commutes with
+    // every earlier op that stays behind and its dense targets fit the tile.  (Layered circuits: a sweep follows
+    // the light cone of its tile's qubits through many layers instead of stopping at the first gate outside.)
+    // `allowed`: the high tile bits a candidate tile may use (~0 = whatever the first ready gates ask for)
     uint64_t high = 0;
-    size_t j = i;
-    size_t est = sizeof(SweepHeader) + 64;
-    int slot_est = 0;
-    while (j < pops.size()) {
-      const PlanOp& p = pops[j];
-      uint64_t need = 0;
-      if (p.kind == CK_DENSE || p.kind == CK_SWAP)
-        for (int t : p.tpos) need |= uint64_t(1) << t;
-      need &= ~lowmask;
-      uint64_t nh = high | need;
-      if (__builtin_popcountll(nh) > free_high) {
-        if (j == i) { err = "gate has more target qubits outside the low bits than a tile can hold"; return false; }
-        break;
+    std::vector<size_t> chosen;
+    bool fatal = false;
+    auto scan = [&](uint64_t allowed, std::vector<size_t>& out, uint64_t& out_high, int& out_dense) {
+      uint64_t hi = 0, blocked_x = 0, blocked_d = 0;
+      size_t est = sizeof(SweepHeader) + 64;
+      int slot_est = 0;
+      out.clear();
+      out_dense = 0;
+      for (size_t q = first; q < N && q < first + window; ++q) {
+        if (done[q]) continue;
+        const PlanOp& p = pops[q];
+        bool ok = !((xset[q] & (blocked_x | blocked_d)) || (dset[q] & blocked_x));
+        if (ok) {
+          const uint64_t nh = hi | (xset[q] & ~lowmask);
+          const size_t add = blob_estimate(p, csize, T, R) + sizeof(PassHeader);
+          const int slot_add = (p.kind == CK_PHASE || p.kind == CK_DIAG || !p.cpos.empty()) ? 1 : 0;  // may need per-tile set-up
+          if (__builtin_popcountll(nh) > free_high || (nh & ~allowed)) {
+            if (allowed == ~uint64_t(0) && out.empty() && q == first) { err = "gate has more target qubits outside the low bits than a tile can hold"; fatal = true; return; }
+            ok = false;
+          } else if (!out.empty() && (est + add > (size_t)SWEEP_BLOB_MAX || (int)out.size() >= max_ops || slot_est + slot_add > SWEEP_MAX_SLOTS)) {
+            ok = false;
+            if ((int)out.size() >= max_ops) break;
+          } else if (est + add > (size_t)SWEEP_BLOB_MAX) {
+            err = "single gate does not fit the sweep program buffer";
+            fatal = true;
+            return;
+          } else {
+            hi = nh;
+            est += add;
+            slot_est += slot_add;
+            out.push_back(q);
+            if (xset[q]) ++out_dense;
+          }
+        }
+        if (!ok) {
+          if (!reorder) break;
+          blocked_x |= xset[q];
+          blocked_d |= dset[q];
+          if ((blocked_x & all) == all) break;
+        }
       }
-      size_t add = blob_estimate(p, csize, T, R) + sizeof(PassHeader);
-      const int slot_add = (p.kind == CK_PHASE || p.kind == CK_DIAG || !p.cpos.empty()) ? 1 : 0;  // may need per-tile set-up
-      if (j > i && (est + add > (size_t)SWEEP_BLOB_MAX || (int)(j - i) >= max_ops || slot_est + slot_add > SWEEP_MAX_SLOTS)) break;
-      if (est + add > (size_t)SWEEP_BLOB_MAX) { err = "single gate does not fit the sweep program buffer"; return false; }
-      high = nh;
-      est += add;
-      slot_est += slot_add;
-      ++j;
+      out_high = hi;
+    };
+    int best_dense = 0;
+    scan(~uint64_t(0), chosen, high, best_dense);
+    if (fatal) return false;
+    if (reorder && free_high > 0 && n > T) {
+      // candidate tiles: the low bits plus a window of contiguous higher bits (widest light cone); keep the one that
+      // takes the most mixing gates
+      const int step = N <= 5000 ? 1 : 3;
+      std::vector<size_t> cand;
+      for (int s0 = Lcfg; s0 + free_high <= n; s0 += step) {
+        const uint64_t allowed = ((uint64_t(1) << free_high) - 1) << s0;
+        uint64_t chigh = 0;
+        int cdense = 0;
+        scan(allowed, cand, chigh, cdense);
+        if (fatal) return false;
+        if (cdense > best_dense) {
+          best_dense = cdense;
+          chosen = cand;
+          high = chigh;
+        }
+      }
     }
+    if (chosen.empty()) { err = "internal: the sweep scheduler made no progress"; return false; }
+    for (size_t q : chosen) done[q] = 1;
+    ndone += chosen.size();
     // ---- complete the tile with the lowest unused bits (longest contiguous runs)
     uint64_t tile_mask = lowmask | high;
     for (int b = 0; b < n && __builtin_popcountll(tile_mask) < T; ++b) tile_mask |= uint64_t(1) << b;
@@ -732,7 +797,9 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
 
     // ---- H-like gates: all but the last one of the sweep run as (a+b, a-b); the last one carries the product of
     // their scalars (a scalar commutes with everything).  Halves the FP work of those gates.
-    std::vector<PlanOp> sops(pops.begin() + i, pops.begin() + j);
+    std::vector<PlanOp> sops;
+    sops.reserve(chosen.size());
+    for (size_t q : chosen) sops.push_back(pops[q]);
     if (!no_fuse && !env_int("QB_NO_ADDSUB", 0)) {
       std::vector<size_t> cand;
       for (size_t q = 0; q < sops.size(); ++q)
@@ -760,26 +827,68 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
       cur_r = 0;
       return ok;
     };
-    for (size_t q = 0; q < sops.size(); ++q) {
-      const PlanOp& p = sops[q];
-      for (int s : p.src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
-      if (p.kind == CK_DENSE && p.tpos.size() > 2) {
-        if (!close_pass()) return false;
-        if (!emit_big_pass<C>(sb, p, err)) return false;
+    // list scheduling again, one level down: a gate joins the open pass when it commutes with every gate of the sweep
+    // that stays behind and the pass still has a register bit for it (a pass follows the light cone of its <= R qubits)
+    {
+      const size_t M = sops.size();
+      std::vector<uint64_t> sx(M, 0), sd_(M, 0);
+      for (size_t q = 0; q < M; ++q) {
+        const PlanOp& p = sops[q];
+        for (int s : p.src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
+        for (int c : p.cpos) sd_[q] |= uint64_t(1) << c;
+        if (p.kind == CK_DENSE || p.kind == CK_SWAP)
+          for (int t : p.tpos) sx[q] |= uint64_t(1) << t;
+        else if (p.kind == CK_DIAG)
+          for (int t : p.tpos) sd_[q] |= uint64_t(1) << t;
+        else
+          for (auto& kv : p.fan) sd_[q] |= uint64_t(1) << kv.first;
+        if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
+      }
+      std::vector<char> placed(M, 0);
+      size_t nplaced = 0, head = 0;
+      while (nplaced < M) {
+        while (head < M && placed[head]) ++head;
+        uint64_t bx = 0, bd = 0;
+        bool took_big = false;
+        for (size_t q = head; q < M; ++q) {
+          if (placed[q]) continue;
+          const PlanOp& p = sops[q];
+          bool ok = !((sx[q] & (bx | bd)) || (sd_[q] & bx));
+          if (ok && p.kind == CK_DENSE && p.tpos.size() > 2) {
+            if (cur.empty()) {  // a dense block on 3..6 targets is a pass of its own
+              if (!emit_big_pass<C>(sb, p, err)) return false;
+              ++sd.npasses;
+              placed[q] = 1;
+              ++nplaced;
+              took_big = true;
+              break;
+            }
+            ok = false;
+          } else if (ok) {
+            uint32_t need = 0;
+            if (p.kind == CK_DENSE || p.kind == CK_SWAP)
+              for (int t : p.tpos) need |= 1u << sb.local_of_pos[t];
+            if (__builtin_popcount(need) > R) { err = "internal: gate needs more register bits than a pass has"; return false; }
+            if (__builtin_popcount(cur_r | need) > R) {
+              ok = false;
+            } else {
+              cur_r |= need;
+              cur.push_back(&p);
+              placed[q] = 1;
+              ++nplaced;
+            }
+          }
+          if (!ok) {
+            if (!reorder) break;
+            bx |= sx[q];
+            bd |= sd_[q];
+          }
+        }
+        if (took_big) continue;
+        if (cur.empty()) { err = "internal: the pass scheduler made no progress"; return false; }
         ++sd.npasses;
-        continue;
-      }
-      uint32_t need = 0;
-      if (p.kind == CK_DENSE || p.kind == CK_SWAP)
-        for (int t : p.tpos) need |= 1u << sb.local_of_pos[t];
-      if (__builtin_popcount(cur_r | need) > R) {
         if (!close_pass()) return false;
       }
-      if (__builtin_popcount(need) > R) { err = "internal: gate needs more register bits than a pass has"; return false; }
-      if (cur.empty()) ++sd.npasses;
-      cur_r |= need;
-      cur.push_back(&p);
-      if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
     }
     if (!close_pass()) return false;
     if ((int)sb.slots.size() > SWEEP_MAX_SLOTS) { err = "internal: too many per-tile slots in one sweep"; return false; }
@@ -788,7 +897,6 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     plan.npasses += sd.npasses;
     plan.ndiag += sd.ndiag;
     plan.sweeps.push_back(sd);
-    i = j;
   }
   return true;
 }

@@ -47,17 +47,54 @@ def test_no_cpu_fallback():
         Engine(0)
 
 
+def _assert_dependencies_kept(ops, sweep_of_op):
+    """The scheduler may move a gate to an earlier sweep only past gates it commutes with: two gates that share a
+    qubit and are not both diagonal must keep their order."""
+    def diag_qubits(op):
+        """qubit -> True when the gate never mixes its 0 and 1 subspaces (controls, diagonal targets)"""
+        out = {q: True for q in op.controls}
+        k = len(op.targets)
+        m = np.diag(op.data) if op.is_diagonal else np.asarray(op.data)
+        idx = np.arange(2**k)
+        for pos, q in enumerate(op.targets):
+            bit = (idx >> (k - 1 - pos)) & 1
+            out[q] = not np.any(m[bit[:, None] != bit[None, :]])
+        return out
+
+    last = {}  # qubit -> list of (sweep, acts diagonally on it) of the gates seen so far
+    for op, s in zip(ops, sweep_of_op):
+        for q, d in diag_qubits(op).items():
+            for s0, d0 in last.get(q, []):
+                if not (d and d0):
+                    assert s0 <= s
+            last.setdefault(q, []).append((s, d))
+
+
 def test_planner_packs_qft_into_few_sweeps():
     for n, dtype in ((30, "complex128"), (32, "complex128"), (31, "complex64")):
         ops = circuits.qft(n)
         stats, sweep_of_op = plan_program(n, dtype, ops)
         assert stats.nops == len(ops) == n * (n + 1) // 2 + n // 2
         assert stats.nsweeps <= 20, stats.nsweeps  # gate-by-gate would be ~500 sweeps
-        assert sweep_of_op == sorted(sweep_of_op)  # program order is preserved
+        _assert_dependencies_kept(ops, sweep_of_op)
         itemsize = 16 if dtype == "complex128" else 8
         assert stats.bytes_moved == stats.nsweeps * 2 * itemsize * 2.0**n
         stats1, _ = plan_program(n, dtype, ops, fuse=False)
         assert stats1.nsweeps == len(ops)
+
+
+def test_planner_follows_light_cones():
+    """Layered circuits: a sweep keeps taking gates of later layers as long as they commute with what stays behind."""
+    n = 32
+    ops = circuits.variational(n, 20, np.random.default_rng(7).random(2 * 20 * n))
+    stats, sweep_of_op = plan_program(n, "complex64", ops)
+    assert all(s >= 0 for s in sweep_of_op)
+    _assert_dependencies_kept(ops, sweep_of_op)
+    assert stats.nsweeps <= 60, stats.nsweeps  # prefix-greedy packing needs 149
+    ops = circuits.random_circuit(30, 300, 11)
+    stats, sweep_of_op = plan_program(30, "complex128", ops)
+    _assert_dependencies_kept(ops, sweep_of_op)
+    assert stats.nsweeps <= 40, stats.nsweeps  # prefix-greedy packing needs 53
 
 
 def test_planner_argument_errors():
