@@ -215,17 +215,17 @@ template <typename C, int R, int GPT>
 QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t swz_on, uint32_t ctid, uint32_t nct) {
   constexpr int D = 1 << R;
   const int gbits = T - R;
-  const uint32_t ngroups = 1u << gbits;
   uint32_t stride[R > 0 ? R : 1];  // physical (swizzled) offset of register bit i
 #pragma unroll
   for (int i = 0; i < R; ++i) stride[i] = swz<C>(1u << ph.pos[i], swz_on);
+  const uint16_t* gtab = reinterpret_cast<const uint16_t*>(blob + ph.gtab);
   C v[GPT][D];
   uint32_t g[GPT], t0[GPT], p0[GPT];  // group index, logical tile index of the group base, its physical index
   bool valid[GPT];
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {
-    g[u] = ctid + (uint32_t)u * nct;
-    valid[u] = g[u] < ngroups;
+    g[u] = gtab[ctid + (uint32_t)u * nct];
+    valid[u] = g[u] != 0xFFFFu;
     uint32_t t = g[u];
 #pragma unroll
     for (int i = 0; i < R; ++i) t = insert_zero32(t, ph.pos[i]);

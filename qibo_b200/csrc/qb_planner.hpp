@@ -11,6 +11,7 @@
 // Device program of one sweep (the "blob"): SweepHeader, DevOp[nops], then 16-byte aligned payloads
 // (matrices / tables in the state's precision).
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -56,6 +57,7 @@ constexpr int SWEEP_MAX_SLOTS = 48;        // ops per sweep that need per-tile s
 constexpr int SWEEP_BLOB_MAX = 26 * 1024;  // program bytes resident in shared memory next to the tiles
 constexpr int SWEEP_TILE_BYTES_LOG2 = 16;  // 64 KiB tiles, three in flight per SM
 constexpr uint32_t MU_NO_SLOT = 0xFFFF;
+constexpr int SWEEP_TEAM_THREADS = 256;    // compute threads that share one tile (8 warps); the group tables below are laid out for it
 constexpr int FAN_EXT_CHUNK = 4;           // a fan's bits outside the tile are folded through tables of 2^4 entries (<= 8 tables: 32 bits)
 constexpr size_t BIG_PAYLOAD_SMEM_MAX = 16 * 1024 + 64;  // larger dense matrices (6 targets) stay in global memory
 
@@ -117,7 +119,9 @@ struct PassHeader {
   uint32_t offset;       // byte offset of MicroOp[0] (REGTILE) or of the DevOp (BIG)
   uint16_t off[16];      // REGTILE: tile-local offset of register index j (deposit of j into rmask), precomputed
   uint8_t pos[8];        // REGTILE: tile-local positions of the register bits, ascending
-  uint32_t pad[2];
+  uint32_t gtab;         // REGTILE: byte offset of uint16[SWEEP_TEAM_THREADS * groups-per-thread]: the group (index over the
+                         // non-register tile bits, ascending) that thread `ctid` handles as its u-th, or 0xFFFF for none
+  uint32_t pad[1];
 };
 static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligned");
 
@@ -134,7 +138,9 @@ struct SweepHeader {
   uint32_t R;              // register bits of the REGTILE passes
   uint32_t slots_offset;   // uint32[nslots]: byte offset of the slot's MicroOp, or of its DevOp with bit 31 set (ops that need per-tile set-up)
   uint32_t swizzle;        // 1: the tile sits in shared memory in the TMA 128-byte swizzle (qb_passes.cuh swz); needs the tensor-map copy
-  uint32_t pad[1];
+  uint32_t warp_private;   // 1: every warp owns the same 1/8 of the tile in every pass (no REGTILE pass mixes across three fixed
+                           // tile bits): passes are separated by __syncwarp instead of a team barrier, so warps drift apart and
+                           // one warp's shared-memory bursts overlap another's FP math
 };
 static_assert(sizeof(SweepHeader) % 16 == 0, "SweepHeader must stay 16-byte aligned");
 
@@ -317,6 +323,10 @@ template <typename C> struct SweepBuilder {
   std::vector<std::vector<C>> payloads;      // one per op
   std::vector<std::pair<int, int>> payload_owner;  // payload -> (pass, micro index or -1)
   std::vector<std::pair<int, int>> slots;    // per-tile set-up slot -> (pass, micro index or -1)
+  std::vector<std::vector<uint16_t>> gtabs;  // distinct group tables
+  std::map<uint32_t, int> gtab_of_rmask;
+  std::vector<int> gtab_of_pass;             // per pass: index into gtabs, -1 for BIG
+  uint32_t split_mask = 0;                   // warp-private sweeps: the three tile bits that select the warp
 };
 
 inline bool is_real_matrix(const std::vector<cd>& m) {
@@ -333,6 +343,116 @@ inline bool is_hadamard_like(const PlanOp& p) {
 }
 
 inline int pair_index(int hi, int lo) { return hi * (hi - 1) / 2 + lo; }
+
+// ---- thread -> group mapping of a REGTILE pass ---------------------------------------------------------------
+inline uint32_t deposit_u32(uint32_t x, uint32_t mask) {
+  uint32_t r = 0;
+  for (int k = 0; mask; ++k) {
+    uint32_t low = mask & (~mask + 1);
+    if ((x >> k) & 1) r |= low;
+    mask ^= low;
+  }
+  return r;
+}
+inline uint32_t extract_u32(uint32_t x, uint32_t mask) {
+  uint32_t r = 0;
+  for (int k = 0; mask; ++k) {
+    uint32_t low = mask & (~mask + 1);
+    if (x & low) r |= 1u << k;
+    mask ^= low;
+  }
+  return r;
+}
+inline uint32_t swz_host(uint32_t x, int csize, bool swizzle) {
+  if (!swizzle) return x;
+  return csize == 16 ? x ^ ((x >> 3) & 7u) : x ^ (((x >> 4) & 7u) << 1);
+}
+// the five lowest tile bits that are neither register bits nor warp-select bits: one per lane bit
+inline uint32_t lane_bits_of(int T, uint32_t rmask, uint32_t smask) {
+  uint32_t lanes = 0;
+  for (int lb = 0; lb < T && __builtin_popcount(lanes) < 5; ++lb)
+    if (!(((rmask | smask) >> lb) & 1)) lanes |= 1u << lb;
+  return lanes;
+}
+// shared-memory wavefronts of one warp-wide tile access relative to the conflict-free count (1.0 = no bank conflict)
+inline double conflict_cost(int T, int csize, bool swizzle, uint32_t rmask, uint32_t smask) {
+  const uint32_t lanes = lane_bits_of(T, rmask, smask);
+  const int per_phase = csize == 16 ? 8 : 16;  // lanes served by one 128-byte wavefront
+  const int unit_mask = csize == 16 ? 7 : 15;  // 16-byte / 8-byte slots of a 128-byte row
+  double total = 0;
+  for (int ph = 0; ph < 32 / per_phase; ++ph) {
+    int count[16] = {0};
+    int worst = 0;
+    for (int l = 0; l < per_phase; ++l) {
+      const uint32_t t = deposit_u32((uint32_t)(ph * per_phase + l), lanes);
+      const int slot = (int)(swz_host(t, csize, swizzle) & unit_mask);
+      worst = std::max(worst, ++count[slot]);
+    }
+    total += worst;
+  }
+  return total / (32 / per_phase);
+}
+// register bits of a pass: the demanded ones, padded to R with the highest tile bits outside `smask`
+inline uint32_t pad_register_bits(int T, int R, uint32_t need, uint32_t smask) {
+  uint32_t rmask = need;
+  for (int lb = T - 1; lb >= 0 && __builtin_popcount(rmask) < R; --lb)
+    if (!(((rmask | smask) >> lb) & 1)) rmask |= 1u << lb;
+  return rmask;
+}
+// uint16 table: thread slot (u * SWEEP_TEAM_THREADS + ctid) -> group index (over the non-register bits, ascending)
+inline std::vector<uint16_t> make_group_table(int T, int R, int csize, uint32_t rmask, uint32_t smask) {
+  const int gbits = T - R;
+  const uint32_t ngroups = 1u << gbits;
+  // the kernel reads a fixed number of groups per thread for each dtype (a full tile has 2^8 / 2^9 groups)
+  const uint32_t gpt = std::max<uint32_t>((ngroups + SWEEP_TEAM_THREADS - 1) / SWEEP_TEAM_THREADS, csize == 16 ? 1u : 2u);
+  std::vector<uint16_t> tab((size_t)gpt * SWEEP_TEAM_THREADS, 0xFFFF);
+  const uint32_t all = (1u << T) - 1;
+  if (smask == 0) {
+    for (uint32_t g = 0; g < ngroups; ++g) tab[g] = (uint16_t)g;
+    return tab;
+  }
+  const uint32_t lanes = lane_bits_of(T, rmask, smask);
+  const uint32_t rest = all & ~(rmask | smask | lanes);  // walked by the group-per-thread index u
+  for (uint32_t u = 0; u < gpt; ++u)
+    for (uint32_t tid = 0; tid < (uint32_t)SWEEP_TEAM_THREADS; ++tid) {
+      const uint32_t t = deposit_u32(tid & 31u, lanes) | deposit_u32(tid >> 5, smask) | deposit_u32(u, rest);
+      tab[(size_t)u * SWEEP_TEAM_THREADS + tid] = (uint16_t)extract_u32(t, all & ~rmask);
+    }
+  return tab;
+}
+// Three tile bits that no pass needs as a register bit, chosen for the fewest bank conflicts; 0 = none (team barriers).
+inline uint32_t choose_split(int T, int R, int csize, bool swizzle, const std::vector<uint32_t>& needs, bool has_big) {
+  // Measured on B200 (QFT(30) complex128, gpurun_out/r3i_*): 9.5 ms per stage sweep with warp-private sub-tiles against
+  // 8.9 ms with team barriers -- the barrier stalls it removes are smaller than the bank conflicts its lane mapping
+  // adds -- so it stays opt-in.
+  if (has_big || !env_int("QB_WARP_PRIVATE", 0)) return 0;
+  if (T - R - 3 < 5 || (1u << (T - R)) % SWEEP_TEAM_THREADS) return 0;  // every lane must own a group
+  uint32_t used = 0;
+  for (uint32_t nd : needs) used |= nd;
+  std::vector<int> free_bits;
+  for (int lb = 0; lb < T; ++lb)
+    if (!((used >> lb) & 1)) free_bits.push_back(lb);
+  if (free_bits.size() < 3) return 0;
+  double best = 1e30;
+  uint32_t best_mask = 0;
+  for (size_t a = 0; a < free_bits.size(); ++a)
+    for (size_t b = a + 1; b < free_bits.size(); ++b)
+      for (size_t c = b + 1; c < free_bits.size(); ++c) {
+        const uint32_t sm = (1u << free_bits[a]) | (1u << free_bits[b]) | (1u << free_bits[c]);
+        double cost = 0;
+        bool ok = true;
+        for (uint32_t nd : needs) {
+          const uint32_t rm = pad_register_bits(T, R, nd, sm);
+          if (__builtin_popcount(rm) != R) { ok = false; break; }
+          cost += conflict_cost(T, csize, swizzle, rm, sm);
+        }
+        if (ok && cost < best - 1e-9) {
+          best = cost;
+          best_mask = sm;
+        }
+      }
+  return best_mask;
+}
 
 // Emits the micro-ops of one REGTILE pass given its final register-bit mask.
 template <typename C>
@@ -531,6 +651,14 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     }
   }
   ph.nmicro = (uint16_t)mops.size();
+  {
+    auto it = sb.gtab_of_rmask.find(rmask);
+    if (it == sb.gtab_of_rmask.end()) {
+      it = sb.gtab_of_rmask.emplace(rmask, (int)sb.gtabs.size()).first;
+      sb.gtabs.push_back(make_group_table(T, R, (int)sizeof(C), rmask, sb.split_mask));
+    }
+    sb.gtab_of_pass.push_back(it->second);
+  }
   sb.passes.push_back(ph);
   sb.micro.push_back(std::move(mops));
   sb.big.push_back(DevOp());
@@ -572,6 +700,7 @@ template <typename C> inline bool emit_big_pass(SweepBuilder<C>& sb, const PlanO
   ph.kind = PASS_BIG;
   sb.payload_owner.push_back({(int)sb.passes.size(), -1});
   sb.payloads.push_back(std::move(payload));
+  sb.gtab_of_pass.push_back(-1);
   sb.passes.push_back(ph);
   sb.micro.push_back({});
   sb.big.push_back(d);
@@ -596,6 +725,13 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
     else sb.micro[own.first][own.second].payload = (uint32_t)off;
     off += align16(sb.payloads[s].size() * sizeof(C));
   }
+  std::vector<uint32_t> gtab_off(sb.gtabs.size(), 0);
+  for (size_t g = 0; g < sb.gtabs.size(); ++g) {
+    gtab_off[g] = (uint32_t)off;
+    off += align16(sb.gtabs[g].size() * sizeof(uint16_t));
+  }
+  for (size_t p = 0; p < sb.passes.size(); ++p)
+    if (sb.gtab_of_pass[p] >= 0) sb.passes[p].gtab = gtab_off[sb.gtab_of_pass[p]];
   hdr.npasses = (uint32_t)sb.passes.size();
   hdr.nslots = (uint32_t)sb.slots.size();
   hdr.blob_bytes = (uint32_t)off;  // the part the kernel copies to shared memory
@@ -621,6 +757,7 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
                                  : sb.passes[own.first].offset + (uint32_t)(own.second * sizeof(MicroOp));
     memcpy(base + hdr.slots_offset + s * sizeof(uint32_t), &so, sizeof(uint32_t));
   }
+  for (size_t g = 0; g < sb.gtabs.size(); ++g) memcpy(base + gtab_off[g], sb.gtabs[g].data(), sb.gtabs[g].size() * sizeof(uint16_t));
   for (size_t s = 0; s < sb.payloads.size(); ++s) {
     auto own = sb.payload_owner[s];
     uint32_t po = own.second < 0 ? sb.big[own.first].payload : sb.micro[own.first][own.second].payload;
@@ -816,16 +953,14 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     // ---- split the sweep's ops into passes: a REGTILE pass holds ops whose dense targets fit R register bits
     std::vector<const PlanOp*> cur;
     uint32_t cur_r = 0;  // tile-local mask of the register bits demanded so far
+    struct PassPlan { std::vector<const PlanOp*> ops; uint32_t need; const PlanOp* big; };
+    std::vector<PassPlan> pplans;
     auto close_pass = [&]() -> bool {
       if (cur.empty()) return true;
-      // pad the register set to R bits, preferring high tile-local bits (keeps lanes on the low bits: no bank conflicts)
-      uint32_t rmask = cur_r;
-      for (int lb = T - 1; lb >= 0 && __builtin_popcount(rmask) < R; --lb)
-        if (!((rmask >> lb) & 1)) rmask |= 1u << lb;
-      bool ok = emit_regtile_pass<C>(sb, cur, rmask, err);
+      pplans.push_back({cur, cur_r, nullptr});
       cur.clear();
       cur_r = 0;
-      return ok;
+      return true;
     };
     // list scheduling again, one level down: a gate joins the open pass when it commutes with every gate of the sweep
     // that stays behind and the pass still has a register bit for it (a pass follows the light cone of its <= R qubits)
@@ -856,7 +991,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
           bool ok = !((sx[q] & (bx | bd)) || (sd_[q] & bx));
           if (ok && p.kind == CK_DENSE && p.tpos.size() > 2) {
             if (cur.empty()) {  // a dense block on 3..6 targets is a pass of its own
-              if (!emit_big_pass<C>(sb, p, err)) return false;
+              pplans.push_back({{}, 0u, &p});
               ++sd.npasses;
               placed[q] = 1;
               ++nplaced;
@@ -891,11 +1026,33 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
       }
     }
     if (!close_pass()) return false;
+    // ---- warp-private sub-tiles when three tile bits stay out of every pass's register set, then emit the passes
+    {
+      std::vector<uint32_t> needs;
+      bool has_big = false;
+      for (auto& pp : pplans) {
+        if (pp.big) has_big = true;
+        else needs.push_back(pp.need);
+      }
+      sb.split_mask = no_fuse ? 0u : choose_split(T, R, csize, hdr.swizzle != 0, needs, has_big);
+      hdr.warp_private = sb.split_mask ? 1u : 0u;
+      for (auto& pp : pplans) {
+        if (pp.big) {
+          if (!emit_big_pass<C>(sb, *pp.big, err)) return false;
+        } else {
+          // pad the register set to R bits, preferring high tile-local bits (keeps lanes on the low bits)
+          if (!emit_regtile_pass<C>(sb, pp.ops, pad_register_bits(T, R, pp.need, sb.split_mask), err)) return false;
+        }
+      }
+    }
     if ((int)sb.slots.size() > SWEEP_MAX_SLOTS) { err = "internal: too many per-tile slots in one sweep"; return false; }
     finish_blob<C>(sb, hdr, plan.blob, sd);
     if (hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
     plan.npasses += sd.npasses;
     plan.ndiag += sd.ndiag;
+    if (env_int("QB_PLAN_DEBUG", 0))
+      fprintf(stderr, "[qb plan] sweep %zu: ops %zu passes %d tile %#llx L %d swizzle %u warp_private %u split %#x blob %u B slots %zu\n", plan.sweeps.size(),
+              sops.size(), sd.npasses, (unsigned long long)tile_mask, L, hdr.swizzle, hdr.warp_private, sb.split_mask, hdr.blob_bytes, sb.slots.size());
     plan.sweeps.push_back(sd);
   }
   return true;

@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
     const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
     const int npasses = (int)hdr.npasses;
     const uint32_t swz_on = hdr.swizzle ? 7u : 0u;
+    const bool warp_private = hdr.warp_private != 0;
+    static_assert(SW_TEAM_THREADS == SWEEP_TEAM_THREADS, "group tables are laid out for SWEEP_TEAM_THREADS");
     constexpr int RB = SweepCfg<C>::RB;                                     // register bits of a REGTILE pass
     constexpr int TB = SWEEP_TILE_BYTES_LOG2 - (sizeof(C) == 16 ? 4 : 3);  // tile bits of a full tile
     constexpr int GPT = ((1 << (TB - RB)) + SW_TEAM_THREADS - 1) / SW_TEAM_THREADS;  // groups per thread
@@ -292,7 +294,10 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
       mbar_wait(&full[b], (uint32_t)((i / SW_NBUF) & 1));  // tile data (async proxy) + slot states (loader warp) are visible
       for (int pi = 0; pi < npasses; ++pi) {
         const PassHeader& ph = passes[pi];
-        if (pi) team_bar(team);
+        if (pi) {
+          if (warp_private) __syncwarp();  // the pass only re-reads what this warp wrote
+          else team_bar(team);
+        }
         if (ph.kind == PASS_REGTILE) {
           // R < RB only occurs for n < 4, which qb_apply_program routes to the K1 kernels
           run_pass<C, RB, GPT>(tile, blob, ts, ph, T, swz_on, ctid, SW_TEAM_THREADS);

@@ -41,26 +41,34 @@ static void run_sweep(C* state, const char* blob) {
         micro_prephase<C>(*reinterpret_cast<const MicroOp*>(blob + so), blob, base, T, ts[sl]);
       }
     }
+    auto regtile = [&](const PassHeader& ph, uint32_t ctid) {
+      if (GPT == 1) {
+        switch (ph.R) {
+          case 1: run_pass<C, 1, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 2: run_pass<C, 2, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 3: run_pass<C, 3, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          default: run_pass<C, 4, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+        }
+      } else {
+        switch (ph.R) {
+          case 1: run_pass<C, 1, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 2: run_pass<C, 2, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 3: run_pass<C, 3, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          default: run_pass<C, 4, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+        }
+      }
+    };
+    if (hdr.warp_private) {
+      // the kernel separates these passes by __syncwarp only: a warp may run all of them before another warp starts.
+      // Emulate exactly that order, so that a pass that needed another warp's output would give a wrong result here.
+      for (uint32_t w = 0; w < EMUL_THREADS / 32; ++w)
+        for (uint32_t pi = 0; pi < hdr.npasses; ++pi)
+          for (uint32_t lane = 0; lane < 32; ++lane) regtile(passes[pi], w * 32 + lane);
+    } else
     for (uint32_t pi = 0; pi < hdr.npasses; ++pi) {
       const PassHeader& ph = passes[pi];
       if (ph.kind == PASS_REGTILE) {
-        for (uint32_t ctid = 0; ctid < EMUL_THREADS; ++ctid) {
-          if (GPT == 1) {
-            switch (ph.R) {
-              case 1: run_pass<C, 1, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-              case 2: run_pass<C, 2, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-              case 3: run_pass<C, 3, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-              default: run_pass<C, 4, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-            }
-          } else {
-            switch (ph.R) {
-              case 1: run_pass<C, 1, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-              case 2: run_pass<C, 2, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-              case 3: run_pass<C, 3, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-              default: run_pass<C, 4, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-            }
-          }
-        }
+        for (uint32_t ctid = 0; ctid < EMUL_THREADS; ++ctid) regtile(ph, ctid);
       } else {
         const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
         if (op.slot != MU_NO_SLOT && !ts[op.slot].active) continue;
