@@ -12,6 +12,10 @@ namespace qb {
 
 constexpr int PERM_THREADS = 256;
 constexpr int PERM_MAX_TILE_BITS = 12;
+constexpr int PERM_MAX_ITERS = (1 << PERM_MAX_TILE_BITS) / PERM_THREADS;
+// one element of padding per 64: the store phase reads the tile transposed (a bit reversal walks it with a stride of
+// 2^6 elements = every lane on the same banks)
+QB_HD uint32_t perm_pad(uint32_t e) { return e + (e >> 6); }
 
 struct PermParams {
   int n;               // qubits
@@ -84,8 +88,11 @@ template <typename C>
 __global__ void __launch_bounds__(PERM_THREADS) k8_permute(const C* __restrict__ src, C* __restrict__ dst, const __grid_constant__ PermParams p) {
   extern __shared__ __align__(16) unsigned char perm_smem[];
   C* tile = reinterpret_cast<C*>(perm_smem);
+  __shared__ uint32_t e_of_k[PERM_MAX_ITERS];  // source-ordered tile index contributed by the iteration counter (store phase)
   const uint32_t tsize = 1u << p.tbits;
   const uint32_t iters = tsize > PERM_THREADS ? tsize / PERM_THREADS : 1;
+  if (threadIdx.x < iters) e_of_k[threadIdx.x] = perm_e_of_f((threadIdx.x * PERM_THREADS) & (tsize - 1), p);
+  __syncthreads();
   const uint64_t other = ~p.smask & ((uint64_t(1) << p.n) - 1);
   // per-thread constants: the thread id supplies the 8 low bits of the src-ordered index e (load phase) and of
   // the dst-ordered index f (store phase); the remaining tile bits advance with a masked increment
@@ -99,9 +106,22 @@ __global__ void __launch_bounds__(PERM_THREADS) k8_permute(const C* __restrict__
     const uint64_t sbase = deposit(t, other);
     const uint64_t dbase = permute_base(sbase, p);
     if (active) {
+      // batches of 8 independent loads per thread: with one load in flight per thread (the rolled loop) a CTA keeps
+      // only 4 KiB in flight and the sweep ran at half of the HBM rate
       uint64_t hi = 0;
-      for (uint32_t k = 0; k < iters; ++k) {
-        tile[threadIdx.x + k * PERM_THREADS] = ld_stream(src + (sbase | soff_lo | hi));
+      uint32_t k = 0;
+      for (; k + 8 <= iters; k += 8) {
+        C v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u] = ld_stream(src + (sbase | soff_lo | hi));
+          hi = ((hi | ~s_hi) + 1) & s_hi;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tile[perm_pad(threadIdx.x + (k + u) * PERM_THREADS)] = v[u];
+      }
+      for (; k < iters; ++k) {
+        tile[perm_pad(threadIdx.x + k * PERM_THREADS)] = ld_stream(src + (sbase | soff_lo | hi));
         hi = ((hi | ~s_hi) + 1) & s_hi;
       }
     }
@@ -109,8 +129,8 @@ __global__ void __launch_bounds__(PERM_THREADS) k8_permute(const C* __restrict__
     if (active) {
       uint64_t hi = 0;
       for (uint32_t k = 0; k < iters; ++k) {
-        const uint32_t e = e_lo_of_f | perm_e_of_f((k * PERM_THREADS) & (tsize - 1), p);
-        st_stream(dst + (dbase | doff_lo | hi), tile[e]);
+        const uint32_t e = e_lo_of_f | e_of_k[k];
+        st_stream(dst + (dbase | doff_lo | hi), tile[perm_pad(e)]);
         hi = ((hi | ~d_hi) + 1) & d_hi;
       }
     }
@@ -120,7 +140,7 @@ __global__ void __launch_bounds__(PERM_THREADS) k8_permute(const C* __restrict__
 
 inline int launch_permute(cudaStream_t stream, int sm_count, const void* src, void* dst, int dtype, const PermParams& p) {
   const size_t esize = dtype == QB_C128 ? 16 : 8;
-  const size_t smem = esize << p.tbits;
+  const size_t smem = esize * (size_t)perm_pad(1u << p.tbits);
   uint64_t cap = (uint64_t)sm_count * 3;
   unsigned grid = (unsigned)(p.ntiles < cap ? p.ntiles : cap);
   if (dtype == QB_C128) {
