@@ -22,6 +22,7 @@ NumPy shard executor over a world_size-2/4 gloo group.
 """
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -407,8 +408,30 @@ def execute_circuit(backend, circuit, initial_state=None, nshots=None):
         host = backend.to_numpy(initial_state) if isinstance(initial_state, DeviceArray) else np.asarray(initial_state)
         shard = prog.scatter(host)
     prog.run(shard, timed=False)
-    if n > 30:
-        raise_error(NotImplementedError, "gathering a state of more than 30 qubits on every rank is not supported; use ShardedProgram")
+    gather_max = int(os.environ.get("QB_GATHER_MAX_QUBITS", 30))
+    if n > gather_max:
+        # too large to replicate: measurement outcomes come from the sharded state (dist_measure.py) -- marginal over the
+        # measured qubits (all-reduce), then inverse-CDF sampling with the global legacy RNG as sample_shots does
+        # (abstract.py:2774-2781).  Without measurements there is nothing a single process could hold.
+        if not circuit.measurements:
+            raise_error(NotImplementedError, f"gathering a state of more than {gather_max} qubits on every rank is not supported; "
+                        "measure it or use ShardedProgram / ShardMeasure")
+        from qibo.result import MeasurementOutcomes
+
+        from qibo_b200.dist_measure import EngineLocal, ShardMeasure
+
+        qubits = []
+        for m in circuit.measurements:
+            qubits.extend(q for q in m.qubits if q not in qubits)
+        qubits = sorted(qubits)  # measurement_gate.qubits order (result.py:204)
+        sm = ShardMeasure(n, EngineLocal(backend.engine_gpu))
+        probs, sharded = sm.probabilities(shard, qubits)
+        nshots = 1000 if nshots is None else nshots
+        uniforms = np.random.random_sample(nshots)  # every rank must hold the same seed (Backend.set_seed)
+        samples = sm.sample(probs, uniforms, sharded).cpu().numpy()
+        binary = backend.samples_to_binary(samples, len(qubits))
+        circuit._final_state = MeasurementOutcomes(circuit.measurements, backend=backend, samples=binary, nshots=nshots)
+        return circuit._final_state
     full = backend.engine_gpu.upload(prog.gather(shard))
     if circuit.measurements:
         circuit._final_state = CircuitResult(full, circuit.measurements, backend=backend, nshots=1000 if nshots is None else nshots)

@@ -129,3 +129,100 @@ def test_specialise_global_control_and_diagonal():
     rz = PhysOp(np.array([np.exp(-0.1j), np.exp(0.1j)]), (4,), (2,), True)
     op = specialise(rz, 4, 1)
     assert op.is_diagonal and op.targets == () and op.controls == (1,) and abs(op.data[0] - np.exp(0.1j)) < 1e-15
+
+
+# ---- sharded measurement (qibo_b200/dist_measure.py): collectives over gloo, shard-local arithmetic by the oracle ----
+class _OracleLocal:
+    """TEST INFRASTRUCTURE: NumPy stand-in for dist_measure.EngineLocal (CPU shards are plain torch tensors)."""
+
+    def probabilities(self, shard, qubits, nlocal):
+        from oracle import numpy_oracle as orc
+
+        return torch.from_numpy(np.ascontiguousarray(orc.calculate_probabilities(shard.numpy(), list(qubits), nlocal)))
+
+    def cdf(self, probs):
+        c = np.cumsum(probs.numpy().astype(np.float64))
+        return torch.from_numpy(c / c[-1])
+
+    def search(self, cdf, uniforms):
+        return torch.from_numpy(np.searchsorted(cdf.numpy(), uniforms.numpy(), side="right").astype(np.int64))
+
+    def collapse(self, shard, nlocal, qubits, outcome):
+        arr = shard.numpy()
+        keep = np.ones(arr.shape[0], dtype=bool)
+        idx = np.arange(arr.shape[0])
+        for pos, q in enumerate(qubits):
+            bit = (outcome >> (len(qubits) - 1 - pos)) & 1
+            keep &= ((idx >> (nlocal - 1 - q)) & 1) == bit
+        arr[~keep] = 0
+
+    def zero(self, shard):
+        shard.zero_()
+
+    def norm2(self, shard):
+        return float((shard.abs() ** 2).sum())
+
+    def scale(self, shard, nlocal, factor):
+        shard.mul_(factor)
+
+    def device(self, shard):
+        return shard.device
+
+
+def _measure_worker(rank, world, port, n, out):
+    sys.path[:0] = [ROOT, HERE]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import rand_state
+        from oracle import numpy_oracle as orc
+        from qibo_b200.dist_measure import ShardMeasure
+
+        psi = rand_state(n, 21)
+        sm = ShardMeasure(n, _OracleLocal())
+        nl = sm.nlocal
+        shard = torch.from_numpy(psi[rank << nl : (rank + 1) << nl].copy())
+        errs = []
+        for qubits in ([0], [n - 1], [1, 3], [3, 0, 2], [4, 1], list(range(n))[::-1], [2, 5, 0, 1]):
+            p, sharded = sm.probabilities(shard, qubits)
+            assert not sharded
+            errs.append(float(np.abs(p.numpy() - orc.calculate_probabilities(psi, qubits, n)).max()))
+        p, sharded = sm.probabilities(shard, list(range(n)))
+        assert sharded and p.numel() == 1 << nl
+        full = np.abs(psi) ** 2
+        errs.append(float(np.abs(p.numpy() - full[rank << nl : (rank + 1) << nl]).max()))
+        # sampling from the sharded distribution == inverse CDF on the full one (same uniforms)
+        u = np.random.default_rng(5).random(2000)
+        s = sm.sample(p, u, sharded=True).numpy()
+        c = np.cumsum(full)
+        ref = np.searchsorted(c / c[-1], u, side="right")
+        mismatch = int((s != ref).sum())
+        # collapse over a mix of global and local qubits
+        for qubits, outcome in (([0, 2], 1), ([1], 1), ([0, 1, 4], 5), ([3, 5], 2)):
+            sh = shard.clone()
+            sm.collapse(sh, qubits, outcome)
+            parts = [torch.empty_like(sh) for _ in range(world)]
+            dist.all_gather(parts, sh)
+            got = torch.cat(parts).numpy()
+            want = orc.collapse_statevector(psi, qubits, [outcome], n)
+            errs.append(float(np.abs(got - want).max()))
+        if rank == 0:
+            out.put((max(errs), mismatch))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_measurement_matches_oracle(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_measure_worker, args=(r, world, port, 7, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    err, mismatch = out.get()
+    assert err < 1e-12
+    assert mismatch <= 2  # a uniform within rounding of a rank boundary of the CDF may land on the neighbouring bin
