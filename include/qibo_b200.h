@@ -149,6 +149,15 @@ int qb_sample(qb_handle h, const void* probs, int rdtype, uint64_t nbins, const 
 int qb_collapse(qb_handle h, void* state, int nqubits, int dtype, const int* qubits, int nmeasured,
                 uint64_t outcome, int normalize);
 
+/* ---- K9: expectation values without leaving the device (abstract.py:2946-3054 exp_value_observable_symbolic: the
+ * einsum contraction of one Pauli term with the state; abstract.py:2180-2190 overlap_statevector) --------------------
+ * <psi| P |psi> for the Pauli string `paulis` (characters I, X, Y, Z; paulis[i] acts on qubits[i]): one read pass over
+ * the state, no copy.  out_host receives (re, im); the imaginary part vanishes up to rounding for a normalised state. */
+int qb_expval_pauli(qb_handle h, const void* state, int nqubits, int dtype, const char* paulis, const int* qubits,
+                    int nterm_qubits, double* out_host);
+/* <a|b> = sum conj(a) b of two buffers of 2^nqubits amplitudes; out_host receives (re, im). */
+int qb_state_vdot(qb_handle h, const void* a, const void* b, int nqubits, int dtype, double* out_host);
+
 /* ---- K7: global<->local qubit exchange for the distributed scheme (models/distcircuit.py; the
  * executor Backend.execute_distributed_circuit is NotImplemented in-tree, abstract.py:2638-2647) -----
  * Copies the half of the shard with local qubit `local_qubit` == `bit` into/out of a contiguous

@@ -404,3 +404,17 @@ def run_ops(state, ops, nqubits, dtype=None):
     for name, qubits, params in ops:
         state = apply_gate(state, gate_matrix(name, *params, dtype=dtype), qubits, nqubits)
     return state
+
+
+def pauli_expectation(state, paulis, qubits, nqubits):
+    """<state| P |state> for a Pauli string: the contraction backends/abstract.py:3030-3053 performs for one term of
+    ``exp_value_observable_symbolic`` ("abc,ad,cf,dbf->": conj(state), the 2x2 matrices, state), restated as
+    einsum over the reshaped state."""
+    mats = {"I": np.eye(2), "X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1.0, -1.0])}
+    psi = np.asarray(state, dtype=np.complex128).reshape(nqubits * (2,))
+    phi = psi
+    for f, q in zip(paulis, qubits):
+        if f == "I":
+            continue
+        phi = np.moveaxis(np.tensordot(mats[f].astype(np.complex128), phi, axes=([1], [q])), 0, q)
+    return complex(np.vdot(psi, phi))

@@ -383,6 +383,32 @@ class B200Backend(NumpyBackend):
         except self.oom_error:
             raise_error(RuntimeError, f"State does not fit in {self.device} memory.")
 
+    # ------------------------------------------------------------------ f1: expectation values ----------------
+    def exp_value_observable_symbolic(self, circuit, terms, term_qubits, term_coefficients, nqubits):
+        """Sum of Pauli-string terms on the final state (abstract.py:2946-3054).  State vectors never leave the GPU:
+        every term is one read pass of K9 (``qb_expval_pauli``) instead of an einsum over a host copy.  Density
+        matrices and non-Pauli factors keep the reference's host contraction."""
+        if circuit.density_matrix or any(f not in "IXYZ" for term in terms for f in term):
+            return super().exp_value_observable_symbolic(circuit, terms, term_qubits, term_coefficients, nqubits)
+        result = circuit._final_state if circuit._final_state is not None else self.execute_circuit(circuit)
+        state = self._to_device(result.state())
+        eng = self.engine_gpu
+        expval = 0.0
+        for term, qubits, coefficient in zip(terms, term_qubits, term_coefficients):
+            kept = [(f, int(q)) for f, q in zip(term, qubits) if f != "I"]
+            value = eng.expval_pauli(state, nqubits, "".join(f for f, _ in kept), [q for _, q in kept])
+            expval += float(np.real(coefficient * value))
+        return expval
+
+    def overlap_statevector(self, state_1, state_2, dtype=None):
+        """<state_1|state_2> (abstract.py:2180-2190) with K9 when both states already live on the device."""
+        if (isinstance(state_1, DeviceArray) and isinstance(state_2, DeviceArray) and state_1.dtype == state_2.dtype
+                and state_1.dtype.kind == "c" and state_1.ndim == 1 and state_1.shape == state_2.shape):
+            n = int(np.log2(state_1.shape[0]))
+            if 1 << n == state_1.shape[0]:
+                return self.engine_gpu.vdot(state_1, state_2, n)
+        return super().overlap_statevector(state_1, state_2, dtype=dtype)
+
     # ------------------------------------------------------------------ P1: probabilities ------------------
     def calculate_probabilities(self, state, qubits, nqubits, density_matrix=False):
         qubits = [int(q) for q in qubits]

@@ -560,6 +560,76 @@ int qb_permute_qubits(qb_handle h, const void* src, void* dst, int nqubits, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K9: expectation values
+// ---------------------------------------------------------------------------------------------------
+static int reduce2_to_host(qb_context* h, int grid, double* out_host) {
+  double* partial = (double*)h->scratch + 8;
+  double* out = (double*)h->scratch;
+  k9_sum_partials2<<<1, 32, 0, h->stream>>>(partial, partial + grid, grid, out);
+  QB_CHECK_LAUNCH("k9_sum_partials2");
+  QB_CUDA(cudaMemcpyAsync(out_host, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB_OK;
+}
+
+int qb_expval_pauli(qb_handle h, const void* state, int nqubits, int dtype, const char* paulis, const int* qubits, int nterms_qubits,
+                    double* out_host) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !out_host || nterms_qubits < 0 || (nterms_qubits && (!paulis || !qubits)))
+    return fail(QB_ERR_INVALID, "bad expectation-value arguments");
+  uint64_t xmask = 0, zmask = 0, seen = 0;
+  int ny = 0;
+  for (int i = 0; i < nterms_qubits; ++i) {
+    const int q = qubits[i];
+    if (q < 0 || q >= nqubits || ((seen >> q) & 1)) return fail(QB_ERR_INVALID, "bad or repeated qubit in Pauli string");
+    seen |= uint64_t(1) << q;
+    const uint64_t bit = uint64_t(1) << (nqubits - 1 - q);
+    switch (paulis[i]) {
+      case 'I': break;
+      case 'X': xmask |= bit; break;
+      case 'Y': xmask |= bit; zmask |= bit; ++ny; break;
+      case 'Z': zmask |= bit; break;
+      default: return fail(QB_ERR_INVALID, "Pauli strings are made of I, X, Y, Z");
+    }
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  const uint64_t count = uint64_t(1) << nqubits;
+  const int grid = grid_for(count, RED_THREADS, h->sm_count, 8);
+  int rc = ensure_scratch(h, (size_t)(2 * grid + 8) * sizeof(double));
+  if (rc != QB_OK) return rc;
+  double* partial = (double*)h->scratch + 8;
+  if (dtype == QB_C128) k9_pauli_expval<double2><<<grid, RED_THREADS, 0, h->stream>>>((const double2*)state, count, xmask, zmask, partial, partial + grid);
+  else k9_pauli_expval<float2><<<grid, RED_THREADS, 0, h->stream>>>((const float2*)state, count, xmask, zmask, partial, partial + grid);
+  QB_CHECK_LAUNCH("k9_pauli_expval");
+  double v[2];
+  rc = reduce2_to_host(h, grid, v);
+  if (rc != QB_OK) return rc;
+  // times i^{nY}
+  switch (ny & 3) {
+    case 0: out_host[0] = v[0]; out_host[1] = v[1]; break;
+    case 1: out_host[0] = -v[1]; out_host[1] = v[0]; break;
+    case 2: out_host[0] = -v[0]; out_host[1] = -v[1]; break;
+    default: out_host[0] = v[1]; out_host[1] = -v[0]; break;
+  }
+  return QB_OK;
+}
+
+int qb_state_vdot(qb_handle h, const void* a, const void* b, int nqubits, int dtype, double* out_host) {
+  if (!h || !valid_state_args(a, nqubits, dtype) || !b || !out_host) return fail(QB_ERR_INVALID, "bad inner-product arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  const uint64_t count = uint64_t(1) << nqubits;
+  const int grid = grid_for(count, RED_THREADS, h->sm_count, 8);
+  int rc = ensure_scratch(h, (size_t)(2 * grid + 8) * sizeof(double));
+  if (rc != QB_OK) return rc;
+  double* partial = (double*)h->scratch + 8;
+  if (dtype == QB_C128) k9_vdot<double2><<<grid, RED_THREADS, 0, h->stream>>>((const double2*)a, (const double2*)b, count, partial, partial + grid);
+  else k9_vdot<float2><<<grid, RED_THREADS, 0, h->stream>>>((const float2*)a, (const float2*)b, count, partial, partial + grid);
+  QB_CHECK_LAUNCH("k9_vdot");
+  return reduce2_to_host(h, grid, out_host);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K3
 // ---------------------------------------------------------------------------------------------------
 int qb_probabilities(qb_handle h, const void* state, int nqubits, int dtype, const int* qubits, int nmeasured,

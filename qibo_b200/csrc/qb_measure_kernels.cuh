@@ -286,4 +286,69 @@ __global__ void __launch_bounds__(256) k5_project(C* __restrict__ state, uint64_
   }
 }
 
+// ---- K9: <psi| P |psi> for a Pauli string, and <a|b> ------------------------------------------------------------------
+// P|x> = i^{nY} (-1)^{popcount(x & zmask)} |x ^ xmask>  (xmask: bits with X or Y, zmask: bits with Z or Y), so
+// <psi|P|psi> = i^{nY} sum_x (-1)^{popcount(x & zmask)} conj(psi[x ^ xmask]) psi[x]: one read pass over the state (the
+// partner read hits the same lines when xmask only flips low bits, another resident line otherwise), no copy of the
+// state and no gate application.  Deterministic two-stage sums (block partials in a fixed order).
+template <typename C>
+__global__ void __launch_bounds__(RED_THREADS) k9_pauli_expval(const C* __restrict__ state, uint64_t count, uint64_t xmask, uint64_t zmask,
+                                                               double* __restrict__ partial_re, double* __restrict__ partial_im) {
+  __shared__ double sm[RED_THREADS / 32];
+  double re = 0.0, im = 0.0;
+  const uint64_t stride = uint64_t(gridDim.x) * RED_THREADS;
+  for (uint64_t x = uint64_t(blockIdx.x) * RED_THREADS + threadIdx.x; x < count; x += stride) {
+    const C a = ld_stream(state + x);
+    const C b = xmask ? __ldg(state + (x ^ xmask)) : a;
+    // conj(b) * a
+    double pr = (double)b.x * (double)a.x + (double)b.y * (double)a.y;
+    double pi = (double)b.x * (double)a.y - (double)b.y * (double)a.x;
+    if (__popcll(x & zmask) & 1) {
+      pr = -pr;
+      pi = -pi;
+    }
+    re += pr;
+    im += pi;
+  }
+  const double r = block_sum<RED_THREADS>(re, sm);
+  __syncthreads();
+  const double i = block_sum<RED_THREADS>(im, sm);
+  if (threadIdx.x == 0) {
+    partial_re[blockIdx.x] = r;
+    partial_im[blockIdx.x] = i;
+  }
+}
+
+template <typename C>
+__global__ void __launch_bounds__(RED_THREADS) k9_vdot(const C* __restrict__ a, const C* __restrict__ b, uint64_t count,
+                                                       double* __restrict__ partial_re, double* __restrict__ partial_im) {
+  __shared__ double sm[RED_THREADS / 32];
+  double re = 0.0, im = 0.0;
+  const uint64_t stride = uint64_t(gridDim.x) * RED_THREADS;
+  for (uint64_t x = uint64_t(blockIdx.x) * RED_THREADS + threadIdx.x; x < count; x += stride) {
+    const C u = ld_stream(a + x), v = ld_stream(b + x);
+    re += (double)u.x * (double)v.x + (double)u.y * (double)v.y;  // conj(u) * v
+    im += (double)u.x * (double)v.y - (double)u.y * (double)v.x;
+  }
+  const double r = block_sum<RED_THREADS>(re, sm);
+  __syncthreads();
+  const double i = block_sum<RED_THREADS>(im, sm);
+  if (threadIdx.x == 0) {
+    partial_re[blockIdx.x] = r;
+    partial_im[blockIdx.x] = i;
+  }
+}
+
+__global__ void k9_sum_partials2(const double* __restrict__ pre, const double* __restrict__ pim, int n, double* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0, t = 0.0;
+    for (int i = 0; i < n; ++i) {
+      s += pre[i];
+      t += pim[i];
+    }
+    out[0] = s;
+    out[1] = t;
+  }
+}
+
 }  // namespace qb

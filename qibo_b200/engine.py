@@ -235,6 +235,25 @@ class Engine:
         _lib.check(self.lib.qb_sample_cdf(self.handle, cdf.data_ptr(), cdf.size, uniforms.data_ptr(), uniforms.size, out.data_ptr()))
         return out
 
+    # ---- K9: expectation values ------------------------------------------------------------------------------
+    def expval_pauli(self, state: DeviceArray, nqubits: int, paulis: str, qubits: Sequence[int]) -> complex:
+        """<state| P |state> for the Pauli string ``paulis`` (one of I, X, Y, Z per entry of ``qubits``)."""
+        out = (ctypes.c_double * 2)()
+        _lib.check(
+            self.lib.qb_expval_pauli(
+                self.handle, state.data_ptr(), nqubits, _DT[state.dtype], paulis.encode(), _int_array(qubits), len(qubits), out
+            )
+        )
+        return complex(out[0], out[1])
+
+    def vdot(self, a: DeviceArray, b: DeviceArray, nqubits: int) -> complex:
+        """<a|b> (conjugate on the first argument, as numpy.vdot)."""
+        if a.dtype != b.dtype:
+            raise ValueError("vdot needs two states of the same dtype")
+        out = (ctypes.c_double * 2)()
+        _lib.check(self.lib.qb_state_vdot(self.handle, a.data_ptr(), b.data_ptr(), nqubits, _DT[a.dtype], out))
+        return complex(out[0], out[1])
+
     # ---- K5: collapse -----------------------------------------------------------------------------------
     def collapse(self, state: DeviceArray, nqubits: int, qubits: Sequence[int], outcome: int, normalize: bool = True):
         _lib.check(

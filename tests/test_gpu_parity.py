@@ -2,6 +2,7 @@
 reference's golden vectors.  Tolerances are the north star's: 1e-12 max-abs complex128, 1e-5 complex64;
 samples bit-exact for the same uniforms."""
 
+import os
 from collections import Counter
 
 import numpy as np
@@ -335,3 +336,36 @@ def test_six_qubit_dense_block(eng, dtype):
     scale = 20 if dtype == "complex64" else 1
     assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
     assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype) * scale  # apply_op routes k = 6 to the sweep kernel
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_pauli_expectation_and_vdot(eng, dtype):
+    """K9 against the reference's golden expectation values and against the oracle on random strings (incl. strings
+    that flip the highest and the lowest bit, identity factors, and many Y factors for the i^nY bookkeeping)."""
+    import json
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "expval_golden.npz"))
+    t = 1e-12 if dtype == "complex128" else 2e-6
+    for i, c in enumerate(json.loads(str(z["cases"]))):
+        n = c["nqubits"]
+        st = eng.upload(z[f"ev{i}_state"].astype(dtype))
+        got = [eng.expval_pauli(st, n, term, q) for term, q in zip(c["terms"], c["term_qubits"])]
+        assert np.abs(np.real(got) - z[f"ev{i}_per_term"]).max() < t
+        assert np.abs(np.imag(got)).max() < t
+        other = eng.upload(z[f"ev{i}_other"].astype(dtype))
+        assert abs(eng.vdot(st, other, n) - complex(z[f"ev{i}_overlap"])) < t
+    n = 18
+    psi = rand_state(n, 5, dtype)
+    st = eng.upload(psi)
+    rng = np.random.default_rng(9)
+    strings = [("X", [0]), ("Y", [n - 1]), ("Z", [3]), ("XYZ", [0, n - 1, 7]), ("YYYY", [1, 2, 3, 4]), ("IZI", [5, 6, 7]), ("", [])]
+    for _ in range(10):
+        k = int(rng.integers(1, 7))
+        strings.append(("".join(rng.choice(list("IXYZ"), size=k)), [int(q) for q in rng.choice(n, size=k, replace=False)]))
+    for term, qubits in strings:
+        want = orc.pauli_expectation(psi.astype(np.complex128), term, qubits, n)
+        assert abs(eng.expval_pauli(st, n, term, qubits) - want) < t, (term, qubits)
+    with pytest.raises(ValueError):
+        eng.expval_pauli(st, n, "XQ", [0, 1])
+    with pytest.raises(ValueError):
+        eng.expval_pauli(st, n, "XX", [1, 1])

@@ -224,3 +224,36 @@ def test_initial_state_not_clobbered_and_errors(backends):
     c.add(gates.H(0))
     with pytest.raises(RuntimeError):
         ours.execute_circuit(c)
+
+
+def test_symbolic_hamiltonian_expectation_on_device(backends):
+    """f1: `SymbolicHamiltonian.expectation(circuit)` -> Backend.exp_value_observable_symbolic
+    (abstract.py:2946-3054) runs term by term on the device state (K9) and matches the NumpyBackend; the overlap of
+    two device states goes through K9 as well."""
+    from qibo import Circuit, gates
+    from qibo.hamiltonians import SymbolicHamiltonian
+    from qibo.symbols import X, Y, Z
+
+    ours, ref = backends
+    n = 6
+
+    def circuit():
+        c = Circuit(n)
+        for q in range(n):
+            c.add(gates.RY(q, theta=0.2 + 0.37 * q))
+            c.add(gates.RX(q, theta=1.1 - 0.21 * q))
+        for q in range(n - 1):
+            c.add(gates.CNOT(q, q + 1))
+        return c
+
+    def form():
+        return 0.7 * X(0) * Z(3) - 1.3 * Y(1) * Y(2) + 0.25 * Z(5) + 2.0 * X(2) * Y(4) * Z(0) + 0.4
+
+    a = SymbolicHamiltonian(form(), nqubits=n, backend=ours).expectation(circuit())
+    b = SymbolicHamiltonian(form(), nqubits=n, backend=ref).expectation(circuit())
+    assert abs(float(a) - float(b)) < 1e-12
+    s1 = ours.execute_circuit(circuit()).state()
+    s2 = ours.execute_circuit(Circuit(n)).state()
+    r1 = ref.execute_circuit(circuit()).state()
+    r2 = ref.execute_circuit(Circuit(n)).state()
+    assert abs(complex(ours.overlap_statevector(s1, s2)) - complex(ref.overlap_statevector(r1, r2))) < 1e-12

@@ -129,3 +129,20 @@ def test_samples_binary_decimal_roundtrip():
     assert b.shape == (4, 10) and b[1].tolist() == [0, 0, 0, 0, 0, 0, 0, 1, 0, 1]
     np.testing.assert_array_equal(orc.samples_to_decimal(b, 10), s)
     assert orc.calculate_frequencies(np.array([1, 1, 3])) == Counter({1: 2, 3: 1})
+
+
+def test_pauli_expectation_matches_reference():
+    """f1: the oracle's one-term contraction against Backend.exp_value_observable_symbolic / overlap_statevector of the
+    reference NumpyBackend (tests/golden/make_expval_golden.py)."""
+    import json
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "expval_golden.npz"))
+    for i, c in enumerate(json.loads(str(z["cases"]))):
+        n, state = c["nqubits"], z[f"ev{i}_state"]
+        got = [orc.pauli_expectation(state, t, q, n) for t, q in zip(c["terms"], c["term_qubits"])]
+        assert np.abs(np.imag(got)).max() < 1e-14
+        assert np.abs(np.real(got) - z[f"ev{i}_per_term"]).max() < 1e-13
+        total = sum(co * g.real for co, g in zip(c["coefficients"], got))
+        assert abs(total - c["total"]) < 1e-12
+        assert abs(np.vdot(state, z[f"ev{i}_other"]) - complex(z[f"ev{i}_overlap"])) < 1e-14
