@@ -158,14 +158,28 @@ template <typename C, int R, int HI, int LO> QB_HD void mu_swap(C* v, uint32_t c
 }
 
 // fan: phase(t) = ext_factor * TA[g & mask] * TB[g >> la] * G[j]  on the amplitudes whose controls are set.
-// CB: 0..R-1 = the only register-bit control is bit CB (static); R = none; R+1 = run-time mask
+// CB: 0..R-1 = the only register-bit control is bit CB (static) AND the fan has no factor on register bits above CB
+// (the planner checks it; true for every QFT stage, whose fan only reaches the qubits after the control): the 2^(R-1)
+// controlled amplitudes then share 2^CB distinct phases -- 47 instead of 64 complex products per four-stage pass;
+// R = no register-bit control; R+1 = run-time mask
 template <typename C, int R, int CB> QB_HD void mu_fan(C* v, const C p0, const C* gt, uint32_t creg) {
   constexpr int D = 1 << R;
+  if constexpr (CB < R) {
+    constexpr int ND = 1 << CB;
+    C ph[ND];
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
-    if (CB < R && !((j >> CB) & 1)) continue;
-    if (CB == R + 1 && (uint32_t(j) & creg) != creg) continue;
-    cmul_inplace(v[j], cmul(p0, gt[j]));
+    for (int jl = 0; jl < ND; ++jl) ph[jl] = cmul(p0, gt[jl | ND]);
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (!((j >> CB) & 1)) continue;
+      cmul_inplace(v[j], ph[j & (ND - 1)]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (CB == R + 1 && (uint32_t(j) & creg) != creg) continue;
+      cmul_inplace(v[j], cmul(p0, gt[j]));
+    }
   }
 }
 // lone controlled phase: v[j] *= ph on the register indices whose control bits are set
@@ -209,13 +223,52 @@ template <typename C, int R> QB_HD void mu_diagk(C* v, const MicroOp& mo, const 
 
 struct alignas(16) MicroHot { uint32_t w0, creg, cthr, payload; };  // first 16 bytes of MicroOp
 
+// one fused stage: 2x2 gate on register bit I ((a+b, a-b) or a real matrix), then the fan controlled by bit I
+template <typename C, int R, int GPT, int I>
+QB_HD void stage_op(C (&v)[GPT][1 << R], const uint32_t* g, const bool* valid, const MicroOp& mo, const char* blob, const TileSlot* ts, int gbits) {
+  const MicroHot hot = *reinterpret_cast<const MicroHot*>(&mo);
+  const uint32_t handler = hot.w0 & 0xFF, slot = hot.w0 >> 16;
+  if (!ts[slot].active) return;
+  const C* ta = reinterpret_cast<const C*>(blob + hot.payload);
+  const uint32_t la = mo.la;
+  const C* tb = ta + (1u << la);
+  const C* gt = tb + (1u << (gbits - (int)la));
+  const C ext = slot_ext<C>(ts[slot]);
+  if (handler >= MH_STAGE_R) {
+    const C* inl = reinterpret_cast<const C*>(mo.inl);
+    const C m[4] = {inl[0], inl[1], inl[2], inl[3]};
+#pragma unroll
+    for (int u = 0; u < GPT; ++u)
+      if (valid[u]) mu_real1<C, R, I, 0>(v[u], m, 0u);
+  } else {
+#pragma unroll
+    for (int u = 0; u < GPT; ++u)
+      if (valid[u]) mu_addsub<C, R, I, 0>(v[u], 0u);
+  }
+#pragma unroll
+  for (int u = 0; u < GPT; ++u)
+    if (valid[u]) {
+      C ph0 = cmul(ext, ta[g[u] & ((1u << la) - 1)]);
+      ph0 = cmul(ph0, tb[g[u] >> la]);
+      mu_fan<C, R, I>(v[u], ph0, gt, 0u);
+    }
+}
+template <typename C, int R, int GPT, int I>
+QB_HD void stage_chain(C (&v)[GPT][1 << R], const uint32_t* g, const bool* valid, const MicroOp* mops, int& mi, uint32_t mask, const char* blob,
+                       const TileSlot* ts, int gbits) {
+  if constexpr (I >= 0) {
+    if ((mask >> I) & 1) stage_op<C, R, GPT, I>(v, g, valid, mops[mi++], blob, ts, gbits);
+    stage_chain<C, R, GPT, I - 1>(v, g, valid, mops, mi, mask, blob, ts, gbits);
+  }
+}
+
 // One REGTILE pass over the tile.  Each thread keeps GPT groups in registers at once, so that the decode of a
 // micro-op is paid once per GPT * 2^R amplitudes.  `ts` = this team's per-tile slot states.
 template <typename C, int R, int GPT>
 QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t swz_on, uint32_t ctid, uint32_t nct) {
   constexpr int D = 1 << R;
   const int gbits = T - R;
-  uint32_t stride[R > 0 ? R : 1];  // physical (swizzled) offset of register bit i
+  uint32_t stride[R > 0 ? R : 1];  // physical (swizzled) offset of register bit i (swz is linear over XOR)
 #pragma unroll
   for (int i = 0; i < R; ++i) stride[i] = swz<C>(1u << ph.pos[i], swz_on);
   const uint16_t* gtab = reinterpret_cast<const uint16_t*>(blob + ph.gtab);
@@ -244,6 +297,12 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
   }
   const MicroOp* mops = reinterpret_cast<const MicroOp*>(blob + ph.offset);
   const int nmicro = (int)ph.nmicro;
+  if (ph.stage_mask) {
+    // a pass made of fused stage ops on descending register bits (every QFT pass): straight-line code, no per-op
+    // jump sequence (ncu: the compare tree nvcc makes of the handler switch costs ~5 dependent branches per op)
+    int mi = 0;
+    stage_chain<C, R, GPT, R - 1>(v, g, valid, mops, mi, ph.stage_mask, blob, ts, gbits);
+  } else
   for (int mi = 0; mi < nmicro; ++mi) {
     const MicroOp& mo = mops[mi];
     const MicroHot hot = *reinterpret_cast<const MicroHot*>(&mo);
@@ -268,14 +327,6 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
 #define QB_CASE_PAIRS(BASE, ...)                                                                                          \
   QB_CASE_PAIR(BASE, 1, 0, 0, __VA_ARGS__) QB_CASE_PAIR(BASE, 2, 0, 1, __VA_ARGS__) QB_CASE_PAIR(BASE, 2, 1, 2, __VA_ARGS__) \
   QB_CASE_PAIR(BASE, 3, 0, 3, __VA_ARGS__) QB_CASE_PAIR(BASE, 3, 1, 4, __VA_ARGS__) QB_CASE_PAIR(BASE, 3, 2, 5, __VA_ARGS__)
-    switch (handler) {
-      QB_CASE_BIT(MH_ADDSUB, QB_EACH((mu_addsub<C, R, I, 0>(v[u], 0u))))
-      QB_CASE_BIT(MH_REAL1, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_real1<C, R, I, 0>(v[u], m, 0u))) })
-      QB_CASE_BIT(MH_CPLX1, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_cplx1<C, R, I, 0>(v[u], m, 0u))) })
-      QB_CASE_BIT(MH_CPLX1_M, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_cplx1<C, R, I, 1>(v[u], m, hot.creg))) })
-      QB_CASE_BIT(MH_XPAIR, QB_EACH((mu_xpair<C, R, I>(v[u], hot.creg))))
-      QB_CASE_PAIRS(MH_DENSE2, { const C* m = reinterpret_cast<const C*>(blob + hot.payload); QB_EACH((mu_dense2<C, R, HI, LO>(v[u], m, hot.creg))) })
-      QB_CASE_PAIRS(MH_SWAP, QB_EACH((mu_swap<C, R, HI, LO>(v[u], hot.creg))))
 #define QB_FAN_BODY(CB)                                                              \
   {                                                                                  \
     const C* ta = reinterpret_cast<const C*>(blob + hot.payload);                    \
@@ -289,9 +340,17 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
       mu_fan<C, R, CB>(v[u], ph0, gt, hot.creg);                                     \
     })                                                                               \
   }
-      QB_CASE_BIT(MH_FAN_C, QB_FAN_BODY(I))
+    switch (handler) {
       QB_CASE_BIT(MH_STAGE_A, { QB_EACH((mu_addsub<C, R, I, 0>(v[u], 0u))) QB_FAN_BODY(I) })
       QB_CASE_BIT(MH_STAGE_R, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_real1<C, R, I, 0>(v[u], m, 0u))) QB_FAN_BODY(I) })
+      QB_CASE_BIT(MH_ADDSUB, QB_EACH((mu_addsub<C, R, I, 0>(v[u], 0u))))
+      QB_CASE_BIT(MH_REAL1, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_real1<C, R, I, 0>(v[u], m, 0u))) })
+      QB_CASE_BIT(MH_CPLX1, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_cplx1<C, R, I, 0>(v[u], m, 0u))) })
+      QB_CASE_BIT(MH_CPLX1_M, { const C m[4] = {inl[0], inl[1], inl[2], inl[3]}; QB_EACH((mu_cplx1<C, R, I, 1>(v[u], m, hot.creg))) })
+      QB_CASE_BIT(MH_XPAIR, QB_EACH((mu_xpair<C, R, I>(v[u], hot.creg))))
+      QB_CASE_PAIRS(MH_DENSE2, { const C* m = reinterpret_cast<const C*>(blob + hot.payload); QB_EACH((mu_dense2<C, R, HI, LO>(v[u], m, hot.creg))) })
+      QB_CASE_PAIRS(MH_SWAP, QB_EACH((mu_swap<C, R, HI, LO>(v[u], hot.creg))))
+      QB_CASE_BIT(MH_FAN_C, QB_FAN_BODY(I))
       case MH_FAN_NC: QB_FAN_BODY(R) break;
       case MH_FAN_M: QB_FAN_BODY(R + 1) break;
       QB_CASE_BIT(MH_PHASE_C, { const C ph = inl[0]; QB_EACH((mu_phase<C, R, I>(v[u], ph, 0u))) })

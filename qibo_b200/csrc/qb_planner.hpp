@@ -57,7 +57,10 @@ constexpr int SWEEP_MAX_SLOTS = 48;        // ops per sweep that need per-tile s
 constexpr int SWEEP_BLOB_MAX = 26 * 1024;  // program bytes resident in shared memory next to the tiles
 constexpr int SWEEP_TILE_BYTES_LOG2 = 16;  // 64 KiB tiles, three in flight per SM
 constexpr uint32_t MU_NO_SLOT = 0xFFFF;
-constexpr int SWEEP_TEAM_THREADS = 256;    // compute threads that share one tile (8 warps); the group tables below are laid out for it
+#ifndef QB_TEAM_THREADS
+#define QB_TEAM_THREADS 256
+#endif
+constexpr int SWEEP_TEAM_THREADS = QB_TEAM_THREADS;  // compute threads that share one tile (8 warps); the group tables are laid out for it
 constexpr int FAN_EXT_CHUNK = 4;           // a fan's bits outside the tile are folded through tables of 2^4 entries (<= 8 tables: 32 bits)
 constexpr size_t BIG_PAYLOAD_SMEM_MAX = 16 * 1024 + 64;  // larger dense matrices (6 targets) stay in global memory
 
@@ -121,7 +124,9 @@ struct PassHeader {
   uint8_t pos[8];        // REGTILE: tile-local positions of the register bits, ascending
   uint32_t gtab;         // REGTILE: byte offset of uint16[SWEEP_TEAM_THREADS * groups-per-thread]: the group (index over the
                          // non-register tile bits, ascending) that thread `ctid` handles as its u-th, or 0xFFFF for none
-  uint32_t pad[1];
+  uint32_t stage_mask;   // REGTILE: non-zero when the pass is nothing but fused stage ops (MH_STAGE_*) on strictly descending
+                         // register bits -- the shape of every QFT pass; bit I set = a stage on register bit I.  The kernel
+                         // then runs them as straight-line code, without the per-op jump sequence
 };
 static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligned");
 
@@ -404,7 +409,8 @@ inline std::vector<uint16_t> make_group_table(int T, int R, int csize, uint32_t 
   const int gbits = T - R;
   const uint32_t ngroups = 1u << gbits;
   // the kernel reads a fixed number of groups per thread for each dtype (a full tile has 2^8 / 2^9 groups)
-  const uint32_t gpt = std::max<uint32_t>((ngroups + SWEEP_TEAM_THREADS - 1) / SWEEP_TEAM_THREADS, csize == 16 ? 1u : 2u);
+  const uint32_t full_groups = 1u << (SWEEP_TILE_BYTES_LOG2 - (csize == 16 ? 4 : 3) - regtile_bits_for(csize == 16 ? QB_C128 : QB_C64));
+  const uint32_t gpt = std::max<uint32_t>((ngroups + SWEEP_TEAM_THREADS - 1) / SWEEP_TEAM_THREADS, (full_groups + SWEEP_TEAM_THREADS - 1) / SWEEP_TEAM_THREADS);
   std::vector<uint16_t> tab((size_t)gpt * SWEEP_TEAM_THREADS, 0xFFFF);
   const uint32_t all = (1u << T) - 1;
   if (smask == 0) {
@@ -561,8 +567,19 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     } else {  // fan
       m.type = MU_FAN;
       needs_slot = true;
+      // MH_FAN_C + I shares one phase among the register indices that differ only above bit I: it needs a fan without
+      // factors on those register bits
+      bool above_free = true;
+      if (__builtin_popcount(m.creg) == 1) {
+        const int cb = __builtin_ctz(m.creg);
+        for (auto& kv : p.fan) {
+          if (!((sb.tile_mask >> kv.first) & 1)) continue;
+          const int rb = rbit_of_local[sb.local_of_pos[kv.first]];
+          if (rb > cb && (kv.second.first != cd(1.0, 0.0) || kv.second.second != cd(1.0, 0.0))) above_free = false;
+        }
+      }
       if (m.creg == 0) m.handler = MH_FAN_NC;
-      else if (__builtin_popcount(m.creg) == 1) m.handler = (uint8_t)(MH_FAN_C + __builtin_ctz(m.creg));
+      else if (__builtin_popcount(m.creg) == 1 && above_free) m.handler = (uint8_t)(MH_FAN_C + __builtin_ctz(m.creg));
       else m.handler = MH_FAN_M;
       m.scalar[0] = p.scalar.real();
       m.scalar[1] = p.scalar.imag();
@@ -651,6 +668,18 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     }
   }
   ph.nmicro = (uint16_t)mops.size();
+  if (!mops.empty() && !env_int("QB_NO_STAGE_PASS", 0)) {
+    uint32_t mask = 0;
+    int prev = 99;
+    bool ok = true;
+    for (auto& m : mops) {
+      const int I = m.handler >= MH_STAGE_R ? m.handler - MH_STAGE_R : m.handler - MH_STAGE_A;
+      if (m.handler < MH_STAGE_A || m.handler >= MH_STAGE_R + 4 || I >= prev || m.cthr != 0) { ok = false; break; }
+      prev = I;
+      mask |= 1u << I;
+    }
+    ph.stage_mask = ok ? mask : 0u;
+  }
   {
     auto it = sb.gtab_of_rmask.find(rmask);
     if (it == sb.gtab_of_rmask.end()) {

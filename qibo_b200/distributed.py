@@ -344,6 +344,8 @@ class ShardedProgram:
                     st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed)
                     out.nsweeps += st.nsweeps
                     out.elapsed_ms += st.elapsed_ms
+                    out.perm_ms += getattr(st, "perm_ms", 0.0)
+                    out.nperm += getattr(st, "nperm", 0)
             else:
                 t0 = None
                 if tensor.is_cuda and timed:
@@ -380,6 +382,8 @@ class RunStats:
     def __init__(self):
         self.nsweeps = 0
         self.elapsed_ms = 0.0  # CUDA-event time of the local sweeps
+        self.perm_ms = 0.0  # of which: K8 permutation launches
+        self.nperm = 0
         self.nexchanges = 0
         self.exchange_ms = 0.0
         self.exchange_bytes = 0

@@ -170,6 +170,7 @@ class Engine:
         Returns the planner/timing statistics."""
         total = _lib.QbProgramStats()
         total.nops = len(ops)
+        total.perm_ms, total.nperm = 0.0, 0  # K8 launches inside this program (reported apart from the sweep kernel)
         segments = split_swap_runs(ops, nqubits) if fuse and self.permute_swap_runs else [("ops", list(ops))]
         for kind, payload in segments:
             if kind == "perm":
@@ -184,6 +185,8 @@ class Engine:
                     total.ndense_passes += 1
                     total.bytes_moved += 2.0 * state.nbytes
                     total.elapsed_ms += ms or 0.0
+                    total.perm_ms += ms or 0.0
+                    total.nperm += 1
                     continue
             st = self._apply_sweeps(state, nqubits, payload, fuse, timed)
             total.nsweeps += st.nsweeps
