@@ -825,7 +825,9 @@ template <typename C>
 inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool no_fuse, Plan& plan, std::string& err) {
   const int Tfull = tile_bits_for(dtype);
   const int T = n < Tfull ? n : Tfull;
-  int Lcfg = env_int("QB_SWEEP_LOW_BITS", dtype == QB_C128 ? 5 : 6);
+  // low bits every tile spans.  complex128: 4 (256-byte rows; the tensor-map copy moves 128-byte swizzle rows anyway),
+  // which leaves 8 free high bits = two full passes of four stages per QFT sweep (measured: QFT(30) 33.0 -> 31.5 ms)
+  int Lcfg = env_int("QB_SWEEP_LOW_BITS", dtype == QB_C128 ? 4 : 6);
   if (Lcfg > T) Lcfg = T;
   if (Lcfg < 1) Lcfg = 1;
   if (T - Lcfg > 8) Lcfg = T - 8;

@@ -22,6 +22,8 @@ if case == "h24":
 elif case == "h1":
     ops = [Op(h, (0,))]
 elif case == "qft":
+    ops = circuits.qft(n, with_swaps=False)
+elif case == "qftswap":
     ops = circuits.qft(n)
 elif case == "var":
     ops = circuits.variational(n, 2, np.random.default_rng(7).random(4 * n) * 6.28)
