@@ -49,6 +49,39 @@ template <typename C> QB_HD void cmul_inplace(C& v, const C ph) {
   v.y = qfma(v.y, ph.x, u);
 }
 
+// ---- packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one instruction for both components of a complex64) ------
+// complex64 sweeps are FP32-issue bound (a 50-gate sweep of the variational ansatz needs ~200 FP32 instructions per
+// amplitude against ~91 issue slots per amplitude at HBM speed), so real-coefficient updates use the packed forms.
+#if defined(__CUDA_ARCH__)
+QB_D float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+      "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+QB_D float2 f2_mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+QB_D float2 f2_add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+#else
+QB_HD float2 f2_fma(float2 a, float2 b, float2 c) { float2 d; d.x = fmaf(a.x, b.x, c.x); d.y = fmaf(a.y, b.y, c.y); return d; }
+QB_HD float2 f2_mul(float2 a, float2 b) { float2 d; d.x = a.x * b.x; d.y = a.y * b.y; return d; }
+QB_HD float2 f2_add(float2 a, float2 b) { float2 d; d.x = a.x + b.x; d.y = a.y + b.y; return d; }
+#endif
+// both components of v times / plus real coefficients: packed for complex64, two scalar ops for complex128
+QB_HD float2 creal_fma(float k, float2 v, float2 c) { float2 kk; kk.x = k; kk.y = k; return f2_fma(kk, v, c); }
+QB_HD float2 creal_mul(float k, float2 v) { float2 kk; kk.x = k; kk.y = k; return f2_mul(kk, v); }
+QB_HD float2 creal_add(float2 a, float2 b) { return f2_add(a, b); }
+QB_HD double2 creal_fma(double k, double2 v, double2 c) { double2 d; d.x = fma(k, v.x, c.x); d.y = fma(k, v.y, c.y); return d; }
+QB_HD double2 creal_mul(double k, double2 v) { double2 d; d.x = k * v.x; d.y = k * v.y; return d; }
+QB_HD double2 creal_add(double2 a, double2 b) { double2 d; d.x = a.x + b.x; d.y = a.y + b.y; return d; }
+
 // ---- bit utilities --------------------------------------------------------------------------------
 // insert a zero bit at position p (bits >= p move up by one)
 QB_HD uint64_t insert_zero(uint64_t x, int p) {

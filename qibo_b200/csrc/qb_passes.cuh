@@ -59,10 +59,8 @@ template <typename C, int R, int I, int MODE> QB_HD void mu_addsub(C* v, uint32_
     C& a = v[j0];
     C& b = v[j0 | (1 << I)];
     typedef typename real_of<C>::type Re;
-    a.x = a.x + b.x;
-    a.y = a.y + b.y;
-    b.x = qfma((Re)-2, b.x, a.x);
-    b.y = qfma((Re)-2, b.y, a.y);
+    a = creal_add(a, b);
+    b = creal_fma((Re)-2, b, a);
   }
 }
 
@@ -77,11 +75,9 @@ template <typename C, int R, int I, int MODE> QB_HD void mu_real1(C* v, const C*
     // cross terms first (temporaries), then one FMA per output INTO the register that holds its own input
     C& a = v[j0];
     C& b = v[j0 | (1 << I)];
-    const Re tx = r01 * b.x, ty = r01 * b.y, ux = r10 * a.x, uy = r10 * a.y;
-    a.x = qfma(r00, a.x, tx);
-    a.y = qfma(r00, a.y, ty);
-    b.x = qfma(r11, b.x, ux);
-    b.y = qfma(r11, b.y, uy);
+    const C t = creal_mul(r01, b), u = creal_mul(r10, a);
+    a = creal_fma(r00, a, t);
+    b = creal_fma(r11, b, u);
   }
 }
 
@@ -185,6 +181,15 @@ template <typename C, int R, int CB> QB_HD void mu_fan(C* v, const C p0, const C
 // lone controlled phase: v[j] *= ph on the register indices whose control bits are set
 template <typename C, int R, int CB> QB_HD void mu_phase(C* v, const C ph, uint32_t creg) {
   constexpr int D = 1 << R;
+  if (ph.y == 0) {  // CZ, Z...: a real factor is half the multiplies (one packed instruction for complex64)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (CB < R && !((j >> CB) & 1)) continue;
+      if (CB == R + 1 && (uint32_t(j) & creg) != creg) continue;
+      v[j] = creal_mul(ph.x, v[j]);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < D; ++j) {
     if (CB < R && !((j >> CB) & 1)) continue;
