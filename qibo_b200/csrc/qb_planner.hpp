@@ -825,9 +825,11 @@ template <typename C>
 inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool no_fuse, Plan& plan, std::string& err) {
   const int Tfull = tile_bits_for(dtype);
   const int T = n < Tfull ? n : Tfull;
-  // low bits every tile spans.  complex128: 4 (256-byte rows; the tensor-map copy moves 128-byte swizzle rows anyway),
-  // which leaves 8 free high bits = two full passes of four stages per QFT sweep (measured: QFT(30) 33.0 -> 31.5 ms)
-  int Lcfg = env_int("QB_SWEEP_LOW_BITS", dtype == QB_C128 ? 4 : 6);
+  // low bits every tile spans.  complex128 up to 30 qubits: 4 (256-byte rows; the tensor-map copy moves 128-byte
+  // swizzle rows anyway), which leaves 8 free high bits = two full passes of four stages per QFT sweep (measured:
+  // QFT(30) 33.0 -> 31.5 ms).  Beyond 32 GiB a tile of 256 short rows touches 256 distant pages and loses more than
+  // the ninth pass costs (QFT(32): 172.7 ms with 4 low bits, 164.5 ms with 5).
+  int Lcfg = env_int("QB_SWEEP_LOW_BITS", dtype == QB_C128 ? (n <= 30 ? 4 : 5) : 6);
   if (Lcfg > T) Lcfg = T;
   if (Lcfg < 1) Lcfg = 1;
   if (T - Lcfg > 8) Lcfg = T - 8;
