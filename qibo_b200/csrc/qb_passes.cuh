@@ -362,6 +362,14 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
       case MH_PHASE_NC: { const C ph = inl[0]; QB_EACH((mu_phase<C, R, R>(v[u], ph, 0u))) } break;
       case MH_PHASE_M: { const C ph = inl[0]; QB_EACH((mu_phase<C, R, R + 1>(v[u], ph, hot.creg))) } break;
       case MH_DIAGK: QB_EACH((mu_diagk<C, R>(v[u], mo, blob, ts[slot].aux, t0[u]))) break;
+      case MH_REAL_LAYER: {
+        const C* m = reinterpret_cast<const C*>(blob + hot.payload);
+        const uint32_t present = mo.k;
+        if (present & 1u) QB_EACH((mu_real1<C, R, 0, 0>(v[u], m, 0u)))
+        if constexpr (R > 1) { if (present & 2u) QB_EACH((mu_real1<C, R, 1, 0>(v[u], m + 4, 0u))) }
+        if constexpr (R > 2) { if (present & 4u) QB_EACH((mu_real1<C, R, 2, 0>(v[u], m + 8, 0u))) }
+        if constexpr (R > 3) { if (present & 8u) QB_EACH((mu_real1<C, R, 3, 0>(v[u], m + 12, 0u))) }
+      } break;
       default: break;
     }
 #undef QB_FAN_BODY

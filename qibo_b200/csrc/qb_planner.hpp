@@ -51,6 +51,8 @@ enum MicroHandler {
   MH_DIAGK = 45,
   MH_STAGE_A = 46,  // +I  (a+b, a-b) on bit I, then a fan whose only control is bit I (a QFT stage in one dispatch)
   MH_STAGE_R = 50,  // +I  real 2x2 on bit I, then that fan
+  MH_REAL_LAYER = 54,  //  up to R uncontrolled real 2x2 gates on distinct register bits (an RY layer) in one dispatch:
+                       //  `k` = mask of the register bits present, payload = their matrices (4 entries each, .x used)
 };
 
 constexpr int SWEEP_MAX_SLOTS = 48;        // ops per sweep that need per-tile set-up (controls / factors from outside the tile)
@@ -664,6 +666,60 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       for (auto& so : sb.slots)
         if (so.first == pass_index && so.second >= 0) so.second = new_index[so.second];
       // a fused pair owns two payload entries (the dense gate's is empty): keep the fan's payload as the op's
+      mops.swap(fused);
+    }
+  }
+  // ---- fuse runs of uncontrolled real one-qubit gates on distinct register bits (they commute) into layer ops
+  if (!env_int("QB_NO_LAYER", 0)) {
+    const size_t first_payload = sb.payloads.size() - mops.size();
+    std::vector<MicroOp> fused;
+    std::vector<int> new_index(mops.size(), -1);
+    std::vector<std::vector<C>> extra_payloads;  // payload of each new layer op
+    std::vector<int> extra_owner;
+    size_t q = 0;
+    while (q < mops.size()) {
+      auto is_real1 = [&](const MicroOp& m) { return m.handler >= MH_REAL1 && m.handler < MH_REAL1 + 4 && m.cthr == 0 && m.slot == MU_NO_SLOT; };
+      if (!is_real1(mops[q])) {
+        new_index[q] = (int)fused.size();
+        fused.push_back(mops[q]);
+        ++q;
+        continue;
+      }
+      uint32_t mask = 0;
+      size_t e = q;
+      while (e < mops.size() && is_real1(mops[e]) && !((mask >> (mops[e].handler - MH_REAL1)) & 1)) {
+        mask |= 1u << (mops[e].handler - MH_REAL1);
+        ++e;
+      }
+      if (e - q < 2) {
+        new_index[q] = (int)fused.size();
+        fused.push_back(mops[q]);
+        ++q;
+        continue;
+      }
+      MicroOp m = mops[q];
+      m.handler = MH_REAL_LAYER;
+      m.k = mask;
+      std::vector<C> pay(4 * R, to_dev<C>(cd(0.0, 0.0)));
+      for (size_t t = q; t < e; ++t) {
+        const int I = mops[t].handler - MH_REAL1;
+        const C* inl = reinterpret_cast<const C*>(mops[t].inl);
+        for (int x = 0; x < 4; ++x) pay[4 * I + x] = inl[x];
+        new_index[t] = (int)fused.size();
+      }
+      extra_payloads.push_back(std::move(pay));
+      extra_owner.push_back((int)fused.size());
+      fused.push_back(m);
+      q = e;
+    }
+    if (fused.size() != mops.size()) {
+      for (size_t t = 0; t < mops.size(); ++t) sb.payload_owner[first_payload + t].second = new_index[t];
+      for (auto& so : sb.slots)
+        if (so.first == pass_index && so.second >= 0) so.second = new_index[so.second];
+      for (size_t x = 0; x < extra_payloads.size(); ++x) {  // the members' own payload entries are empty (inline matrices)
+        sb.payload_owner.push_back({pass_index, extra_owner[x]});
+        sb.payloads.push_back(std::move(extra_payloads[x]));
+      }
       mops.swap(fused);
     }
   }

@@ -166,6 +166,33 @@ def test_qft_full_size_properties(eng, n, dtype):
         assert float((st2.tensor - (0.3 - 0.4j) * st.tensor).abs().max()) < tol(dtype)
 
 
+@pytest.mark.parametrize("case,n,dtype", [("variational", 27, "complex64"), ("random", 26, "complex128"), ("variational", 25, "complex128"),
+                                          ("random", 27, "complex64")])
+def test_scheduled_sweeps_match_gate_by_gate_at_scale(eng, case, n, dtype):
+    """BASELINE configs 3 and 4 at sizes the oracle cannot reach: the sweep path (list-scheduled light-cone sweeps,
+    reordered passes, tensor-map copies, swizzled tiles) against the one-gate-per-sweep K1 kernels, which are checked
+    against the oracle gate by gate at small n.  Same device, same input, every amplitude compared."""
+    from qibo_b200 import circuits
+    from qibo_b200.array import DeviceArray
+
+    if case == "variational":
+        ops = circuits.variational(n, 4, 2 * np.pi * np.random.default_rng(7).random(2 * 4 * n))
+    else:
+        ops = circuits.random_circuit(n, 150, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(n)
+    rdt = torch.float64 if dtype == "complex128" else torch.float32
+    psi = torch.complex(torch.randn(2**n, dtype=rdt, device="cuda", generator=g), torch.randn(2**n, dtype=rdt, device="cuda", generator=g))
+    psi /= torch.linalg.vector_norm(psi)
+    a = DeviceArray(psi.clone())
+    stats = eng.apply_program(a, n, ops)
+    assert stats.nsweeps < len(ops) / 5
+    b = DeviceArray(psi.clone())
+    for op in ops:
+        eng.apply_op(b, n, op)
+    assert float((a.tensor - b.tensor).abs().max()) < tol(dtype)
+    assert abs(eng.norm2(a) - 1.0) < (1e-9 if dtype == "complex128" else 1e-4)
+
+
 # ------------------------------------------------------------------------------------------ P1
 def test_probabilities_golden(eng, golden):
     for i, c in enumerate(golden.cases("prob_cases")):
