@@ -233,13 +233,9 @@ template <typename C, int R, int GPT, int I>
 QB_HD void stage_op(C (&v)[GPT][1 << R], const uint32_t* g, const bool* valid, const MicroOp& mo, const char* blob, const TileSlot* ts, int gbits) {
   const MicroHot hot = *reinterpret_cast<const MicroHot*>(&mo);
   const uint32_t handler = hot.w0 & 0xFF, slot = hot.w0 >> 16;
-  if (!ts[slot].active) return;
-  const C* ta = reinterpret_cast<const C*>(blob + hot.payload);
-  const uint32_t la = mo.la;
-  const C* tb = ta + (1u << la);
-  const C* gt = tb + (1u << (gbits - (int)la));
-  const C ext = slot_ext<C>(ts[slot]);
-  if (handler >= MH_STAGE_R) {
+  const bool has_fan = handler >= MH_STAGE_A;  // else a bare (a+b, a-b) / real 2x2 gate (the last H of a QFT has no fan)
+  if (has_fan && !ts[slot].active) return;
+  if (handler >= MH_STAGE_R || (handler >= MH_REAL1 && handler < MH_REAL1 + 4)) {
     const C* inl = reinterpret_cast<const C*>(mo.inl);
     const C m[4] = {inl[0], inl[1], inl[2], inl[3]};
 #pragma unroll
@@ -250,6 +246,12 @@ QB_HD void stage_op(C (&v)[GPT][1 << R], const uint32_t* g, const bool* valid, c
     for (int u = 0; u < GPT; ++u)
       if (valid[u]) mu_addsub<C, R, I, 0>(v[u], 0u);
   }
+  if (!has_fan) return;
+  const C* ta = reinterpret_cast<const C*>(blob + hot.payload);
+  const uint32_t la = mo.la;
+  const C* tb = ta + (1u << la);
+  const C* gt = tb + (1u << (gbits - (int)la));
+  const C ext = slot_ext<C>(ts[slot]);
 #pragma unroll
   for (int u = 0; u < GPT; ++u)
     if (valid[u]) {
@@ -269,7 +271,7 @@ QB_HD void stage_chain(C (&v)[GPT][1 << R], const uint32_t* g, const bool* valid
 
 // One REGTILE pass over the tile.  Each thread keeps GPT groups in registers at once, so that the decode of a
 // micro-op is paid once per GPT * 2^R amplitudes.  `ts` = this team's per-tile slot states.
-template <typename C, int R, int GPT>
+template <typename C, int R, int GPT, bool SO = false>
 QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t swz_on, uint32_t ctid, uint32_t nct) {
   constexpr int D = 1 << R;
   const int gbits = T - R;
@@ -307,7 +309,7 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
     // jump sequence (ncu: the compare tree nvcc makes of the handler switch costs ~5 dependent branches per op)
     int mi = 0;
     stage_chain<C, R, GPT, R - 1>(v, g, valid, mops, mi, ph.stage_mask, blob, ts, gbits);
-  } else
+  } else if constexpr (!SO) {  // (a stage-only kernel is launched for sweeps made of stage passes alone)
   for (int mi = 0; mi < nmicro; ++mi) {
     const MicroOp& mo = mops[mi];
     const MicroHot hot = *reinterpret_cast<const MicroHot*>(&mo);
@@ -377,6 +379,7 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
 #undef QB_CASE_PAIR
 #undef QB_CASE_BIT
 #undef QB_EACH
+  }
   }
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {

@@ -165,6 +165,7 @@ struct PlanOp {
 
 struct SweepDesc {
   int swizzle = 0;
+  int stage_only = 0;  // every pass is a straight-line stage pass: the lean two-team kernel instantiation may run it
   int T = 0, L = 0;
   uint64_t tile_mask = 0;
   size_t blob_offset = 0, blob_bytes = 0;
@@ -728,13 +729,20 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     uint32_t mask = 0;
     int prev = 99;
     bool ok = true;
+    bool any_stage = false;
     for (auto& m : mops) {
-      const int I = m.handler >= MH_STAGE_R ? m.handler - MH_STAGE_R : m.handler - MH_STAGE_A;
-      if (m.handler < MH_STAGE_A || m.handler >= MH_STAGE_R + 4 || I >= prev || m.cthr != 0) { ok = false; break; }
+      int I = -1;
+      if (m.handler >= MH_STAGE_A && m.handler < MH_STAGE_R + 4) {
+        I = m.handler >= MH_STAGE_R ? m.handler - MH_STAGE_R : m.handler - MH_STAGE_A;
+        any_stage = true;
+      } else if (m.handler >= MH_ADDSUB && m.handler < MH_REAL1 + 4 && m.slot == MU_NO_SLOT) {
+        I = (m.handler - MH_ADDSUB) & 3;  // a bare (a+b, a-b) / real 2x2 gate rides along (the last H of a QFT has no fan)
+      }
+      if (I < 0 || I >= prev || m.cthr != 0) { ok = false; break; }
       prev = I;
       mask |= 1u << I;
     }
-    ph.stage_mask = ok ? mask : 0u;
+    ph.stage_mask = ok && any_stage ? mask : 0u;
   }
   {
     auto it = sb.gtab_of_rmask.find(rmask);
@@ -1135,6 +1143,9 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
       }
     }
     if ((int)sb.slots.size() > SWEEP_MAX_SLOTS) { err = "internal: too many per-tile slots in one sweep"; return false; }
+    sd.stage_only = sb.passes.empty() ? 0 : 1;
+    for (auto& ph_ : sb.passes)
+      if (ph_.kind != PASS_REGTILE || ph_.stage_mask == 0) sd.stage_only = 0;
     finish_blob<C>(sb, hdr, plan.blob, sd);
     if (hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
     plan.npasses += sd.npasses;

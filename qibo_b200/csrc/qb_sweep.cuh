@@ -46,15 +46,26 @@ constexpr int SW_TILE_BYTES = 1 << SWEEP_TILE_BYTES_LOG2;
 #endif
 constexpr int SW_TEAM_THREADS = QB_TEAM_THREADS;
 constexpr int SW_MAX_TEAMS = 2;
-template <typename C> struct SweepCfg;
-template <> struct SweepCfg<double2> {
+// SO ("stage only"): a second instantiation for sweeps whose passes are all straight-line stage passes (every QFT
+// sweep).  Without the 54-handler switch the compute code fits 112 registers, so complex128 can run two teams there.
+#ifndef QB_TEAMS128_SO
+#define QB_TEAMS128_SO 2
+#endif
+#ifndef QB_REGS128_SO
+#define QB_REGS128_SO 112
+#endif
+template <typename C, bool SO> struct SweepCfg;
+template <> struct SweepCfg<double2, false> {
   static constexpr int TEAMS = QB_TEAMS128, COMPUTE_REGS = QB_REGS128, RB = QB_R128;
 };
-template <> struct SweepCfg<float2> {
+template <> struct SweepCfg<double2, true> {
+  static constexpr int TEAMS = QB_TEAMS128_SO, COMPUTE_REGS = QB_REGS128_SO, RB = QB_R128;
+};
+template <bool SO> struct SweepCfg<float2, SO> {
   static constexpr int TEAMS = QB_TEAMS64, COMPUTE_REGS = QB_REGS64, RB = QB_R64;
 };
-template <typename C> constexpr int sw_copy_threads() { return SweepCfg<C>::COMPUTE_REGS ? 128 : 64; }  // warp 0: loader, warp 1: storer
-template <typename C> constexpr int sw_threads() { return SweepCfg<C>::TEAMS * SW_TEAM_THREADS + sw_copy_threads<C>(); }
+template <typename C, bool SO> constexpr int sw_copy_threads() { return SweepCfg<C, SO>::COMPUTE_REGS ? 128 : 64; }  // warp 0: loader, warp 1: storer
+template <typename C, bool SO> constexpr int sw_threads() { return SweepCfg<C, SO>::TEAMS * SW_TEAM_THREADS + sw_copy_threads<C, SO>(); }
 constexpr int SW_MAX_RUNS = 256;
 constexpr int SW_FIXED_BYTES = SW_NBUF * SW_TILE_BYTES + SW_MAX_RUNS * 8 + SW_NBUF * SWEEP_MAX_SLOTS * (int)sizeof(TileSlot) + 128;
 constexpr int SW_BLOB_REGION = ((226 * 1024 - SW_FIXED_BYTES) / 16) * 16;
@@ -161,8 +172,8 @@ QB_D void team_bar(int team) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------
-template <typename C>
-__global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict__ state, const char* __restrict__ prog, const __grid_constant__ TmaDesc tma) {
+template <typename C, bool SO>
+__global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __restrict__ state, const char* __restrict__ prog, const __grid_constant__ TmaDesc tma) {
   extern __shared__ __align__(1024) unsigned char smem[];
   C* tiles = reinterpret_cast<C*>(smem);
   char* blob = reinterpret_cast<char*>(smem + SW_NBUF * SW_TILE_BYTES);
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
   uint64_t* done = full + SW_NBUF;
   uint64_t* freeb = done + SW_NBUF;
 
-  constexpr int SW_TEAMS = SweepCfg<C>::TEAMS, SW_COPY_THREADS = sw_copy_threads<C>(), SW_THREADS = sw_threads<C>();
+  constexpr int SW_TEAMS = SweepCfg<C, SO>::TEAMS, SW_COPY_THREADS = sw_copy_threads<C, SO>(), SW_THREADS = sw_threads<C, SO>();
   const int tid = threadIdx.x;
   {
     const uint32_t nbytes = reinterpret_cast<const SweepHeader*>(prog)->blob_bytes;
@@ -202,9 +213,9 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
   const int nslots = (int)hdr.nslots;
   const uint64_t ntiles = hdr.ntiles;
   const uint64_t my_n = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  if constexpr (SweepCfg<C>::COMPUTE_REGS != 0) {
+  if constexpr (SweepCfg<C, SO>::COMPUTE_REGS != 0) {
     if (tid < SW_COPY_THREADS) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SweepCfg<C>::COMPUTE_REGS));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SweepCfg<C, SO>::COMPUTE_REGS));
   }
 
   if (tid < 32) {
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
     const uint32_t swz_on = hdr.swizzle ? 7u : 0u;
     const bool warp_private = hdr.warp_private != 0;
     static_assert(SW_TEAM_THREADS == SWEEP_TEAM_THREADS, "group tables are laid out for SWEEP_TEAM_THREADS");
-    constexpr int RB = SweepCfg<C>::RB;                                     // register bits of a REGTILE pass
+    constexpr int RB = SweepCfg<C, SO>::RB;                                     // register bits of a REGTILE pass
     constexpr int TB = SWEEP_TILE_BYTES_LOG2 - (sizeof(C) == 16 ? 4 : 3);  // tile bits of a full tile
     constexpr int GPT = ((1 << (TB - RB)) + SW_TEAM_THREADS - 1) / SW_TEAM_THREADS;  // groups per thread
     for (uint64_t i = team; i < my_n; i += SW_TEAMS) {
@@ -300,8 +311,8 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
         }
         if (ph.kind == PASS_REGTILE) {
           // R < RB only occurs for n < 4, which qb_apply_program routes to the K1 kernels
-          run_pass<C, RB, GPT>(tile, blob, ts, ph, T, swz_on, ctid, SW_TEAM_THREADS);
-        } else {
+          run_pass<C, RB, GPT, SO>(tile, blob, ts, ph, T, swz_on, ctid, SW_TEAM_THREADS);
+        } else if constexpr (!SO) {
           const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
           if (op.slot == MU_NO_SLOT || ts[op.slot].active) {
             const C* payload = op.payload_global ? reinterpret_cast<const C*>(prog + op.payload) : reinterpret_cast<const C*>(blob + op.payload);
@@ -325,10 +336,10 @@ __global__ void __launch_bounds__(sw_threads<C>(), 1) sweep_kernel(C* __restrict
 
 inline int sweep_configure(const cudaDeviceProp& prop) {
   if ((int)prop.sharedMemPerBlockOptin < SW_SMEM_BYTES) return QB_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(sweep_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES) != cudaSuccess)
-    return QB_ERR_CUDA;
-  if (cudaFuncSetAttribute(sweep_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES) != cudaSuccess)
-    return QB_ERR_CUDA;
+  if (cudaFuncSetAttribute(sweep_kernel<double2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES) != cudaSuccess) return QB_ERR_CUDA;
+  if (cudaFuncSetAttribute(sweep_kernel<double2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES) != cudaSuccess) return QB_ERR_CUDA;
+  if (cudaFuncSetAttribute(sweep_kernel<float2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES) != cudaSuccess) return QB_ERR_CUDA;
+  if (cudaFuncSetAttribute(sweep_kernel<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES) != cudaSuccess) return QB_ERR_CUDA;
   return QB_OK;
 }
 
@@ -393,19 +404,23 @@ inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqub
   uint64_t grid = sd.ntiles < (uint64_t)sm_count ? sd.ntiles : (uint64_t)sm_count;
   TmaDesc tma;
   if (!tma_describe(state, nqubits, dtype, sd.tile_mask, sd.swizzle != 0, tma) && sd.swizzle) return QB_ERR_UNSUPPORTED;  // planned for a swizzled tile
-  if (dtype == QB_C128)
-    sweep_kernel<double2><<<(unsigned)grid, sw_threads<double2>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
-  else
-    sweep_kernel<float2><<<(unsigned)grid, sw_threads<float2>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma);
+  const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);
+  if (dtype == QB_C128) {
+    if (so) sweep_kernel<double2, true><<<(unsigned)grid, sw_threads<double2, true>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
+    else sweep_kernel<double2, false><<<(unsigned)grid, sw_threads<double2, false>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
+  } else {
+    if (so) sweep_kernel<float2, true><<<(unsigned)grid, sw_threads<float2, true>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma);
+    else sweep_kernel<float2, false><<<(unsigned)grid, sw_threads<float2, false>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma);
+  }
   return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
 }
 
 // resources of the compiled kernel, for launch-failure messages
 inline std::string sweep_resources(int dtype) {
   cudaFuncAttributes a;
-  cudaError_t e = dtype == QB_C128 ? cudaFuncGetAttributes(&a, sweep_kernel<double2>) : cudaFuncGetAttributes(&a, sweep_kernel<float2>);
+  cudaError_t e = dtype == QB_C128 ? cudaFuncGetAttributes(&a, sweep_kernel<double2, false>) : cudaFuncGetAttributes(&a, sweep_kernel<float2, false>);
   if (e != cudaSuccess) return "(no attributes)";
-  return "threads=" + std::to_string(dtype == QB_C128 ? sw_threads<double2>() : sw_threads<float2>()) + " regs=" + std::to_string(a.numRegs) + " maxThreadsPerBlock=" + std::to_string(a.maxThreadsPerBlock) +
+  return "threads=" + std::to_string(dtype == QB_C128 ? sw_threads<double2, false>() : sw_threads<float2, false>()) + " regs=" + std::to_string(a.numRegs) + " maxThreadsPerBlock=" + std::to_string(a.maxThreadsPerBlock) +
          " static_smem=" + std::to_string(a.sharedSizeBytes) + " dyn_smem=" + std::to_string(SW_SMEM_BYTES) +
          " max_dyn_smem=" + std::to_string(a.maxDynamicSharedSizeBytes) + " local=" + std::to_string(a.localSizeBytes);
 }
