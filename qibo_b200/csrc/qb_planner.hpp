@@ -499,8 +499,32 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
   }
   std::vector<MicroOp> mops;
   const int pass_index = (int)sb.passes.size();
+  const PlanOp* prev_op = nullptr;
   for (const PlanOp* pp : ops) {
-    const PlanOp& p = *pp;
+    // A two-qubit controlled phase right after an uncontrolled one-qubit gate on one of its qubits (the tail of a QFT:
+    // H(q) CU1(q, q+1)) is re-rooted as a one-entry fan controlled by that qubit, so that the pair fuses into a stage op
+    // and the pass stays a straight-line stage pass.  (A pure phase is symmetric in its qubits.)
+    PlanOp rerooted;
+    bool force_fan = false;
+    if (pp->kind == CK_PHASE && pp->fan.size() == 1 && pp->fan.begin()->second.first == cd(1.0, 0.0) && pp->cpos.size() == 1 && prev_op &&
+        prev_op->kind == CK_DENSE && prev_op->tpos.size() == 1 && prev_op->cpos.empty()) {
+      const int d = prev_op->tpos[0], a = pp->cpos[0], b = pp->fan.begin()->first;
+      if (d == a || d == b) {
+        const int other = d == a ? b : a;
+        const bool in_tile = ((sb.tile_mask >> d) & 1) && ((sb.tile_mask >> other) & 1);
+        if (in_tile && rbit_of_local[sb.local_of_pos[d]] >= 0 && rbit_of_local[sb.local_of_pos[other]] >= 0 &&
+            rbit_of_local[sb.local_of_pos[other]] < rbit_of_local[sb.local_of_pos[d]]) {
+          rerooted = *pp;
+          rerooted.cpos = {d};
+          const cd phase = pp->fan.begin()->second.second;
+          rerooted.fan.clear();
+          rerooted.fan[other] = {cd(1.0, 0.0), phase};
+          force_fan = true;
+        }
+      }
+    }
+    prev_op = pp;
+    const PlanOp& p = force_fan ? rerooted : *pp;
     MicroOp m;
     memset(&m, 0, sizeof(m));
     memset(m.tbit, 0xFF, sizeof(m.tbit));
@@ -556,7 +580,7 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
         else m.tbit[i] = (uint8_t)sb.local_of_pos[pos];
       }
       for (auto& v : p.data) payload.push_back(to_dev<C>(v));
-    } else if (p.fan.size() == 1 && p.fan.begin()->second.first == cd(1.0, 0.0)) {
+    } else if (!force_fan && p.fan.size() == 1 && p.fan.begin()->second.first == cd(1.0, 0.0)) {
       // a lone controlled phase (CZ, CU1, Z, T...): scalar on the slice where all of its bits are 1
       m.type = MU_PHASE;
       int pos = p.fan.begin()->first;
@@ -1151,8 +1175,14 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     plan.npasses += sd.npasses;
     plan.ndiag += sd.ndiag;
     if (env_int("QB_PLAN_DEBUG", 0))
-      fprintf(stderr, "[qb plan] sweep %zu: ops %zu passes %d tile %#llx L %d swizzle %u warp_private %u split %#x blob %u B slots %zu\n", plan.sweeps.size(),
-              sops.size(), sd.npasses, (unsigned long long)tile_mask, L, hdr.swizzle, hdr.warp_private, sb.split_mask, hdr.blob_bytes, sb.slots.size());
+      fprintf(stderr, "[qb plan] sweep %zu: ops %zu passes %d tile %#llx L %d swizzle %u warp_private %u split %#x blob %u B slots %zu stage_only %d\n", plan.sweeps.size(),
+              sops.size(), sd.npasses, (unsigned long long)tile_mask, L, hdr.swizzle, hdr.warp_private, sb.split_mask, hdr.blob_bytes, sb.slots.size(), sd.stage_only);
+    if (env_int("QB_PLAN_DEBUG", 0) > 1)
+      for (size_t p_ = 0; p_ < sb.passes.size(); ++p_) {
+        fprintf(stderr, "[qb plan]   pass %zu kind %u rmask %#x stage_mask %#x handlers:", p_, sb.passes[p_].kind, sb.passes[p_].rmask, sb.passes[p_].stage_mask);
+        for (auto& m_ : sb.micro[p_]) fprintf(stderr, " %d", (int)m_.handler);
+        fprintf(stderr, "\n");
+      }
     plan.sweeps.push_back(sd);
   }
   return true;
