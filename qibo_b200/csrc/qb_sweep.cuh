@@ -179,11 +179,18 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
   char* blob = reinterpret_cast<char*>(smem + SW_NBUF * SW_TILE_BYTES);
   uint64_t* run_off = reinterpret_cast<uint64_t*>(blob + SW_BLOB_REGION);
   TileSlot* tslots = reinterpret_cast<TileSlot*>(run_off + SW_MAX_RUNS);
+  constexpr int SW_TEAMS = SweepCfg<C, SO>::TEAMS, SW_COPY_THREADS = sw_copy_threads<C, SO>(), SW_THREADS = sw_threads<C, SO>();
+  // One `full` barrier per (buffer, team) pair: tile i lands in buffer i % NBUF and signals full[i % NFULL].  With one
+  // barrier per buffer a team would revisit it every 2 * NBUF tiles with the SAME parity while the phase in between
+  // belongs to the other team: if that load is still in flight when a fast team comes round (one-stage sweeps: the
+  // compute phase is shorter than the jitter of a 64 KiB load), a parity wait is satisfied by the stale phase and both
+  // teams end up in one buffer.  Here consecutive phases of a barrier are all waited for by the same team.
+  constexpr int SW_NFULL = SW_NBUF * SW_TEAMS;
+  static_assert((2 * SW_NBUF + SW_NBUF * SW_MAX_TEAMS) * 8 <= 128, "mbarrier area");
   uint64_t* full = reinterpret_cast<uint64_t*>(tslots + SW_NBUF * SWEEP_MAX_SLOTS);
-  uint64_t* done = full + SW_NBUF;
+  uint64_t* done = full + SW_NBUF * SW_MAX_TEAMS;
   uint64_t* freeb = done + SW_NBUF;
 
-  constexpr int SW_TEAMS = SweepCfg<C, SO>::TEAMS, SW_COPY_THREADS = sw_copy_threads<C, SO>(), SW_THREADS = sw_threads<C, SO>();
   const int tid = threadIdx.x;
   {
     const uint32_t nbytes = reinterpret_cast<const SweepHeader*>(prog)->blob_bytes;
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
   const uint32_t tile_elems = 1u << T;
   for (uint32_t r = tid; r < nruns; r += SW_THREADS) run_off[r] = deposit(uint64_t(r) << L, hdr.tile_mask) * sizeof(C);
   if (tid == 0) {
+    for (int b = 0; b < SW_NFULL; ++b) mbar_init(&full[b], 1);
     for (int b = 0; b < SW_NBUF; ++b) {
-      mbar_init(&full[b], 1);
       mbar_init(&done[b], 1);
       mbar_init(&freeb[b], 1);
     }
@@ -225,6 +232,7 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
     const uint64_t dstep = deposit(gridDim.x, hdr.other_mask);
     for (uint64_t i = 0; i < my_n; ++i, base = masked_add(base, dstep, hdr.other_mask)) {
       const int b = (int)(i % SW_NBUF);
+      uint64_t* fullb = &full[i % SW_NFULL];
       // buffer b was last used by tile i-3: wait until the storer has drained it
       if (i >= SW_NBUF) mbar_wait_sleep(&freeb[b], (uint32_t)(((i / SW_NBUF) - 1) & 1));
       // per-tile set-up of the ops that depend on bits outside the tile (control predicates, fan factors), by the
@@ -246,16 +254,16 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
       char* sbase = reinterpret_cast<char*>(tiles + (size_t)b * tile_elems);
       if (tma.enabled) {
         if (lane == 0) {
-          mbar_expect_tx(&full[b], tile_bytes);
+          mbar_expect_tx(fullb, tile_bytes);
           tma_load_5d(sbase, &tma.map, (int)((base >> tma.shift[0]) & tma.mask[0]), (int)((base >> tma.shift[1]) & tma.mask[1]),
                       (int)((base >> tma.shift[2]) & tma.mask[2]), (int)((base >> tma.shift[3]) & tma.mask[3]),
-                      (int)((base >> tma.shift[4]) & tma.mask[4]), &full[b]);
+                      (int)((base >> tma.shift[4]) & tma.mask[4]), fullb);
         }
       } else {
-        if (lane == 0) mbar_expect_tx(&full[b], tile_bytes);
+        if (lane == 0) mbar_expect_tx(fullb, tile_bytes);
         __syncwarp();
         const char* gbase = reinterpret_cast<const char*>(state + base);
-        for (uint32_t r = lane; r < nruns; r += 32) bulk_g2s(sbase + r * run_bytes, gbase + run_off[r], run_bytes, &full[b]);
+        for (uint32_t r = lane; r < nruns; r += 32) bulk_g2s(sbase + r * run_bytes, gbase + run_off[r], run_bytes, fullb);
       }
     }
   } else if (tid < 64) {
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
       const int b = (int)(i % SW_NBUF);
       C* tile = tiles + (size_t)b * tile_elems;
       const TileSlot* ts = tslots + b * SWEEP_MAX_SLOTS;
-      mbar_wait(&full[b], (uint32_t)((i / SW_NBUF) & 1));  // tile data (async proxy) + slot states (loader warp) are visible
+      mbar_wait(&full[i % SW_NFULL], (uint32_t)((i / SW_NFULL) & 1));  // tile data (async proxy) + slot states (loader warp) are visible
       for (int pi = 0; pi < npasses; ++pi) {
         const PassHeader& ph = passes[pi];
         if (pi) {

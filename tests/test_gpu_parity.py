@@ -193,6 +193,40 @@ def test_scheduled_sweeps_match_gate_by_gate_at_scale(eng, case, n, dtype):
     assert abs(eng.norm2(a) - 1.0) < (1e-9 if dtype == "complex128" else 1e-4)
 
 
+@pytest.mark.parametrize("n,world,rank,dtype", [(29, 8, 0, "complex128"), (29, 8, 5, "complex128"), (30, 4, 0, "complex64"),
+                                                 (31, 8, 0, "complex128")])
+def test_rank_specialised_segments_at_scale(eng, n, world, rank, dtype):
+    """What rank `rank` of `world` runs in a sharded QFT(n), on one GPU: the local segments of the distributed plan (fans
+    with global qubits folded in, one-stage sweeps whose compute phase is far shorter than a tile load -- the case that
+    exposed a stale-parity race between the two compute teams) against the gate-by-gate K1 kernels."""
+    from qibo_b200 import circuits, distributed as D
+    from qibo_b200.array import DeviceArray
+
+    g = world.bit_length() - 1
+    nlocal = n - g
+    plan = D.Plan(n, g, circuits.qft(n))
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    rdt = torch.float64 if dtype == "complex128" else torch.float32
+    psi = torch.complex(torch.randn(2**nlocal, dtype=rdt, device="cuda", generator=gen), torch.randn(2**nlocal, dtype=rdt, device="cuda", generator=gen))
+    psi /= torch.linalg.vector_norm(psi)
+    a, b = DeviceArray(psi.clone()), DeviceArray(psi.clone())
+    del psi
+    nseg = 0
+    for seg in plan.segments:
+        if seg.kind != "local":
+            continue
+        local = [o for o in (D.specialise(p, nlocal, rank) for p in seg.ops) if o is not None]
+        if not local:
+            continue
+        for _ in range(3 if len(local) < 40 else 1):  # short sweeps: repeat (U^3 on both sides) to give a race its chance
+            eng.apply_program(a, nlocal, local)
+            for op in local:
+                eng.apply_op(b, nlocal, op)
+        nseg += 1
+        assert float((a.tensor - b.tensor).abs().max()) < tol(dtype) * (10 if dtype == "complex64" else 1)
+    assert nseg >= 4
+
+
 # ------------------------------------------------------------------------------------------ P1
 def test_probabilities_golden(eng, golden):
     for i, c in enumerate(golden.cases("prob_cases")):
