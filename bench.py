@@ -210,7 +210,7 @@ def run_gpu(args):
     if world > 1:
         from qibo_b200 import distributed
 
-        runner = distributed.ShardedProgram(eng, n, args.dtype, ops)
+        runner = distributed.ShardedProgram(eng, n, args.dtype, ops, global_qubits=args.layout if args.layout == "auto" else None)
         state = runner.basis_state() if args.exchange == "nccl" else runner.peer_shard(0)
         step = lambda: runner.run(state)  # noqa: E731
         barrier = dist.barrier
@@ -340,9 +340,11 @@ def run_gpu(args):
                 f"{2 ** nlocal * itemsize / 2 ** 30:.0f} GiB per GPU", "nqubits": n, "global_qubits": g,
                 "sweeps_per_step": nsweeps // args.steps, "l2": "state (>= 16 GiB) is far larger than the 126 MB L2",
                 "parallelism": f"global-qubit sharding x{world}" if world > 1 else "single GPU",
+                **({"layout": f"global qubits {list(runner.global_qubits)} (--layout {args.layout}); rank = their bits, shard index = "
+                    "the other qubits in ascending order"} if world > 1 else {}),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(nsweeps), "whole_circuit_wall_s": ms_per_step / 1e3,
+            "gpu_launches": int(nsweeps + nxch), "whole_circuit_wall_s": ms_per_step / 1e3,
             "circuit_gates_per_s": circuit_gates_per_s,
             "value_definition": "gates applied x shards (N ranks each apply every gate to their 2^nlocal-amplitude shard) per second; equals circuit gates/s at N=1",
         }
@@ -369,6 +371,9 @@ def main():
     ap.add_argument("--impl", default="qibo_b200", choices=["qibo_b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--layout", default="auto", choices=["auto", "block"],
+                    help="N > 1: which qubits are global -- 'auto' picks the layout with the fewest exchanges (trailing qubits for a QFT, "
+                         "as the reference's _DistributedQFT), 'block' the leading ones")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="global<->local exchange: NVLink peer-memory kernel or NCCL send/recv")
     args = ap.parse_args()
     if args.impl == "reference":

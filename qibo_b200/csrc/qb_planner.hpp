@@ -233,7 +233,12 @@ inline void merge_ops(const std::vector<CanonOp>& ops, bool no_fuse, std::vector
         }
       } else {
         // pure phase on the set P: any member may play the target
-        if (P.size() == f.cpos.size() + 1 && std::includes(P.begin(), P.end(), f.cpos.begin(), f.cpos.end())) {
+        if (!f.cpos.empty() && P == f.cpos) {
+          // exactly the fan's controls (a CU1 whose other qubit is a global qubit set to 1 on this rank): a scalar on
+          // the slice the fan acts on
+          f.scalar *= entry.second;
+          merged = true;
+        } else if (P.size() == f.cpos.size() + 1 && std::includes(P.begin(), P.end(), f.cpos.begin(), f.cpos.end())) {
           int b = -1;
           for (int x : P)
             if (!std::binary_search(f.cpos.begin(), f.cpos.end(), x)) b = x;
@@ -245,7 +250,18 @@ inline void merge_ops(const std::vector<CanonOp>& ops, bool no_fuse, std::vector
           // re-root a single-entry fan so that the shared bits become the controls
           std::vector<int> P0 = fan_set(f), common;
           std::set_intersection(P.begin(), P.end(), P0.begin(), P0.end(), std::back_inserter(common));
-          if (P.size() == P0.size() && common.size() + 1 == P0.size()) {
+          if (!P.empty() && P.size() + 1 == P0.size() && common.size() == P.size() && f.scalar == cd(1.0, 0.0)) {
+            // P is the fan's set minus one bit b0: control on P, and b0 selects between the new phase alone and the
+            // product (the tail of a QFT on a rank whose global control qubits are 1)
+            cd ph0 = f.fan.begin()->second.second;
+            int b0 = -1;
+            for (int x : P0)
+              if (!std::binary_search(P.begin(), P.end(), x)) b0 = x;
+            f.cpos = P;
+            f.fan.clear();
+            f.fan[b0] = {entry.second, entry.second * ph0};
+            merged = true;
+          } else if (P.size() == P0.size() && common.size() + 1 == P0.size()) {
             cd ph0 = f.fan.begin()->second.second;
             int b0 = -1, b1 = -1;
             for (int x : P0)
@@ -522,6 +538,18 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
           force_fan = true;
         }
       }
+    }
+    // A lone phase on the qubit of the one-qubit gate right before it (H(q) U1(q): the last stage of a QFT on a rank whose
+    // global control qubits are 1) becomes a fan without factors controlled by that qubit, for the same reason.
+    if (!force_fan && pp->kind == CK_PHASE && pp->fan.size() == 1 && pp->fan.begin()->second.first == cd(1.0, 0.0) && pp->cpos.empty() &&
+        prev_op && prev_op->kind == CK_DENSE && prev_op->tpos.size() == 1 && prev_op->cpos.empty() &&
+        prev_op->tpos[0] == pp->fan.begin()->first && ((sb.tile_mask >> prev_op->tpos[0]) & 1) &&
+        rbit_of_local[sb.local_of_pos[prev_op->tpos[0]]] >= 0) {
+      rerooted = *pp;
+      rerooted.cpos = {prev_op->tpos[0]};
+      rerooted.scalar = pp->scalar * pp->fan.begin()->second.second;
+      rerooted.fan.clear();
+      force_fan = true;
     }
     prev_op = pp;
     const PlanOp& p = force_fan ? rerooted : *pp;

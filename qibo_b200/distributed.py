@@ -88,18 +88,48 @@ def is_plain_swap(op: Op) -> bool:
 _SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
 
 
-class Plan:
-    """Host-side plan: identical on every rank (pure function of the op list, n and g)."""
+def block_layout(nqubits: int, nglobal: int) -> Tuple[int, ...]:
+    """Global qubits = the ``g`` leading qubits: rank r holds a contiguous block of the canonical state."""
+    return tuple(range(nglobal))
 
-    def __init__(self, nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True, high_window: int = 8):
+
+def cyclic_layout(nqubits: int, nglobal: int) -> Tuple[int, ...]:
+    """Global qubits = the ``g`` trailing qubits (what ``_DistributedQFT`` asks for, models/qft.py:66): rank r holds the
+    amplitudes whose canonical index is congruent to r modulo 2^g."""
+    return tuple(range(nqubits - nglobal, nqubits))
+
+
+class Plan:
+    """Host-side plan: identical on every rank (pure function of the op list, n, g and the layout).
+
+    ``global_qubits[j]`` is the logical qubit that sits on the j-th most significant rank bit (physical bit n-1-j)
+    before the first and after the last gate; the local qubits follow in ascending order (the first local qubit is the
+    most significant bit of the shard index).  The reference picks its global qubits per circuit as well
+    (DistributedQubits, distcircuit.py:287-298; ``_DistributedQFT`` makes them the trailing ones): with the trailing
+    qubits global a QFT needs one exchange per global qubit, because its closing SWAPs put every early, finished qubit
+    exactly where a late one has to leave from."""
+
+    def __init__(self, nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True, high_window: int = 8,
+                 global_qubits: Optional[Sequence[int]] = None, batch_exchanges: bool = True):
         self.n, self.g = nqubits, nglobal
         self.nlocal = nqubits - nglobal
         if self.nlocal < 1:
             raise ValueError("need at least one local qubit per rank")
         n, nlocal = self.n, self.nlocal
+        gq = tuple(int(q) for q in (block_layout(n, nglobal) if global_qubits is None else global_qubits))
+        if len(gq) != nglobal or len(set(gq)) != nglobal or any(q < 0 or q >= n for q in gq):
+            raise ValueError(f"global_qubits must name {nglobal} distinct qubits, got {gq}")
+        self.global_qubits = gq
+        self.local_qubits = tuple(q for q in range(n) if q not in gq)
         self.segments: List[Segment] = []
         self.nexchanges = 0
-        pos = [n - 1 - q for q in range(n)]  # logical qubit -> physical bit
+        home = [0] * n  # logical qubit -> physical bit of the layout
+        for j, q in enumerate(gq):
+            home[q] = n - 1 - j
+        for k, q in enumerate(self.local_qubits):
+            home[q] = nlocal - 1 - k
+        self.home = tuple(home)
+        pos = list(home)
         # next dense use of every logical qubit, for the furthest-in-future eviction rule
         needs = [mixing_targets(op) for op in ops]
         swaps = [relabel_swaps and is_plain_swap(op) for op in ops]
@@ -109,9 +139,34 @@ class Plan:
                 continue
             for q in nd:
                 next_use[q].append(i)
+        # label_at_end[i][q]: the label the amplitudes called q before op i carry after the last relabelling SWAP -- the
+        # bit they belong on at the end is home[that label].  Walked backwards; only stored where it changes.
+        end_label = list(range(n))
+        label_changes = {}
+        for i in range(len(ops) - 1, -1, -1):
+            if swaps[i]:
+                a, b = ops[i].targets
+                end_label[a], end_label[b] = end_label[b], end_label[a]
+                label_changes[i] = list(end_label)
+        change_points = sorted(label_changes)
+
+        def end_home(q, i):
+            """Physical bit where the amplitudes named q before op i must end up."""
+            import bisect
+
+            k = bisect.bisect_left(change_points, i)
+            lab = label_changes[change_points[k]][q] if k < len(change_points) else q
+            return home[lab]
+
         ptr = [0] * n
         cur: List[PhysOp] = []
         window = [b for b in range(nlocal - 1, max(nlocal - 1 - high_window, -1), -1)]
+        never = len(ops) + 1
+
+        def use_after(q, i):
+            while ptr[q] < len(next_use[q]) and next_use[q][ptr[q]] < i:
+                ptr[q] += 1
+            return next_use[q][ptr[q]] if ptr[q] < len(next_use[q]) else never
 
         def flush():
             if cur:
@@ -125,42 +180,60 @@ class Plan:
             qa, qb = pos.index(gbit), pos.index(lbit)
             pos[qa], pos[qb] = lbit, gbit
 
+        def evictee(gbit, i, busy, only_finished):
+            """Window bit whose qubit leaves for ``gbit``: the one needed furthest in the future; among equals the one
+            that belongs on ``gbit`` at the end (saves the exchange that would bring it there later)."""
+            best, best_key = None, None
+            for b in window:
+                e = pos.index(b)
+                if e in busy:
+                    continue
+                use = use_after(e, i)
+                if only_finished and use != never:
+                    continue
+                key = (use, 1 if end_home(e, i) == gbit else 0)
+                if best_key is None or key > best_key:
+                    best, best_key = b, key
+            return best
+
         for i, op in enumerate(ops):
-            for q in set(op.targets) | set(op.controls):
-                while ptr[q] < len(next_use[q]) and next_use[q][ptr[q]] < i:
-                    ptr[q] += 1
             if swaps[i]:
                 a, b = op.targets
                 pos[a], pos[b] = pos[b], pos[a]  # the label "a" now names the amplitudes that were "b"
                 continue
             if len(needs[i]) > nlocal:
                 raise ValueError("gate has more mixing targets than there are local qubits")
+            exchanged = False
             for q in needs[i]:
                 if pos[q] < nlocal:
                     continue
-                best, best_use = None, -1
-                for b in window:
-                    e = pos.index(b)
-                    if e in needs[i]:
-                        continue
-                    while ptr[e] < len(next_use[e]) and next_use[e][ptr[e]] < i:
-                        ptr[e] += 1
-                    use = next_use[e][ptr[e]] if ptr[e] < len(next_use[e]) else len(ops) + 1
-                    if use > best_use:
-                        best, best_use = b, use
+                best = evictee(pos[q], i, needs[i], False)
                 if best is None:
                     raise ValueError("no local qubit available to exchange with")
                 exchange(pos[q], best)
+                exchanged = True
+            if exchanged and batch_exchanges:
+                # the local segment has been cut anyway: bring in every other global qubit that still has a mixing gate
+                # ahead, as long as a FINISHED qubit (no mixing gate ahead: it never has to come back) can leave for it.
+                # Same number of exchanges, but the gates between them end up in one local segment (one sweep).
+                ahead = sorted((use_after(q, i), q) for q in range(n) if pos[q] >= nlocal)
+                for use, q in ahead:
+                    if use == never:
+                        continue
+                    best = evictee(pos[q], i, needs[i], True)
+                    if best is None:
+                        break
+                    exchange(pos[q], best)
             cur.append(PhysOp(op.data, tuple(pos[q] for q in op.targets), tuple(pos[q] for q in op.controls), op.is_diagonal))
 
-        # ---- back to the canonical layout: logical qubit q on physical bit n-1-q
+        # ---- back to the layout: logical qubit q on physical bit home[q]
         def local_swap(b1, b2):
             cur.append(PhysOp(_SWAP, (b1, b2), (), False))
             qa, qb = pos.index(b1), pos.index(b2)
             pos[qa], pos[qb] = b2, b1
 
         for gbit in range(n - 1, nlocal - 1, -1):  # fix the global bits first
-            want = n - 1 - gbit  # logical qubit that belongs here
+            want = home.index(gbit)  # logical qubit that belongs here
             if pos[want] == gbit:
                 continue
             if pos[want] >= nlocal:  # it sits on another global bit: route through a high local bit
@@ -172,11 +245,22 @@ class Plan:
                 b = free
             exchange(gbit, b)
         for q in range(n):  # then the local permutation, as SWAP gates for the sweep planner
-            target = n - 1 - q
+            target = home[q]
             if target < nlocal and pos[q] != target:
                 local_swap(pos[q], target)
         flush()
-        assert pos == [n - 1 - q for q in range(n)]
+        assert pos == list(home)
+
+
+def choose_layout(nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True) -> Plan:
+    """The plan with the fewest exchanges among the block layout and the two orders of the cyclic one (ties: block)."""
+    cyc = cyclic_layout(nqubits, nglobal)
+    best = None
+    for gq in (block_layout(nqubits, nglobal), cyc, cyc[::-1]):
+        plan = Plan(nqubits, nglobal, ops, relabel_swaps=relabel_swaps, global_qubits=gq)
+        if best is None or plan.nexchanges < best.nexchanges:
+            best = plan
+    return best
 
 
 def specialise(p: PhysOp, nlocal: int, rank_: int) -> Optional[Op]:
@@ -251,14 +335,29 @@ class PeerShard:
         import torch.distributed as dist
 
         self.engine = engine
+        # two exported buffers: the out-of-place permutation kernel (K8) writes into the other one and the shard moves
+        # there -- on every rank at the same point of the plan (SWAP runs are never specialised away), so each rank knows
+        # which of a peer's two mappings is current without asking
         self.array = engine.malloc_exportable((1 << nlocal,), dtype)
+        self.alt = engine.malloc_exportable((1 << nlocal,), dtype)
+        self._base = (self.array.data_ptr(), self.alt.data_ptr())
         handles = [None] * dist.get_world_size()
-        dist.all_gather_object(handles, engine.ipc_handle(self.array))
-        self.peer_ptr = {}
-        for r, h in enumerate(handles):
+        dist.all_gather_object(handles, (engine.ipc_handle(self.array), engine.ipc_handle(self.alt)))
+        self._peer_ptrs = {}
+        for r, (h0, h1) in enumerate(handles):
             if r != dist.get_rank():
-                self.peer_ptr[r] = engine.ipc_open(h)
+                self._peer_ptrs[r] = (engine.ipc_open(h0), engine.ipc_open(h1))
         self.flag = torch.zeros(1, device=self.array.tensor.device)
+
+    @property
+    def current(self) -> int:
+        return self._base.index(self.array.data_ptr())
+
+    @property
+    def peer_ptr(self):
+        """rank -> device pointer of that rank's CURRENT buffer in this process."""
+        cur = self.current
+        return {r: p[cur] for r, p in self._peer_ptrs.items()}
 
     def fence(self):
         """Stream-ordered barrier across ranks: kernels enqueued after it start only when every rank's stream got here."""
@@ -275,7 +374,9 @@ class ShardedProgram:
     """A gate queue planned once for (n, world size) and specialised for this rank; ``run`` applies it to a shard."""
 
     def __init__(self, engine, nqubits: int, dtype, ops: Sequence[Op], relabel_swaps: bool = True, apply=None,
-                 staging_elems: int = 1 << 26):
+                 staging_elems: int = 1 << 26, global_qubits=None):
+        """``global_qubits``: None = the leading qubits (block layout: rank r holds state[r * 2^nlocal : (r+1) * 2^nlocal]),
+        a sequence of qubits (Plan), or "auto" = whichever of the block / cyclic layouts needs the fewest exchanges."""
         self.engine = engine
         self.world, self.rank = world_size(), rank()
         self.g = int(round(math.log2(self.world)))
@@ -283,7 +384,13 @@ class ShardedProgram:
             raise ValueError("the number of ranks must be a power of two")
         self.n, self.dtype = nqubits, np.dtype(dtype)
         self.nlocal = nqubits - self.g
-        self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps)
+        if isinstance(global_qubits, str):
+            if global_qubits != "auto":
+                raise ValueError(f"unknown layout {global_qubits!r}")
+            self.plan = choose_layout(nqubits, self.g, ops, relabel_swaps=relabel_swaps)
+        else:
+            self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps, global_qubits=global_qubits)
+        self.global_qubits, self.local_qubits = self.plan.global_qubits, self.plan.local_qubits
         self.segments = []
         for seg in self.plan.segments:
             if seg.kind == "local":
@@ -296,29 +403,53 @@ class ShardedProgram:
         self._staging_elems = staging_elems
         self.ngates = len(ops)
 
+    # ---- layout: canonical index <-> (rank, index in the shard) ------------------------------------------
+    def locate(self, index: int):
+        """-> (rank, shard index) of the amplitude with canonical index ``index`` (qubit 0 = most significant bit)."""
+        bit = lambda q: (index >> (self.n - 1 - q)) & 1  # noqa: E731
+        r = 0
+        for q in self.global_qubits:
+            r = (r << 1) | bit(q)
+        loc = 0
+        for q in self.local_qubits:
+            loc = (loc << 1) | bit(q)
+        return r, loc
+
+    def _axes(self):
+        return list(self.global_qubits) + list(self.local_qubits)
+
     # ---- shard constructors --------------------------------------------------------------------
     def peer_shard(self, index: Optional[int] = 0):
         """A shard in peer-mapped memory (enables the single-kernel NVLink exchange), initialised to |index>."""
         ps = PeerShard(self.engine, self.nlocal, self.dtype)
         ps.tensor.zero_()
-        if index is not None and (index >> self.nlocal) == self.rank:
-            ps.tensor[index & ((1 << self.nlocal) - 1)] = 1
+        if index is not None:
+            r, loc = self.locate(index)
+            if r == self.rank:
+                ps.tensor[loc] = 1
         return ps
 
     def basis_state(self, index: int = 0):
-        """|index> of the full register: the amplitude lives on rank index >> nlocal."""
+        """|index> of the full register: one amplitude on the rank that ``locate`` names."""
+        r, loc = self.locate(index)
         st = self.engine.basis_state(self.nlocal, self.dtype, 0)
-        if (index >> self.nlocal) != self.rank:
+        if r != self.rank:
             st.tensor.zero_()
-        elif index & ((1 << self.nlocal) - 1):
+        elif loc:
             st.tensor.zero_()
-            st.tensor[index & ((1 << self.nlocal) - 1)] = 1
+            st.tensor[loc] = 1
         return st
 
+    def shard_of(self, full: np.ndarray) -> np.ndarray:
+        """This rank's shard of a full host state in canonical order (small n)."""
+        if self.global_qubits == tuple(range(self.g)):
+            lo = self.rank << self.nlocal
+            return np.ascontiguousarray(full[lo : lo + (1 << self.nlocal)])
+        t = np.asarray(full).reshape((2,) * self.n).transpose(self._axes()).reshape(self.world, 1 << self.nlocal)
+        return np.ascontiguousarray(t[self.rank])
+
     def scatter(self, full: np.ndarray):
-        """This rank's shard of a full host state (canonical layout)."""
-        lo = self.rank << self.nlocal
-        return self.engine.upload(np.ascontiguousarray(full[lo : lo + (1 << self.nlocal)]).astype(self.dtype))
+        return self.engine.upload(self.shard_of(full).astype(self.dtype))
 
     # ---- execution ---------------------------------------------------------------------------------
     def _stage(self, tensor):
@@ -332,16 +463,16 @@ class ShardedProgram:
         peer = state if isinstance(state, PeerShard) else None
         if peer is not None:
             state = peer.array
-        tensor = state.tensor if hasattr(state, "tensor") else state
         out = RunStats()
         for seg in self.segments:
+            tensor = state.tensor if hasattr(state, "tensor") else state  # (a permutation re-points the DeviceArray)
             if seg[0] == "local":
                 if not seg[1]:
                     continue
                 if self._apply is not None:
                     self._apply(tensor, self.nlocal, seg[1])
                 else:
-                    st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed)
+                    st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed, alt=peer.alt if peer is not None else None)
                     out.nsweeps += st.nsweeps
                     out.elapsed_ms += st.elapsed_ms
                     out.perm_ms += getattr(st, "perm_ms", 0.0)
@@ -368,14 +499,18 @@ class ShardedProgram:
         return out
 
     def gather(self, state) -> np.ndarray:
-        """Full state on every rank (small n only)."""
+        """Full state in canonical order on every rank (small n only)."""
         import torch.distributed as dist
 
         tensor = state.tensor if hasattr(state, "tensor") else state
         tensor = tensor.clone()
         parts = [torch.empty_like(tensor) for _ in range(self.world)]
         dist.all_gather(parts, tensor)
-        return torch.cat(parts).cpu().numpy()
+        full = torch.cat(parts).cpu().numpy()
+        if self.global_qubits == tuple(range(self.g)):
+            return full
+        inv = np.argsort(self._axes())
+        return np.ascontiguousarray(full.reshape((2,) * self.n).transpose(inv)).reshape(-1)
 
 
 class RunStats:
@@ -405,14 +540,15 @@ def execute_circuit(backend, circuit, initial_state=None, nshots=None):
                 continue
             raise_error(NotImplementedError, "callbacks / collapsing measurements need the full state: not available across ranks")
         ops.extend(backend._gate_ops(gate, n))
-    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops)
+    gather_max = int(os.environ.get("QB_GATHER_MAX_QUBITS", 30))
+    # the sharded measurement path (dist_measure.py) works on the block layout; a state that is gathered may use any
+    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops, global_qubits="auto" if n <= gather_max else None)
     if initial_state is None:
         shard = prog.basis_state(0)
     else:
         host = backend.to_numpy(initial_state) if isinstance(initial_state, DeviceArray) else np.asarray(initial_state)
         shard = prog.scatter(host)
     prog.run(shard, timed=False)
-    gather_max = int(os.environ.get("QB_GATHER_MAX_QUBITS", 30))
     if n > gather_max:
         # too large to replicate: measurement outcomes come from the sharded state (dist_measure.py) -- marginal over the
         # measured qubits (all-reduce), then inverse-CDF sampling with the global legacy RNG as sample_shots does

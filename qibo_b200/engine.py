@@ -142,10 +142,12 @@ class Engine:
         del keep
         return stats
 
-    def permute_qubits(self, state: DeviceArray, nqubits: int, dest_of_qubit: Sequence[int], timed: bool = False):
-        """K8: out-of-place qubit permutation in one sweep; the DeviceArray is re-pointed at the result buffer
-        (buffers that other ranks have mapped through CUDA IPC are copied back instead).  Returns elapsed ms or None."""
-        scratch = torch.empty_like(state.tensor)
+    def permute_qubits(self, state: DeviceArray, nqubits: int, dest_of_qubit: Sequence[int], timed: bool = False, alt: Optional[DeviceArray] = None):
+        """K8: out-of-place qubit permutation in one sweep; the DeviceArray is re-pointed at the result buffer.  ``alt``:
+        a second buffer of the same shape to permute into -- the two DeviceArrays then trade buffers (shards that other
+        ranks have mapped through CUDA IPC ping-pong between two exported buffers this way); an IPC-exported buffer
+        without ``alt`` gets its result copied back in place.  Returns elapsed ms or None."""
+        scratch = torch.empty_like(state.tensor) if alt is None else alt.tensor
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -154,7 +156,11 @@ class Engine:
                 self.handle, state.data_ptr(), scratch.data_ptr(), nqubits, _DT[state.dtype], _int_array(dest_of_qubit)
             )
         )
-        if getattr(state, "_owner", None) is not None:
+        if alt is not None:
+            state.tensor, alt.tensor = alt.tensor, state.tensor
+            so, ao = getattr(state, "_owner", None), getattr(alt, "_owner", None)
+            state._owner, alt._owner = ao, so
+        elif getattr(state, "_owner", None) is not None:
             state.tensor.copy_(scratch)
         else:
             state.tensor = scratch
@@ -164,7 +170,8 @@ class Engine:
             return e0.elapsed_time(e1)
         return None
 
-    def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False):
+    def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False,
+                      alt: Optional[DeviceArray] = None):
         """Apply ``ops`` in order, several gates per HBM sweep.  Runs of >= MIN_SWAP_RUN uncontrolled SWAP gates (the
         bit reversal ending a QFT) become ONE out-of-place permutation sweep when a scratch buffer fits in memory.
         Returns the planner/timing statistics."""
@@ -175,7 +182,7 @@ class Engine:
         for kind, payload in segments:
             if kind == "perm":
                 try:
-                    ms = self.permute_qubits(state, nqubits, payload, timed=timed)
+                    ms = self.permute_qubits(state, nqubits, payload, timed=timed, alt=alt)
                 except torch.cuda.OutOfMemoryError:
                     ms = None
                     payload = swaps_for_permutation(payload)

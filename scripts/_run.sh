@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-for n in 29 33; do timeout 120 python scripts/dist_local_repro.py $n 8 0 --check > gpurun_out/r4d_repro$n.log 2>&1; done
-timeout 200 python scripts/dist_local_repro.py 35 8 0 > gpurun_out/r4d_repro35.log 2>&1
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/r4d_pytest.log 2>&1
+timeout 500 python -m pytest tests/test_gpu_distributed.py -x -q -m gpu > gpurun_out/r4f_dist_pytest.log 2>&1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r4f_bench2.log 2>&1
 echo finished

@@ -1,6 +1,6 @@
 """One-GPU reproduction of what rank R of W does in a sharded QFT(n): every local segment of the plan runs through
 Engine.apply_program on a 2^(n-g) shard (exchanges skipped: they only move data), optionally checked against the
-gate-by-gate K1 kernels on a second copy.   python scripts/dist_local_repro.py N W RANK [--check] [--c64]"""
+gate-by-gate K1 kernels on a second copy.   python scripts/dist_local_repro.py N W RANK [--check] [--c64] [--block]"""
 import os
 import sys
 import time
@@ -21,7 +21,8 @@ def main():
     g = W.bit_length() - 1
     nlocal = n - g
     eng = Engine(0)
-    plan = D.Plan(n, g, circuits.qft(n))
+    plan = D.Plan(n, g, circuits.qft(n)) if "--block" in sys.argv else D.choose_layout(n, g, circuits.qft(n))
+    print("global qubits", plan.global_qubits, "exchanges", plan.nexchanges, flush=True)
     gen = torch.Generator(device="cuda").manual_seed(1)
     tdt = torch.float64 if dtype == "complex128" else torch.float32
     a = eng.empty((1 << nlocal,), dtype)

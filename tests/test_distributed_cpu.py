@@ -30,7 +30,7 @@ def _oracle_apply(tensor, nlocal, ops):
     arr[:] = oracle_run(arr.copy(), ops, nlocal)
 
 
-def _worker(rank, world, port, case, n, seed, out):
+def _worker(rank, world, port, case, n, seed, layout, out):
     sys.path[:0] = [ROOT, HERE]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -48,9 +48,15 @@ def _worker(rank, world, port, case, n, seed, out):
         else:
             ops = random_zoo(n, 40, seed, max_dense=3)
         psi = rand_state(n, seed)
-        prog = ShardedProgram(None, n, "complex128", ops, apply=_oracle_apply, staging_elems=8)
+        prog = ShardedProgram(None, n, "complex128", ops, apply=_oracle_apply, staging_elems=8, global_qubits=layout)
         nl = prog.nlocal
-        shard = torch.from_numpy(psi[rank << nl : (rank + 1) << nl].copy())
+        if layout is None:
+            assert np.array_equal(prog.shard_of(psi), psi[rank << nl : (rank + 1) << nl])
+        shard = torch.from_numpy(prog.shard_of(psi).copy())
+        r0, loc0 = prog.locate(5)
+        basis = np.zeros(2**n)
+        basis[5] = 1
+        assert (prog.shard_of(basis)[loc0] == 1) == (r0 == rank) and prog.shard_of(basis).sum() == (1 if r0 == rank else 0)
         stats = prog.run(shard, timed=False)
         full = prog.gather(shard)
         ref = oracle_run(psi, ops, n)
@@ -61,11 +67,11 @@ def _worker(rank, world, port, case, n, seed, out):
         dist.destroy_process_group()
 
 
-def _run(world, case, n, seed=0):
+def _run(world, case, n, seed=0, layout=None):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, seed, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, n, seed, layout, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -80,6 +86,49 @@ def test_sharded_program_matches_oracle(world, case):
     err, nex, planned = _run(world, case, 7 if case != "qft" else 8, seed=3)
     assert err < 1e-12
     assert nex == planned
+
+
+@pytest.mark.parametrize("world,case,layout", [(2, "qft", "auto"), (4, "qft", "auto"), (4, "zoo", "auto"), (4, "qft", (5, 2)),
+                                               (2, "variational", (3,)), (4, "random", (7, 0))])
+def test_sharded_program_other_layouts(world, case, layout):
+    """Global qubits other than the leading ones (cyclic layout for the QFT, arbitrary sets): shard_of / gather map the
+    canonical state onto the ranks, and the plan returns to the same layout."""
+    err, nex, planned = _run(world, case, 8, seed=4, layout=layout)
+    assert err < 1e-12
+    assert nex == planned
+    if case == "qft" and layout == "auto":
+        assert planned == world.bit_length() - 1  # one exchange per global qubit, as the reference's _DistributedQFT
+
+
+def test_cyclic_layout_qft_plan():
+    """QFT with the trailing qubits global (models/qft.py:66): one exchange per global qubit, back to back, so that the
+    closing stages share one local segment; every rank-specialised segment reproduces the oracle through the product's
+    planner + passes (tests/emul)."""
+    sys.path[:0] = [ROOT, HERE]
+    import emul
+    from helpers import oracle_run, rand_state
+    from qibo_b200 import circuits
+    from qibo_b200.distributed import Plan, choose_layout, cyclic_layout, specialise
+
+    for n, g in ((33, 1), (34, 2), (35, 3)):
+        plan = choose_layout(n, g, circuits.qft(n))
+        assert plan.nexchanges == g and plan.global_qubits in (cyclic_layout(n, g), cyclic_layout(n, g)[::-1])
+        kinds = [s.kind for s in plan.segments]
+        assert kinds == ["local"] + ["exchange"] * g + ["local"]
+    n, g = 17, 3
+    nl = n - g
+    plan = Plan(n, g, circuits.qft(n), global_qubits=cyclic_layout(n, g))
+    assert plan.nexchanges == g
+    for r in range(1 << g):
+        for si, seg in enumerate(plan.segments):
+            if seg.kind != "local":
+                continue
+            local = [o for o in (specialise(p, nl, r) for p in seg.ops) if o is not None]
+            psi = rand_state(nl, si + r)
+            out, stats = emul.apply_program(psi, nl, local)
+            assert np.abs(out - oracle_run(psi, local, nl)).max() < 1e-12
+            if si == 0:
+                assert stats.nsweeps <= 3  # the global controls fold into the fans: no extra ops on the other ranks
 
 
 def test_plan_properties():

@@ -60,6 +60,28 @@ def _worker(rank, world, port, case, n, dtype, out):
         pfull = prog.gather(ps)
         err = max(err, float(np.abs(pfull - ref).max()))
         assert st2.nexchanges == stats.nexchanges
+        # run it twice more on the peer shard: the permutation ping-pongs between the two exported buffers, so the
+        # second and third runs exchange through the other mapping
+        ref2 = oracle_run(oracle_run(ref, ops, n), ops, n)
+        prog.run(ps)
+        prog.run(ps)
+        err = max(err, float(np.abs(prog.gather(ps) - ref2).max()))
+        # the layout with the fewest exchanges (trailing qubits global for a QFT), NCCL and peer-memory transports
+        auto = ShardedProgram(eng, n, dtype, ops, staging_elems=1 << 10, global_qubits="auto")
+        if case == "qft":
+            assert auto.plan.nexchanges == auto.g
+        sh = auto.scatter(psi)
+        auto.run(sh)
+        err = max(err, float(np.abs(auto.gather(sh) - ref).max()))
+        ps2 = auto.peer_shard(None)
+        ps2.tensor.copy_(auto.scatter(psi).tensor)
+        auto.run(ps2)
+        err = max(err, float(np.abs(auto.gather(ps2) - ref).max()))
+        zb = auto.basis_state(3)
+        auto.run(zb)
+        e3 = np.zeros(2**n, dtype=dtype)
+        e3[3] = 1
+        err = max(err, float(np.abs(auto.gather(zb) - oracle_run(e3, ops, n)).max()))
         if rank == 0:
             out.put((err, stats.nexchanges, stats.nsweeps))
     finally:
