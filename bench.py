@@ -185,6 +185,48 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def verify_sharded_qft(runner, state, args, eng, dist):
+    """Outside the timed region: QFT|x> on the shards against the closed form exp(2 pi i x k / 2^n) / sqrt(2^n) at sample
+    amplitudes of every rank (a misplaced chunk or a wrong rank-specialised phase shows; the norm alone would not).
+    If the all-to-all transport fails the check, fall back to the pairwise exchange kernel and check again."""
+    import cmath
+
+    import torch
+
+    n = runner.n
+    x = int("1011001110001011010111001010011011"[: n - 1] + "1", 2)
+    rk, loc = runner.locate(x)
+    rng = np.random.default_rng(17 + runner.rank)
+    sample = sorted({0, (1 << runner.nlocal) - 1, *rng.integers(0, 1 << runner.nlocal, size=256).tolist()})
+    tol = 1e-9 if args.dtype == "complex128" else 1e-4
+    out = {}
+    for attempt in ("alltoall" if runner.alltoall else "pairwise", "pairwise"):
+        st = state
+        st.tensor.zero_()
+        if rk == runner.rank:
+            st.tensor[loc] = 1
+        runner.run(st, timed=False)
+        got = st.tensor[torch.as_tensor(sample, device=st.tensor.device)].cpu().numpy()
+        err = 0.0
+        for v, l in zip(got, sample):
+            k = runner.canonical_index(runner.rank, int(l))
+            phase = (x * k) % (1 << n)
+            want = cmath.exp(2j * cmath.pi * (phase / float(1 << n))) / (2.0 ** (n / 2))
+            err = max(err, abs(complex(v) - want) * 2.0 ** (n / 2))
+        t = torch.tensor([err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = {"basis_state": x, "samples_per_rank": len(sample), "max_rel_err": float(t.item()), "exchange_path": attempt}
+        if out["max_rel_err"] < tol or attempt == "pairwise" or not runner.alltoall:
+            break
+        runner.alltoall = False  # every rank sees the same all-reduced error, so they switch together
+    if not out["max_rel_err"] < tol:
+        raise AssertionError(f"sharded QFT does not match the closed form: {out}")
+    state.tensor.zero_()
+    if runner.rank == runner.locate(0)[0]:
+        state.tensor[0] = 1
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -219,6 +261,9 @@ def run_gpu(args):
         step = lambda: eng.apply_program(state, n, ops, timed=True)  # noqa: E731
         barrier = lambda: None  # noqa: E731
 
+    verify = None
+    if world > 1:
+        verify = verify_sharded_qft(runner, state, args, eng, dist)
     for _ in range(args.warmup):
         stats = step()
     barrier()
@@ -227,7 +272,7 @@ def run_gpu(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    sweep_ms, nsweeps, xch_ms, xch_bytes, nxch, perm_ms, nperm = 0.0, 0, 0.0, 0, 0, 0.0, 0
+    sweep_ms, nsweeps, xch_ms, xch_bytes, nxch, perm_ms, nperm, nxl = 0.0, 0, 0.0, 0, 0, 0.0, 0, 0
     for _ in range(args.steps):
         stats = step()
         sweep_ms += stats.elapsed_ms
@@ -237,6 +282,7 @@ def run_gpu(args):
         xch_ms += getattr(stats, "exchange_ms", 0.0)
         xch_bytes += getattr(stats, "exchange_bytes", 0)
         nxch += getattr(stats, "nexchanges", 0)
+        nxl += getattr(stats, "nexchange_launches", 0)
     ev1.record()
     barrier()
     torch.cuda.synchronize()
@@ -344,16 +390,17 @@ def run_gpu(args):
                     "the other qubits in ascending order"} if world > 1 else {}),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(nsweeps + nxch), "whole_circuit_wall_s": ms_per_step / 1e3,
+            "gpu_launches": int(nsweeps + nxl), "whole_circuit_wall_s": ms_per_step / 1e3,
             "circuit_gates_per_s": circuit_gates_per_s,
             "value_definition": "gates applied x shards (N ranks each apply every gate to their 2^nlocal-amplitude shard) per second; equals circuit gates/s at N=1",
         }
         if world > 1:
             line["exchange"] = {
-                "count_per_step": nxch // args.steps, "ms_per_step_rank0": xch_ms / args.steps,
+                "count_per_step": nxch // args.steps, "launches_per_step": nxl // args.steps, "ms_per_step_rank0": xch_ms / args.steps,
                 "GBps_per_direction_rank0": (xch_bytes / 2) / max(xch_ms, 1e-9) / 1e6,
-                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": "one swap kernel over NVLink peer memory (CUDA IPC)" if args.exchange == "p2p" else "NCCL send/recv over NVLink, half-shard pairwise",
+                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": ("one all-to-all kernel per run of exchanges over NVLink peer memory (CUDA IPC)" if nxl < nxch else "one swap kernel over NVLink peer memory (CUDA IPC)") if args.exchange == "p2p" else "NCCL send/recv over NVLink, half-shard pairwise",
             }
+            line["verify"] = verify
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

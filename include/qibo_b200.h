@@ -172,6 +172,13 @@ int qb_unpack_half(qb_handle h, void* state, int nqubits, int dtype, int local_q
  * barrier on both ranks. */
 int qb_swap_half_p2p(qb_handle h, void* state, void* peer_state, int nqubits, int dtype, int local_qubit, int my_bit,
                      int part, int nparts);
+/* Several exchanges at once (k global qubits <-> the k leading local qubits): an all-to-all of contiguous chunks in ONE
+ * kernel.  Entry i swaps state[my_offsets[i] + e] with peer_states[i][peer_offsets[i] + e] for e in [begins[i], ends[i])
+ * (offsets and ranges in amplitudes; the two ranks of a pair take disjoint ranges).  1..8 entries.  Replaces k calls of
+ * qb_swap_half_p2p: (2^k - 1) / 2^k of a shard crosses NVLink instead of k / 2 (distcircuit.py:194-196 swaps one pair of
+ * qubits at a time).  Same stream-ordered barriers around it. */
+int qb_alltoall_p2p(qb_handle h, void* state, int dtype, int npeers, void* const* peer_states, const uint64_t* my_offsets,
+                    const uint64_t* peer_offsets, const uint64_t* begins, const uint64_t* ends);
 /* CUDA IPC plumbing so that ranks (one process per GPU) can map each other's buffers */
 int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes);
 int qb_ipc_open_handle(qb_handle h, const void* handle_64bytes, void** dptr_out);

@@ -866,6 +866,29 @@ int qb_swap_half_p2p(qb_handle h, void* state, void* peer_state, int nqubits, in
   return QB_OK;
 }
 
+int qb_alltoall_p2p(qb_handle h, void* state, int dtype, int npeers, void* const* peer_states, const uint64_t* my_offsets,
+                    const uint64_t* peer_offsets, const uint64_t* begins, const uint64_t* ends) {
+  if (!h || !state || (dtype != QB_C128 && dtype != QB_C64)) return fail(QB_ERR_INVALID, "bad state arguments");
+  if (npeers < 1 || npeers > 8 || !peer_states || !my_offsets || !peer_offsets || !begins || !ends)
+    return fail(QB_ERR_INVALID, "bad all-to-all arguments (1..8 peers)");
+  A2ATable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.npeers = npeers;
+  for (int i = 0; i < npeers; ++i) {
+    if (!peer_states[i] || begins[i] > ends[i]) return fail(QB_ERR_INVALID, "bad all-to-all entry");
+    tab.peer[i] = peer_states[i];
+    tab.my_off[i] = my_offsets[i];
+    tab.peer_off[i] = peer_offsets[i];
+    tab.begin[i] = begins[i];
+    tab.end[i] = ends[i];
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  int rc = launch_alltoall_p2p(h->stream, h->sm_count, state, dtype, tab);
+  if (rc != QB_OK) return cuda_fail(cudaGetLastError(), "alltoall_p2p");
+  return QB_OK;
+}
+
 int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes) {
   if (!h || !dptr || !handle_out_64bytes) return fail(QB_ERR_INVALID, "null argument");
   DeviceGuard guard(h->device);

@@ -493,6 +493,52 @@ inline int launch_swap_half_p2p(cudaStream_t stream, int sm_count, void* state, 
   return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
 }
 
+// ---- K7b: several global<->local exchanges at once = an all-to-all of contiguous chunks ------------------------------
+// k exchanges on the k leading local bits move chunk t of rank r to chunk t' of rank r' (an involution): ONE kernel swaps
+// this rank's share of every pair through the peers' mapped shards -- (2^k - 1) / 2^k of a shard crosses NVLink instead
+// of k / 2.  Block b serves peer b % npeers, so all pairs progress together.
+struct A2ATable {
+  void* peer[8];
+  uint64_t my_off[8], peer_off[8], begin[8], end[8];  // amplitudes; [begin, end) = this rank's share of the pair's chunk
+  int npeers;
+  int pad;
+};
+template <typename C, int U>
+__global__ void __launch_bounds__(256) k7_alltoall_p2p(C* __restrict__ mine, const __grid_constant__ A2ATable tab) {
+  const int p = blockIdx.x % tab.npeers;
+  const uint64_t stride = uint64_t(gridDim.x / tab.npeers) * blockDim.x;
+  C* __restrict__ a = mine + tab.my_off[p];
+  C* __restrict__ b = reinterpret_cast<C*>(tab.peer[p]) + tab.peer_off[p];
+  const uint64_t end = tab.end[p];
+  for (uint64_t i0 = tab.begin[p] + uint64_t(blockIdx.x / tab.npeers) * blockDim.x + threadIdx.x; i0 < end; i0 += stride * U) {
+    C x[U], y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * stride;
+      if (i < end) {
+        x[u] = ld_stream(a + i);
+        y[u] = ld_stream(b + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * stride;
+      if (i < end) {
+        st_stream(a + i, y[u]);
+        st_stream(b + i, x[u]);
+      }
+    }
+  }
+}
+
+inline int launch_alltoall_p2p(cudaStream_t stream, int sm_count, void* state, int dtype, const A2ATable& tab) {
+  const int per_peer = (sm_count * env_int("QB_P2P_BLOCKS_PER_SM", 8) + tab.npeers - 1) / tab.npeers;
+  const int grid = per_peer * tab.npeers;
+  if (dtype == QB_C128) k7_alltoall_p2p<double2, 4><<<grid, 256, 0, stream>>>((double2*)state, tab);
+  else k7_alltoall_p2p<float2, 4><<<grid, 256, 0, stream>>>((float2*)state, tab);
+  return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
+}
+
 inline int launch_half_copy(cudaStream_t stream, int sm_count, void* state, void* staging, int nqubits, int dtype, int pos, int bit,
                             int unpack) {
   const uint64_t half = uint64_t(1) << (nqubits - 1);

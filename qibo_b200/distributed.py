@@ -63,6 +63,48 @@ class Segment:
     lbit: int = -1  # exchange: local physical bit
 
 
+def exchange_runs(segments):
+    """Consecutive exchange segments on pairwise distinct bits, as lists of (gbit, lbit): they commute, so a run can be
+    carried out as ONE all-to-all (ShardedProgram.run) -- [("local", ops) | ("exchange", [(gbit, lbit), ...])]."""
+    out = []
+    for seg in segments:
+        if seg.kind == "local":
+            out.append(("local", seg.ops))
+            continue
+        if out and out[-1][0] == "exchange":
+            used = {b for pr in out[-1][1] for b in pr}
+            if seg.gbit not in used and seg.lbit not in used:
+                out[-1][1].append((seg.gbit, seg.lbit))
+                continue
+        out.append(("exchange", [(seg.gbit, seg.lbit)]))
+    return out
+
+
+def alltoall_entries(rank_: int, nlocal: int, pairs):
+    """The chunk swaps of rank ``rank_`` for a run of exchanges whose local bits are the k leading ones: chunk t (the k
+    leading bits of the shard index) trades places with chunk t' of rank r', where every (gbit, lbit) pair swaps one bit
+    of r with one bit of t.  -> [(peer rank, my offset, peer offset, begin, end)] in amplitudes, or None when the local
+    bits are not the leading ones.  The two ranks of a pair split the chunk: the lower rank moves the first half."""
+    k = len(pairs)
+    lo = nlocal - k
+    if sorted(l for _, l in pairs) != list(range(lo, nlocal)) or len({g for g, _ in pairs}) != k:
+        return None
+    csz = 1 << lo
+    out = []
+    for t in range(1 << k):
+        r2, t2 = rank_, t
+        for gbit, lbit in pairs:
+            j, c = gbit - nlocal, lbit - lo
+            rb, tb = (rank_ >> j) & 1, (t >> c) & 1
+            r2 = (r2 & ~(1 << j)) | (tb << j)
+            t2 = (t2 & ~(1 << c)) | (rb << c)
+        if r2 == rank_:
+            continue
+        begin, end = (0, csz // 2) if rank_ < r2 else (csz // 2, csz)
+        out.append((r2, t * csz, t2 * csz, begin, end))
+    return out
+
+
 def mixing_targets(op: Op) -> List[int]:
     """Targets whose 0/1 subspaces the matrix mixes -- the only qubits that must be local."""
     if op.is_diagonal:
@@ -392,12 +434,15 @@ class ShardedProgram:
             self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps, global_qubits=global_qubits)
         self.global_qubits, self.local_qubits = self.plan.global_qubits, self.plan.local_qubits
         self.segments = []
-        for seg in self.plan.segments:
-            if seg.kind == "local":
-                local = [o for o in (specialise(p, self.nlocal, self.rank) for p in seg.ops) if o is not None]
+        for kind, payload in exchange_runs(self.plan.segments):
+            if kind == "local":
+                local = [o for o in (specialise(p, self.nlocal, self.rank) for p in payload) if o is not None]
                 self.segments.append(("local", local))
             else:
-                self.segments.append(("exchange", seg.gbit, seg.lbit))
+                self.segments.append(("exchange", list(payload)))
+        # runs of >= alltoall_min exchanges go through the all-to-all kernel (peer-memory shards only)
+        self.alltoall = os.environ.get("QB_NO_ALLTOALL", "") in ("", "0")
+        self.alltoall_min = int(os.environ.get("QB_ALLTOALL_MIN", "2"))
         self._apply = apply  # test hook: NumPy shard executor
         self._staging = None
         self._staging_elems = staging_elems
@@ -414,6 +459,16 @@ class ShardedProgram:
         for q in self.local_qubits:
             loc = (loc << 1) | bit(q)
         return r, loc
+
+    def canonical_index(self, rank_: int, loc: int) -> int:
+        """Inverse of ``locate``."""
+        index = 0
+        for j, q in enumerate(self.global_qubits):
+            index |= ((rank_ >> (self.g - 1 - j)) & 1) << (self.n - 1 - q)
+        nl = len(self.local_qubits)
+        for k, q in enumerate(self.local_qubits):
+            index |= ((loc >> (nl - 1 - k)) & 1) << (self.n - 1 - q)
+        return index
 
     def _axes(self):
         return list(self.global_qubits) + list(self.local_qubits)
@@ -478,20 +533,33 @@ class ShardedProgram:
                     out.perm_ms += getattr(st, "perm_ms", 0.0)
                     out.nperm += getattr(st, "nperm", 0)
             else:
+                pairs = seg[1]
                 t0 = None
                 if tensor.is_cuda and timed:
                     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     t0.record()
-                if peer is not None:
-                    j = seg[1] - self.nlocal
-                    b = (self.rank >> j) & 1
+                entries = alltoall_entries(self.rank, self.nlocal, pairs) if (peer is not None and self.alltoall and len(pairs) >= self.alltoall_min) else None
+                if entries is not None:
+                    # ONE kernel for the whole run of exchanges: an all-to-all of contiguous chunks over peer memory
+                    ptrs = peer.peer_ptr
                     peer.fence()
-                    self.engine.swap_half_p2p(state, peer.peer_ptr[self.rank ^ (1 << j)], self.nlocal, self.nlocal - 1 - seg[2], b, b, 2)
+                    self.engine.alltoall_p2p(state, [(ptrs[r2], a, b, lo, hi) for r2, a, b, lo, hi in entries])
                     peer.fence()
-                    out.exchange_bytes += tensor.element_size() * tensor.numel()
+                    out.exchange_bytes += 2 * tensor.element_size() * sum(hi - lo for _, _, _, lo, hi in entries) * 2
+                    out.nexchange_launches += 1
                 else:
-                    out.exchange_bytes += exchange_half(tensor, self.nlocal, seg[1], seg[2], self._stage(tensor))
-                out.nexchanges += 1
+                    for gbit, lbit in pairs:
+                        if peer is not None:
+                            j = gbit - self.nlocal
+                            b = (self.rank >> j) & 1
+                            peer.fence()
+                            self.engine.swap_half_p2p(state, peer.peer_ptr[self.rank ^ (1 << j)], self.nlocal, self.nlocal - 1 - lbit, b, b, 2)
+                            peer.fence()
+                            out.exchange_bytes += tensor.element_size() * tensor.numel()
+                        else:
+                            out.exchange_bytes += exchange_half(tensor, self.nlocal, gbit, lbit, self._stage(tensor))
+                        out.nexchange_launches += 1
+                out.nexchanges += len(pairs)
                 if t0 is not None:
                     t1.record()
                     t1.synchronize()
@@ -520,6 +588,7 @@ class RunStats:
         self.perm_ms = 0.0  # of which: K8 permutation launches
         self.nperm = 0
         self.nexchanges = 0
+        self.nexchange_launches = 0  # kernels (or NCCL rounds): a run of exchanges done as one all-to-all counts once
         self.exchange_ms = 0.0
         self.exchange_bytes = 0
 

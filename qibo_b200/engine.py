@@ -305,6 +305,13 @@ class Engine:
             )
         )
 
+    def alltoall_p2p(self, state: DeviceArray, entries):
+        """K7b: ``entries`` = [(peer_ptr, my_offset, peer_offset, begin, end)] in amplitudes (distributed.alltoall_entries)."""
+        k = len(entries)
+        ptrs = (ctypes.c_void_p * k)(*[e[0] for e in entries])
+        cols = [(ctypes.c_uint64 * k)(*[int(e[c]) for e in entries]) for c in (1, 2, 3, 4)]
+        _lib.check(self.lib.qb_alltoall_p2p(self.handle, state.data_ptr(), _DT[state.dtype], k, ptrs, *cols))
+
     def mem_info(self):
         free, total = ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(self.lib.qb_mem_info(self.handle, ctypes.byref(free), ctypes.byref(total)))

@@ -131,6 +131,46 @@ def test_cyclic_layout_qft_plan():
                 assert stats.nsweeps <= 3  # the global controls fold into the fans: no extra ops on the other ranks
 
 
+def test_alltoall_entries_equal_sequential_exchanges():
+    """A run of exchanges as one all-to-all of chunks (K7b, alltoall_entries) moves every amplitude where the pairwise
+    half-shard exchanges would, one after the other -- all ranks simulated in one process."""
+    sys.path[:0] = [ROOT, HERE]
+    from qibo_b200.distributed import Segment, alltoall_entries, exchange_runs
+
+    rng = np.random.default_rng(0)
+    for g, nlocal, pairs in ((3, 6, [(8, 3), (7, 4), (6, 5)]), (3, 5, [(5, 4), (7, 2), (6, 3)]), (2, 4, [(5, 3), (4, 2)]),
+                             (1, 3, [(3, 2)]), (3, 5, [(6, 4), (5, 3)])):
+        W = 1 << g
+        shards = [rng.normal(size=1 << nlocal) for _ in range(W)]
+        # reference: the pairwise exchanges in sequence (exchange_half semantics: rank r, bit value b of global bit j,
+        # trades its half with local bit == 1 - b against the partner's half with local bit == b)
+        ref = [s.copy() for s in shards]
+        for gbit, lbit in pairs:
+            j = gbit - nlocal
+            new = [s.copy() for s in ref]
+            for r in range(W):
+                b = (r >> j) & 1
+                idx = np.arange(1 << nlocal)
+                mine = idx[((idx >> lbit) & 1) == 1 - b]
+                new[r][mine] = ref[r ^ (1 << j)][mine ^ (1 << lbit)]
+            ref = new
+        got = [s.copy() for s in shards]
+        for r in range(W):
+            ent = alltoall_entries(r, nlocal, pairs)
+            assert ent is not None and len(ent) == (1 << len(pairs)) - 1
+            assert len({e[0] for e in ent}) == len(ent)  # every peer once
+            for r2, a, b_, lo, hi in ent:
+                x = got[r][a + lo : a + hi].copy()
+                got[r][a + lo : a + hi] = got[r2][b_ + lo : b_ + hi]
+                got[r2][b_ + lo : b_ + hi] = x
+        for r in range(W):
+            np.testing.assert_array_equal(got[r], ref[r])
+    assert alltoall_entries(0, 6, [(8, 3), (7, 5)]) is None  # local bits are not the leading ones: pairwise exchanges
+    runs = exchange_runs([Segment("exchange", gbit=8, lbit=5), Segment("exchange", gbit=7, lbit=4), Segment("exchange", gbit=8, lbit=3),
+                          Segment("local", ops=[]), Segment("exchange", gbit=6, lbit=5)])
+    assert [(k, p) for k, p in runs if k == "exchange"] == [("exchange", [(8, 5), (7, 4)]), ("exchange", [(8, 3)]), ("exchange", [(6, 5)])]
+
+
 def test_plan_properties():
     """Device-free planner checks in the spirit of tests/test_models_distcircuit.py:95-103: no mixing target is
     ever on a global bit inside a local segment, and the layout is canonical at the end."""

@@ -75,8 +75,14 @@ def _worker(rank, world, port, case, n, dtype, out):
         err = max(err, float(np.abs(auto.gather(sh) - ref).max()))
         ps2 = auto.peer_shard(None)
         ps2.tensor.copy_(auto.scatter(psi).tensor)
-        auto.run(ps2)
+        st3 = auto.run(ps2)
         err = max(err, float(np.abs(auto.gather(ps2) - ref).max()))
+        # ... and with every run of exchanges on the leading local bits as ONE all-to-all kernel (K7b), single ones too
+        auto.alltoall_min = 1
+        ps2.tensor.copy_(auto.scatter(psi).tensor)
+        st4 = auto.run(ps2)
+        err = max(err, float(np.abs(auto.gather(ps2) - ref).max()))
+        assert st4.nexchanges == st3.nexchanges and st4.nexchange_launches <= st3.nexchange_launches
         zb = auto.basis_state(3)
         auto.run(zb)
         e3 = np.zeros(2**n, dtype=dtype)
