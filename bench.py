@@ -200,7 +200,13 @@ def verify_sharded_qft(runner, state, args, eng, dist):
     sample = sorted({0, (1 << runner.nlocal) - 1, *rng.integers(0, 1 << runner.nlocal, size=256).tolist()})
     tol = 1e-9 if args.dtype == "complex128" else 1e-4
     out = {}
-    for attempt in ("alltoall" if runner.alltoall else "pairwise", "pairwise"):
+    def path():
+        if not runner.alltoall:
+            return "pairwise"
+        return "alltoall-push" if runner.alltoall_push else "alltoall-swap"
+
+    for _ in range(3):  # all-to-all out of place -> all-to-all in place -> pairwise exchanges
+        attempt = path()
         st = state
         st.tensor.zero_()
         if rk == runner.rank:
@@ -216,9 +222,13 @@ def verify_sharded_qft(runner, state, args, eng, dist):
         t = torch.tensor([err], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out = {"basis_state": x, "samples_per_rank": len(sample), "max_rel_err": float(t.item()), "exchange_path": attempt}
-        if out["max_rel_err"] < tol or attempt == "pairwise" or not runner.alltoall:
+        if out["max_rel_err"] < tol or attempt == "pairwise":
             break
-        runner.alltoall = False  # every rank sees the same all-reduced error, so they switch together
+        # every rank sees the same all-reduced error, so they switch together
+        if runner.alltoall_push:
+            runner.alltoall_push = False
+        else:
+            runner.alltoall = False
     if not out["max_rel_err"] < tol:
         raise AssertionError(f"sharded QFT does not match the closed form: {out}")
     state.tensor.zero_()
@@ -398,7 +408,7 @@ def run_gpu(args):
             line["exchange"] = {
                 "count_per_step": nxch // args.steps, "launches_per_step": nxl // args.steps, "ms_per_step_rank0": xch_ms / args.steps,
                 "GBps_per_direction_rank0": (xch_bytes / 2) / max(xch_ms, 1e-9) / 1e6,
-                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": ("one all-to-all kernel per run of exchanges over NVLink peer memory (CUDA IPC)" if nxl < nxch else "one swap kernel over NVLink peer memory (CUDA IPC)") if args.exchange == "p2p" else "NCCL send/recv over NVLink, half-shard pairwise",
+                "bytes_per_step_rank0": xch_bytes // args.steps, "transport": (("one all-to-all kernel per run of exchanges over NVLink peer memory (CUDA IPC)" + (", out of place: remote stores only" if runner.alltoall_push else ", in-place chunk swaps")) if (nxl < nxch or runner.alltoall_min <= 1) and runner.alltoall else "one swap kernel over NVLink peer memory (CUDA IPC)") if args.exchange == "p2p" else "NCCL send/recv over NVLink, half-shard pairwise",
             }
             line["verify"] = verify
         print(json.dumps(line), flush=True)

@@ -179,6 +179,11 @@ int qb_swap_half_p2p(qb_handle h, void* state, void* peer_state, int nqubits, in
  * qubits at a time).  Same stream-ordered barriers around it. */
 int qb_alltoall_p2p(qb_handle h, void* state, int dtype, int npeers, void* const* peer_states, const uint64_t* my_offsets,
                     const uint64_t* peer_offsets, const uint64_t* begins, const uint64_t* ends);
+/* Out-of-place form of the same all-to-all: entry i copies state[my_offsets[i] + e] to dest_buffers[i][dest_offsets[i] + e]
+ * for e in [begins[i], ends[i]) -- the destination ranks' SECOND buffers (this rank's own for the chunk that stays).
+ * Remote stores only; afterwards every rank continues in its second buffer. */
+int qb_alltoall_push_p2p(qb_handle h, const void* state, int dtype, int nentries, void* const* dest_buffers,
+                         const uint64_t* my_offsets, const uint64_t* dest_offsets, const uint64_t* begins, const uint64_t* ends);
 /* CUDA IPC plumbing so that ranks (one process per GPU) can map each other's buffers */
 int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes);
 int qb_ipc_open_handle(qb_handle h, const void* handle_64bytes, void** dptr_out);

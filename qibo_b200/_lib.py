@@ -76,6 +76,7 @@ PROTOTYPES = {
     "qb_unpack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qb_swap_half_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
     "qb_alltoall_p2p": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]),
+    "qb_alltoall_push_p2p": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]),
     "qb_ipc_get_handle": (c_int, [c_void_p, c_void_p, c_void_p]),
     "qb_ipc_open_handle": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "qb_ipc_close_handle": (c_int, [c_void_p, c_void_p]),

@@ -866,11 +866,11 @@ int qb_swap_half_p2p(qb_handle h, void* state, void* peer_state, int nqubits, in
   return QB_OK;
 }
 
-int qb_alltoall_p2p(qb_handle h, void* state, int dtype, int npeers, void* const* peer_states, const uint64_t* my_offsets,
-                    const uint64_t* peer_offsets, const uint64_t* begins, const uint64_t* ends) {
+static int alltoall_common(qb_handle h, const void* state, int dtype, int npeers, void* const* peer_states, const uint64_t* my_offsets,
+                           const uint64_t* peer_offsets, const uint64_t* begins, const uint64_t* ends, bool push) {
   if (!h || !state || (dtype != QB_C128 && dtype != QB_C64)) return fail(QB_ERR_INVALID, "bad state arguments");
   if (npeers < 1 || npeers > 8 || !peer_states || !my_offsets || !peer_offsets || !begins || !ends)
-    return fail(QB_ERR_INVALID, "bad all-to-all arguments (1..8 peers)");
+    return fail(QB_ERR_INVALID, "bad all-to-all arguments (1..8 entries)");
   A2ATable tab;
   memset(&tab, 0, sizeof(tab));
   tab.npeers = npeers;
@@ -884,9 +884,20 @@ int qb_alltoall_p2p(qb_handle h, void* state, int dtype, int npeers, void* const
   }
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
-  int rc = launch_alltoall_p2p(h->stream, h->sm_count, state, dtype, tab);
-  if (rc != QB_OK) return cuda_fail(cudaGetLastError(), "alltoall_p2p");
+  int rc = push ? launch_alltoall_push(h->stream, h->sm_count, state, dtype, tab)
+                : launch_alltoall_p2p(h->stream, h->sm_count, const_cast<void*>(state), dtype, tab);
+  if (rc != QB_OK) return cuda_fail(cudaGetLastError(), push ? "alltoall_push" : "alltoall_p2p");
   return QB_OK;
+}
+
+int qb_alltoall_p2p(qb_handle h, void* state, int dtype, int npeers, void* const* peer_states, const uint64_t* my_offsets,
+                    const uint64_t* peer_offsets, const uint64_t* begins, const uint64_t* ends) {
+  return alltoall_common(h, state, dtype, npeers, peer_states, my_offsets, peer_offsets, begins, ends, false);
+}
+
+int qb_alltoall_push_p2p(qb_handle h, const void* state, int dtype, int nentries, void* const* dest_buffers, const uint64_t* my_offsets,
+                         const uint64_t* dest_offsets, const uint64_t* begins, const uint64_t* ends) {
+  return alltoall_common(h, state, dtype, nentries, dest_buffers, my_offsets, dest_offsets, begins, ends, true);
 }
 
 int qb_ipc_get_handle(qb_handle h, void* dptr, void* handle_out_64bytes) {

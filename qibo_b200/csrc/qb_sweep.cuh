@@ -531,6 +531,38 @@ __global__ void __launch_bounds__(256) k7_alltoall_p2p(C* __restrict__ mine, con
   }
 }
 
+// Out-of-place variant: every chunk is read locally and WRITTEN into the destination rank's second buffer (or this
+// rank's own for the chunk that stays) -- remote stores only, no remote loads.  The shards then flip buffers.
+template <typename C, int U>
+__global__ void __launch_bounds__(256) k7_alltoall_push(const C* __restrict__ mine, const __grid_constant__ A2ATable tab) {
+  const int p = blockIdx.x % tab.npeers;
+  const uint64_t stride = uint64_t(gridDim.x / tab.npeers) * blockDim.x;
+  const C* __restrict__ a = mine + tab.my_off[p];
+  C* __restrict__ b = reinterpret_cast<C*>(tab.peer[p]) + tab.peer_off[p];
+  const uint64_t end = tab.end[p];
+  for (uint64_t i0 = tab.begin[p] + uint64_t(blockIdx.x / tab.npeers) * blockDim.x + threadIdx.x; i0 < end; i0 += stride * U) {
+    C x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * stride;
+      if (i < end) x[u] = ld_stream(a + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * stride;
+      if (i < end) st_stream(b + i, x[u]);
+    }
+  }
+}
+
+inline int launch_alltoall_push(cudaStream_t stream, int sm_count, const void* state, int dtype, const A2ATable& tab) {
+  const int per_peer = (sm_count * env_int("QB_P2P_BLOCKS_PER_SM", 8) + tab.npeers - 1) / tab.npeers;
+  const int grid = per_peer * tab.npeers;
+  if (dtype == QB_C128) k7_alltoall_push<double2, 8><<<grid, 256, 0, stream>>>((const double2*)state, tab);
+  else k7_alltoall_push<float2, 8><<<grid, 256, 0, stream>>>((const float2*)state, tab);
+  return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
+}
+
 inline int launch_alltoall_p2p(cudaStream_t stream, int sm_count, void* state, int dtype, const A2ATable& tab) {
   const int per_peer = (sm_count * env_int("QB_P2P_BLOCKS_PER_SM", 8) + tab.npeers - 1) / tab.npeers;
   const int grid = per_peer * tab.npeers;

@@ -105,6 +105,26 @@ def alltoall_entries(rank_: int, nlocal: int, pairs):
     return out
 
 
+def alltoall_push_entries(rank_: int, nlocal: int, pairs):
+    """Out-of-place form: EVERY chunk t of this rank (the one that stays included) is copied to chunk t' of rank r''s second
+    buffer -> [(destination rank, my offset, its offset, 0, chunk size)], or None (see ``alltoall_entries``)."""
+    k = len(pairs)
+    lo = nlocal - k
+    if sorted(l for _, l in pairs) != list(range(lo, nlocal)) or len({g for g, _ in pairs}) != k:
+        return None
+    csz = 1 << lo
+    out = []
+    for t in range(1 << k):
+        r2, t2 = rank_, t
+        for gbit, lbit in pairs:
+            j, c = gbit - nlocal, lbit - lo
+            rb, tb = (rank_ >> j) & 1, (t >> c) & 1
+            r2 = (r2 & ~(1 << j)) | (tb << j)
+            t2 = (t2 & ~(1 << c)) | (rb << c)
+        out.append((r2, t * csz, t2 * csz, 0, csz))
+    return out
+
+
 def mixing_targets(op: Op) -> List[int]:
     """Targets whose 0/1 subspaces the matrix mixes -- the only qubits that must be local."""
     if op.is_diagonal:
@@ -396,6 +416,21 @@ class PeerShard:
         return self._base.index(self.array.data_ptr())
 
     @property
+    def alt_ptrs(self):
+        """rank -> device pointer of that rank's SECOND (not current) buffer in this process, this rank included."""
+        import torch.distributed as dist
+
+        other = 1 - self.current
+        out = {r: p[other] for r, p in self._peer_ptrs.items()}
+        out[dist.get_rank()] = self.alt.data_ptr()
+        return out
+
+    def flip(self):
+        """Continue in the second buffer (every rank does so at the same point of the plan)."""
+        self.array.tensor, self.alt.tensor = self.alt.tensor, self.array.tensor
+        self.array._owner, self.alt._owner = self.alt._owner, self.array._owner
+
+    @property
     def peer_ptr(self):
         """rank -> device pointer of that rank's CURRENT buffer in this process."""
         cur = self.current
@@ -442,7 +477,9 @@ class ShardedProgram:
                 self.segments.append(("exchange", list(payload)))
         # runs of >= alltoall_min exchanges go through the all-to-all kernel (peer-memory shards only)
         self.alltoall = os.environ.get("QB_NO_ALLTOALL", "") in ("", "0")
-        self.alltoall_min = int(os.environ.get("QB_ALLTOALL_MIN", "2"))
+        self.alltoall_min = int(os.environ.get("QB_ALLTOALL_MIN", "1"))
+        # out-of-place all-to-all (remote stores only, then flip buffers): 676 vs 653 GB/s per direction on 2 GPUs
+        self.alltoall_push = os.environ.get("QB_ALLTOALL_PUSH", "1") not in ("", "0")
         self._apply = apply  # test hook: NumPy shard executor
         self._staging = None
         self._staging_elems = staging_elems
@@ -538,33 +575,52 @@ class ShardedProgram:
                 if tensor.is_cuda and timed:
                     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     t0.record()
-                entries = alltoall_entries(self.rank, self.nlocal, pairs) if (peer is not None and self.alltoall and len(pairs) >= self.alltoall_min) else None
-                if entries is not None:
-                    # ONE kernel for the whole run of exchanges: an all-to-all of contiguous chunks over peer memory
-                    ptrs = peer.peer_ptr
-                    peer.fence()
-                    self.engine.alltoall_p2p(state, [(ptrs[r2], a, b, lo, hi) for r2, a, b, lo, hi in entries])
-                    peer.fence()
-                    out.exchange_bytes += 2 * tensor.element_size() * sum(hi - lo for _, _, _, lo, hi in entries) * 2
-                    out.nexchange_launches += 1
-                else:
-                    for gbit, lbit in pairs:
-                        if peer is not None:
-                            j = gbit - self.nlocal
-                            b = (self.rank >> j) & 1
-                            peer.fence()
-                            self.engine.swap_half_p2p(state, peer.peer_ptr[self.rank ^ (1 << j)], self.nlocal, self.nlocal - 1 - lbit, b, b, 2)
-                            peer.fence()
-                            out.exchange_bytes += tensor.element_size() * tensor.numel()
-                        else:
-                            out.exchange_bytes += exchange_half(tensor, self.nlocal, gbit, lbit, self._stage(tensor))
-                        out.nexchange_launches += 1
+                self._exchange_run(state, peer, tensor, pairs, out)
                 out.nexchanges += len(pairs)
                 if t0 is not None:
                     t1.record()
                     t1.synchronize()
                     out.exchange_ms += t0.elapsed_time(t1)
         return out
+
+    def _exchange_run(self, state, peer, tensor, pairs, out):
+        """One run of exchanges [(gbit, lbit), ...] on pairwise distinct bits."""
+        use_a2a = peer is not None and self.alltoall and len(pairs) >= self.alltoall_min
+        elem = tensor.element_size()
+        if use_a2a and self.alltoall_push and len(pairs) <= 3:
+            entries = alltoall_push_entries(self.rank, self.nlocal, pairs)
+            if entries is not None:
+                # out of place: local loads, remote STORES into the destination ranks' second buffers, then every rank
+                # continues in its second buffer (the same flip the K8 permutation does)
+                dst = peer.alt_ptrs
+                peer.fence()
+                self.engine.alltoall_p2p(state, [(dst[r2], a, b, lo, hi) for r2, a, b, lo, hi in entries], push=True)
+                peer.fence()
+                peer.flip()
+                out.exchange_bytes += 2 * elem * sum(hi - lo for r2, _, _, lo, hi in entries if r2 != self.rank)
+                out.nexchange_launches += 1
+                return
+        entries = alltoall_entries(self.rank, self.nlocal, pairs) if use_a2a else None
+        if entries is not None:
+            # ONE kernel for the whole run of exchanges: an all-to-all of contiguous chunks over peer memory
+            ptrs = peer.peer_ptr
+            peer.fence()
+            self.engine.alltoall_p2p(state, [(ptrs[r2], a, b, lo, hi) for r2, a, b, lo, hi in entries])
+            peer.fence()
+            out.exchange_bytes += 4 * elem * sum(hi - lo for _, _, _, lo, hi in entries)
+            out.nexchange_launches += 1
+            return
+        for gbit, lbit in pairs:
+            if peer is not None:
+                j = gbit - self.nlocal
+                b = (self.rank >> j) & 1
+                peer.fence()
+                self.engine.swap_half_p2p(state, peer.peer_ptr[self.rank ^ (1 << j)], self.nlocal, self.nlocal - 1 - lbit, b, b, 2)
+                peer.fence()
+                out.exchange_bytes += elem * tensor.numel()
+            else:
+                out.exchange_bytes += exchange_half(tensor, self.nlocal, gbit, lbit, self._stage(tensor))
+            out.nexchange_launches += 1
 
     def gather(self, state) -> np.ndarray:
         """Full state in canonical order on every rank (small n only)."""

@@ -305,12 +305,15 @@ class Engine:
             )
         )
 
-    def alltoall_p2p(self, state: DeviceArray, entries):
-        """K7b: ``entries`` = [(peer_ptr, my_offset, peer_offset, begin, end)] in amplitudes (distributed.alltoall_entries)."""
+    def alltoall_p2p(self, state: DeviceArray, entries, push: bool = False):
+        """K7b: ``entries`` = [(buffer pointer, my_offset, its_offset, begin, end)] in amplitudes
+        (distributed.alltoall_entries: in-place chunk swaps; distributed.alltoall_push_entries with ``push``: copies
+        into the destination ranks' second buffers)."""
         k = len(entries)
         ptrs = (ctypes.c_void_p * k)(*[e[0] for e in entries])
         cols = [(ctypes.c_uint64 * k)(*[int(e[c]) for e in entries]) for c in (1, 2, 3, 4)]
-        _lib.check(self.lib.qb_alltoall_p2p(self.handle, state.data_ptr(), _DT[state.dtype], k, ptrs, *cols))
+        fn = self.lib.qb_alltoall_push_p2p if push else self.lib.qb_alltoall_p2p
+        _lib.check(fn(self.handle, state.data_ptr(), _DT[state.dtype], k, ptrs, *cols))
 
     def mem_info(self):
         free, total = ctypes.c_size_t(), ctypes.c_size_t()

@@ -135,7 +135,7 @@ def test_alltoall_entries_equal_sequential_exchanges():
     """A run of exchanges as one all-to-all of chunks (K7b, alltoall_entries) moves every amplitude where the pairwise
     half-shard exchanges would, one after the other -- all ranks simulated in one process."""
     sys.path[:0] = [ROOT, HERE]
-    from qibo_b200.distributed import Segment, alltoall_entries, exchange_runs
+    from qibo_b200.distributed import Segment, alltoall_entries, alltoall_push_entries, exchange_runs
 
     rng = np.random.default_rng(0)
     for g, nlocal, pairs in ((3, 6, [(8, 3), (7, 4), (6, 5)]), (3, 5, [(5, 4), (7, 2), (6, 3)]), (2, 4, [(5, 3), (4, 2)]),
@@ -165,7 +165,17 @@ def test_alltoall_entries_equal_sequential_exchanges():
                 got[r2][b_ + lo : b_ + hi] = x
         for r in range(W):
             np.testing.assert_array_equal(got[r], ref[r])
-    assert alltoall_entries(0, 6, [(8, 3), (7, 5)]) is None  # local bits are not the leading ones: pairwise exchanges
+        # out-of-place form: every chunk is copied into the destination rank's second buffer, each slot written once
+        second = [np.full(1 << nlocal, np.nan) for _ in range(W)]
+        for r in range(W):
+            ent = alltoall_push_entries(r, nlocal, pairs)
+            assert len(ent) == 1 << len(pairs)
+            for r2, a, b_, lo, hi in ent:
+                assert np.isnan(second[r2][b_ + lo : b_ + hi]).all()
+                second[r2][b_ + lo : b_ + hi] = shards[r][a + lo : a + hi]
+        for r in range(W):
+            np.testing.assert_array_equal(second[r], ref[r])
+    assert alltoall_entries(0, 6, [(8, 3), (7, 5)]) is None and alltoall_push_entries(0, 6, [(8, 3), (7, 5)]) is None  # local bits are not the leading ones: pairwise exchanges
     runs = exchange_runs([Segment("exchange", gbit=8, lbit=5), Segment("exchange", gbit=7, lbit=4), Segment("exchange", gbit=8, lbit=3),
                           Segment("local", ops=[]), Segment("exchange", gbit=6, lbit=5)])
     assert [(k, p) for k, p in runs if k == "exchange"] == [("exchange", [(8, 5), (7, 4)]), ("exchange", [(8, 3)]), ("exchange", [(6, 5)])]

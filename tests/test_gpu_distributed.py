@@ -83,6 +83,14 @@ def _worker(rank, world, port, case, n, dtype, out):
         st4 = auto.run(ps2)
         err = max(err, float(np.abs(auto.gather(ps2) - ref).max()))
         assert st4.nexchanges == st3.nexchanges and st4.nexchange_launches <= st3.nexchange_launches
+        # ... and out of place: remote stores into the peers' second buffers, then the shards flip (twice: both buffers)
+        auto.alltoall_push = True
+        ref2 = oracle_run(ref, ops, n)
+        ps2.tensor.copy_(auto.scatter(psi).tensor)
+        auto.run(ps2)
+        err = max(err, float(np.abs(auto.gather(ps2) - ref).max()))
+        auto.run(ps2)
+        err = max(err, float(np.abs(auto.gather(ps2) - ref2).max()))
         zb = auto.basis_state(3)
         auto.run(zb)
         e3 = np.zeros(2**n, dtype=dtype)
