@@ -114,6 +114,16 @@ typedef struct {
 #define QB_PROGRAM_NO_FUSE 2   /* one sweep per gate (gate-by-gate accounting)           */
 int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
                      qb_program_stats* stats /* may be NULL */);
+/* Compiled programs: the same gate queue planned ONCE, its sweep programs kept resident in device memory, and launched
+ * as often as needed without host planning or a program upload -- what repeated execution asks for (one simulation per
+ * shot in Backend.execute_circuit_repeated, abstract.py:2532-2636; re-execution of a circuit, models/circuit.py:1071-1110;
+ * every step of a distributed run).  `qb_program_run` applies it to any state of the nqubits/dtype it was compiled for,
+ * on the stream of `h`; flags: QB_PROGRAM_TIME.  Destroy with the handle it was created on. */
+typedef struct qb_program_s* qb_program;
+int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program* out,
+                      qb_program_stats* stats /* may be NULL */);
+int qb_program_run(qb_handle h, qb_program program, void* state, int flags, qb_program_stats* stats /* may be NULL */);
+int qb_program_destroy(qb_handle h, qb_program program);
 /* host-only: run the sweep planner without touching a device (used by the CPU test-suite) */
 int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program_stats* stats,
                     int32_t* sweep_of_op /* nops entries, may be NULL */);

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "qb_apply_program": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(QbProgramStats)]),
     "qb_expval_pauli": (c_int, [c_void_p, c_void_p, c_int, c_int, c_char_p, POINTER(c_int), c_int, POINTER(c_double)]),
     "qb_state_vdot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_double)]),
+    "qb_program_create": (c_int, [c_void_p, c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(c_void_p), POINTER(QbProgramStats)]),
+    "qb_program_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(QbProgramStats)]),
+    "qb_program_destroy": (c_int, [c_void_p, c_void_p]),
     "qb_plan_program": (c_int, [c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(QbProgramStats), POINTER(c_int32)]),
     "qb_permute_qubits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
     "qb_probabilities": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p]),

@@ -219,27 +219,47 @@ class B200Backend(NumpyBackend):
         """True for gates whose apply() is Gate.apply -> backend.apply_gate (everything but M, callbacks, channels)."""
         return type(gate).apply is Gate.apply
 
-    def _run_queue(self, queue, state, nqubits, density_matrix, substitute_symbols=False):
+    def _run_queue(self, queue, state, nqubits, density_matrix, substitute_symbols=False, program_cache=None):
         """The gate loop of _execute_circuit (abstract.py:3321-3322), with maximal runs of plain gates handed
-        to the sweep planner in one C call."""
+        to the sweep planner in one C call.  ``program_cache`` (a dict owned by the caller, one per circuit and
+        nqubits/dtype): runs of plain gates without symbolic parameters are compiled on first use
+        (qb_program_create) and re-launched afterwards -- execute_circuit_repeated simulates the same queue once per
+        shot (abstract.py:2532-2636)."""
         flat_n = 2 * nqubits if density_matrix else nqubits
-        pending = []
+        pending, gates_of_run = [], []
+        run_start = [0, True]  # index of the run's first gate in the queue, cacheable
 
         def flush(st):
-            if pending:
+            if gates_of_run:
                 flat = st.reshape(-1) if density_matrix else st
-                self.engine_gpu.apply_program(flat, flat_n, pending)
+                key = (run_start[0], len(gates_of_run), flat_n, str(flat.dtype))
+                cacheable = program_cache is not None and run_start[1] and str(flat.dtype) in ("complex64", "complex128")
+                prog = program_cache.get(key) if cacheable else None
+                if prog is None:
+                    for g in gates_of_run:
+                        pending.extend(self._gate_ops(g, nqubits, density_matrix))
+                    if cacheable:
+                        prog = program_cache[key] = self.engine_gpu.compile(flat_n, flat.dtype, pending)
+                if prog is not None:
+                    self.engine_gpu.run_program(prog, flat)
+                else:
+                    self.engine_gpu.apply_program(flat, flat_n, pending)
                 if flat is not st and flat.tensor.data_ptr() != st.tensor.data_ptr():
                     st.tensor = flat.tensor.reshape(st.shape)  # a permutation sweep re-pointed the flat view
                 pending.clear()
+                gates_of_run.clear()
             return st
 
-        for gate in queue:
+        for index, gate in enumerate(queue):
             if substitute_symbols and gate.symbolic_parameters:
                 # abstract.py:2590-2592: evaluated in queue order, i.e. after the collapses they depend on
                 gate.substitute_symbols()
             if self._is_plain(gate):
-                pending.extend(self._gate_ops(gate, nqubits, density_matrix))
+                if not gates_of_run:
+                    run_start[0], run_start[1] = index, True
+                if gate.symbolic_parameters:
+                    run_start[1] = False  # its matrix depends on earlier measurement outcomes: plan afresh
+                gates_of_run.append(gate)
             else:
                 state = flush(state)
                 state = gate.apply(self, state, nqubits)
@@ -331,9 +351,10 @@ class B200Backend(NumpyBackend):
         else:
             state_copy = self._to_device(initial_state)
 
+        program_cache = {}  # the plain-gate runs of the queue, compiled once for all shots
         for _ in range(nshots):
             state = state_copy.copy()
-            state = self._run_queue(circuit.queue, state, nqubits, density_matrix, substitute_symbols=True)
+            state = self._run_queue(circuit.queue, state, nqubits, density_matrix, substitute_symbols=True, program_cache=program_cache)
             if density_matrix:
                 final_states.append(state)
             if circuit.measurements:

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -532,6 +533,102 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
     QB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (stats) stats->elapsed_ms = ms;
   }
+  return QB_OK;
+}
+
+// ---- compiled programs: plan once, keep the sweep programs resident in device memory, launch many times ----------
+struct qb_program_s {
+  int nqubits = 0, dtype = 0, nops = 0, device = 0;
+  Plan plan;                    // sweep descriptors (the blob itself lives in `dev`)
+  std::vector<CanonOp> canon;   // nqubits < 4: the K1 kernels apply the queue gate by gate
+  void* dev = nullptr;
+  qb_program_stats stats;
+};
+
+int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program* out,
+                      qb_program_stats* stats) {
+  if (!h || !out || nqubits < 1 || nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128) || nops < 0 || (nops && !ops))
+    return fail(QB_ERR_INVALID, "bad program arguments");
+  *out = nullptr;
+  std::unique_ptr<qb_program_s> p(new qb_program_s());
+  p->nqubits = nqubits;
+  p->dtype = dtype;
+  p->nops = nops;
+  p->device = h->device;
+  int rc = canonicalize_program(nqubits, ops, nops, p->canon);
+  if (rc != QB_OK) return rc;
+  memset(&p->stats, 0, sizeof(p->stats));
+  p->stats.nops = nops;
+  if (nqubits < 4) {
+    p->stats.nsweeps = nops;
+    p->stats.bytes_moved = (double)nops * 2.0 * (dtype == QB_C128 ? 16.0 : 8.0) * (double)(uint64_t(1) << nqubits);
+  } else {
+    std::string err;
+    if (!plan_program(nqubits, dtype, p->canon, (flags & QB_PROGRAM_NO_FUSE) != 0, p->plan, err)) return fail(QB_ERR_UNSUPPORTED, err);
+    fill_stats(p->plan, nqubits, dtype, nops, &p->stats);
+    p->canon.clear();
+    if (!p->plan.blob.empty()) {
+      std::lock_guard<std::mutex> lk(h->mu);
+      DeviceGuard guard(h->device);
+      QB_CUDA(cudaMalloc(&p->dev, p->plan.blob.size()));
+      cudaError_t e = cudaMemcpyAsync(p->dev, p->plan.blob.data(), p->plan.blob.size(), cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // the host blob is released below
+      if (e != cudaSuccess) {
+        cudaFree(p->dev);
+        return cuda_fail(e, "program upload");
+      }
+      std::vector<char>().swap(p->plan.blob);
+    }
+  }
+  if (stats) *stats = p->stats;
+  *out = p.release();
+  return QB_OK;
+}
+
+int qb_program_run(qb_handle h, qb_program p, void* state, int flags, qb_program_stats* stats) {
+  if (!h || !p || !valid_state_args(state, p->nqubits, p->dtype)) return fail(QB_ERR_INVALID, "bad program arguments");
+  if (p->device != h->device) return fail(QB_ERR_INVALID, "the program was compiled for another device");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  if (stats) *stats = p->stats;
+  if (flags & QB_PROGRAM_TIME) QB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  if (p->nqubits < 4) {
+    for (auto& c : p->canon) {
+      int rc = p->dtype == QB_C128 ? apply_canon_k1<double2>(h, state, p->nqubits, c) : apply_canon_k1<float2>(h, state, p->nqubits, c);
+      if (rc != QB_OK) return rc;
+    }
+  } else {
+    for (size_t s = 0; s < p->plan.sweeps.size(); ++s) {
+      int rc = launch_sweep(h->stream, h->sm_count, state, p->nqubits, p->dtype, p->plan.sweeps[s], (const char*)p->dev);
+      if (rc != QB_OK) {
+        const std::string what = cudaGetErrorString(cudaGetLastError());
+        return fail(rc, "sweep launch failed: " + what + " [" + sweep_resources(p->dtype) + "]");
+      }
+    }
+  }
+  if (flags & QB_PROGRAM_TIME) {
+    QB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    QB_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (stats) stats->elapsed_ms = ms;
+  }
+  return QB_OK;
+}
+
+int qb_program_destroy(qb_handle h, qb_program p) {
+  if (!p) return QB_OK;
+  if (p->dev) {
+    if (h) {
+      std::lock_guard<std::mutex> lk(h->mu);
+      DeviceGuard guard(h->device);
+      cudaStreamSynchronize(h->stream);  // a launch may still be reading the program
+      cudaFree(p->dev);
+    } else {
+      cudaFree(p->dev);
+    }
+  }
+  delete p;
   return QB_OK;
 }
 

@@ -481,6 +481,7 @@ class ShardedProgram:
         # out-of-place all-to-all (remote stores only, then flip buffers): 676 vs 653 GB/s per direction on 2 GPUs
         self.alltoall_push = os.environ.get("QB_ALLTOALL_PUSH", "1") not in ("", "0")
         self._apply = apply  # test hook: NumPy shard executor
+        self._programs = {}  # id(segment) -> engine.CompiledProgram
         self._staging = None
         self._staging_elems = staging_elems
         self.ngates = len(ops)
@@ -550,8 +551,10 @@ class ShardedProgram:
             self._staging = [torch.empty(n, dtype=tensor.dtype, device=tensor.device) for _ in range(2)]
         return self._staging
 
-    def run(self, state, timed: bool = True):
-        """Apply the program to this rank's shard (DeviceArray, or a torch tensor with the test hook)."""
+    def run(self, state, timed: bool = True, compiled: bool = True):
+        """Apply the program to this rank's shard (DeviceArray, or a torch tensor with the test hook).  ``compiled``: the
+        local segments run as device-resident compiled programs (planned on first use); False sends the host gate
+        matrices through qb_apply_program on every call."""
         peer = state if isinstance(state, PeerShard) else None
         if peer is not None:
             state = peer.array
@@ -564,7 +567,11 @@ class ShardedProgram:
                 if self._apply is not None:
                     self._apply(tensor, self.nlocal, seg[1])
                 else:
-                    st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed, alt=peer.alt if peer is not None else None)
+                    alt = peer.alt if peer is not None else None
+                    if compiled:
+                        st = self.engine.run_program(self._compiled(seg), state, timed=timed, alt=alt)
+                    else:
+                        st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed, alt=alt)
                     out.nsweeps += st.nsweeps
                     out.elapsed_ms += st.elapsed_ms
                     out.perm_ms += getattr(st, "perm_ms", 0.0)
@@ -582,6 +589,15 @@ class ShardedProgram:
                     t1.synchronize()
                     out.exchange_ms += t0.elapsed_time(t1)
         return out
+
+    def _compiled(self, seg):
+        """The local segment compiled for this rank's engine, on first use (qb_program_create): later runs of the plan
+        launch kernels only."""
+        key = id(seg)
+        prog = self._programs.get(key)
+        if prog is None:
+            prog = self._programs[key] = self.engine.compile(self.nlocal, self.dtype, seg[1])
+        return prog
 
     def _exchange_run(self, state, peer, tensor, pairs, out):
         """One run of exchanges [(gbit, lbit), ...] on pairwise distinct bits."""

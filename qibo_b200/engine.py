@@ -207,6 +207,47 @@ class Engine:
     def plan(self, nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
         return plan_program(nqubits, dtype, ops, fuse)
 
+    # ---- compiled programs: plan once, launch many times ------------------------------------------------
+    def compile(self, nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True) -> "CompiledProgram":
+        """The queue ``apply_program`` would run, planned once and kept resident on the device (qb_program_create):
+        ``run_program`` then costs kernel launches only -- no canonicalisation, planning or program upload per call."""
+        return CompiledProgram(self, nqubits, dtype, ops, fuse)
+
+    def run_program(self, prog: "CompiledProgram", state: DeviceArray, timed: bool = False, alt: Optional[DeviceArray] = None):
+        """Apply a compiled program to ``state`` (same nqubits / dtype / device as it was compiled for)."""
+        if np.dtype(state.dtype) != prog.dtype or state.size != (1 << prog.nqubits):
+            raise ValueError(f"program compiled for {prog.nqubits} qubits of {prog.dtype}, got a state of {state.size} x {state.dtype}")
+        total = _lib.QbProgramStats()
+        total.nops = prog.nops
+        total.perm_ms, total.nperm = 0.0, 0
+        flags = _lib.QB_PROGRAM_TIME if timed else 0
+        for kind, payload in prog.segments:
+            if kind == "perm":
+                try:
+                    ms = self.permute_qubits(state, prog.nqubits, payload, timed=timed, alt=alt)
+                except torch.cuda.OutOfMemoryError:  # no room for the scratch buffer: in place, as SWAP gates
+                    st = self._apply_sweeps(state, prog.nqubits, swaps_for_permutation(payload), True, timed)
+                    total.nsweeps += st.nsweeps
+                    total.bytes_moved += st.bytes_moved
+                    total.elapsed_ms += st.elapsed_ms
+                    continue
+                total.nsweeps += 1
+                total.ndense_passes += 1
+                total.bytes_moved += 2.0 * state.nbytes
+                total.elapsed_ms += ms or 0.0
+                total.perm_ms += ms or 0.0
+                total.nperm += 1
+                continue
+            st = _lib.QbProgramStats()
+            _lib.check(self.lib.qb_program_run(self.handle, payload, state.data_ptr(), flags, ctypes.byref(st)))
+            total.nsweeps += st.nsweeps
+            total.ndense_passes += st.ndense_passes
+            total.ndiag_ops += st.ndiag_ops
+            total.bytes_moved += st.bytes_moved
+            total.elapsed_ms += st.elapsed_ms
+        self.last_stats = total
+        return total
+
     # ---- K3: probabilities --------------------------------------------------------------------------
     def probabilities(self, state: DeviceArray, qubits: Sequence[int], nqubits: int) -> DeviceArray:
         rdtype = np.dtype("float64") if state.dtype == np.dtype("complex128") else np.dtype("float32")
@@ -332,6 +373,48 @@ class _RawCuda:
         try:
             if self.engine.handle:
                 self.engine.lib.qb_free(self.engine.handle, ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+class CompiledProgram:
+    """Segments of a gate queue compiled for one Engine: ("prog", qb_program handle) for runs of gates, ("perm", dest) for
+    runs of plain SWAPs (K8).  Frees its device programs with the object."""
+
+    def __init__(self, engine: "Engine", nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
+        self.engine, self.nqubits, self.dtype, self.nops = engine, nqubits, np.dtype(dtype), len(ops)
+        self.segments = []
+        self.nsweeps = 0
+        segments = split_swap_runs(ops, nqubits) if fuse and engine.permute_swap_runs else [("ops", list(ops))]
+        flags = 0 if fuse else _lib.QB_PROGRAM_NO_FUSE
+        try:
+            for kind, payload in segments:
+                if kind == "perm":
+                    self.segments.append(("perm", list(payload)))
+                    self.nsweeps += 1
+                    continue
+                if not payload:
+                    continue
+                arr, keep = pack_ops(payload)
+                handle, st = ctypes.c_void_p(), _lib.QbProgramStats()
+                _lib.check(engine.lib.qb_program_create(engine.handle, nqubits, _DT[self.dtype], arr, len(payload), flags,
+                                                        ctypes.byref(handle), ctypes.byref(st)))
+                del keep
+                self.segments.append(("prog", handle))
+                self.nsweeps += st.nsweeps
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        for kind, payload in self.segments:
+            if kind == "prog" and payload and getattr(self.engine, "handle", None):
+                self.engine.lib.qb_program_destroy(self.engine.handle, payload)
+        self.segments = []
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

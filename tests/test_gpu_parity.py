@@ -227,6 +227,33 @@ def test_rank_specialised_segments_at_scale(eng, n, world, rank, dtype):
     assert nseg >= 4
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [2, 3, 9, 16, 21])
+def test_compiled_program_equals_apply_program(eng, n, dtype):
+    """qb_program_create / qb_program_run: the same queue planned once and launched repeatedly gives bit-identical
+    amplitudes to qb_apply_program on every launch, on different states, and next to other programs."""
+    from helpers import random_zoo
+    from qibo_b200 import circuits
+
+    for ops in (circuits.qft(n),) + ((random_zoo(n, 30, seed=n),) if n >= 9 else ()):
+        prog = eng.compile(n, dtype, ops)
+        other = eng.compile(n, dtype, list(reversed(ops)))
+        for seed in (1, 2):
+            psi = rand_state(n, seed, dtype)
+            a, b = eng.upload(psi), eng.upload(psi)
+            s1 = eng.apply_program(a, n, ops)
+            s2 = eng.run_program(prog, b, timed=True)
+            assert np.array_equal(a.numpy(), b.numpy())
+            assert s2.nsweeps == s1.nsweeps == prog.nsweeps and s2.nops == len(ops)
+            eng.run_program(other, b)
+            eng.apply_program(a, n, list(reversed(ops)))
+            assert np.array_equal(a.numpy(), b.numpy())
+        prog.close()
+        other.close()
+    with pytest.raises(ValueError):
+        eng.run_program(eng.compile(n, dtype, circuits.qft(n)), eng.upload(rand_state(n + 1, 0, dtype)))
+
+
 # ------------------------------------------------------------------------------------------ P1
 def test_probabilities_golden(eng, golden):
     for i, c in enumerate(golden.cases("prob_cases")):
