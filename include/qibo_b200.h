@@ -107,7 +107,7 @@ typedef struct {
   int32_t ndiag_ops;       /* diagonal bundles applied                           */
   double bytes_moved;      /* algorithmic bytes: sum over sweeps of 2*B*2^n      */
   float elapsed_ms;        /* CUDA-event time of the whole program (flags & QB_PROGRAM_TIME) */
-  float reserved;
+  int32_t nstage_sweeps;   /* of nsweeps: sweeps made of straight-line stage passes only (the lean two-team kernel) */
 } qb_program_stats;
 
 #define QB_PROGRAM_TIME 1      /* bracket with CUDA events, synchronise, fill elapsed_ms */

@@ -39,7 +39,7 @@ class QbProgramStats(ctypes.Structure):
         ("ndiag_ops", c_int32),
         ("bytes_moved", c_double),
         ("elapsed_ms", c_float),
-        ("reserved", c_float),
+        ("nstage_sweeps", c_int32),
     ]
 
 

@@ -1232,6 +1232,7 @@ inline void fill_stats(const Plan& plan, int n, int dtype, int nops, qb_program_
   st->ndense_passes = plan.npasses;
   st->ndiag_ops = plan.ndiag;
   st->bytes_moved = (double)plan.sweeps.size() * 2.0 * (dtype == QB_C128 ? 16.0 : 8.0) * (double)(uint64_t(1) << n);
+  for (auto& sd : plan.sweeps) st->nstage_sweeps += sd.stage_only ? 1 : 0;
 }
 
 }  // namespace qb

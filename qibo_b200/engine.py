@@ -199,6 +199,7 @@ class Engine:
             total.nsweeps += st.nsweeps
             total.ndense_passes += st.ndense_passes
             total.ndiag_ops += st.ndiag_ops
+            total.nstage_sweeps += st.nstage_sweeps
             total.bytes_moved += st.bytes_moved
             total.elapsed_ms += st.elapsed_ms
         self.last_stats = total
@@ -243,6 +244,7 @@ class Engine:
             total.nsweeps += st.nsweeps
             total.ndense_passes += st.ndense_passes
             total.ndiag_ops += st.ndiag_ops
+            total.nstage_sweeps += st.nstage_sweeps
             total.bytes_moved += st.bytes_moved
             total.elapsed_ms += st.elapsed_ms
         self.last_stats = total

@@ -15,7 +15,10 @@ using namespace qb;
 
 constexpr uint32_t EMUL_THREADS = 256;  // the kernel's compute-thread count: same group -> thread mapping
 
-template <typename C>
+// SO: the sweep would be launched on the stage-only kernel instantiation (sweep_kernel<C, true>): REGTILE passes run
+// through run_pass<..., true>, which has no handler switch, and other pass kinds are not executed at all -- so a sweep
+// the planner flags stage_only by mistake gives a wrong state here, as it would on the GPU.
+template <typename C, bool SO>
 static void run_sweep(C* state, const char* blob) {
   const SweepHeader& hdr = *reinterpret_cast<const SweepHeader*>(blob);
   const int T = (int)hdr.T, L = (int)hdr.L;
@@ -44,17 +47,17 @@ static void run_sweep(C* state, const char* blob) {
     auto regtile = [&](const PassHeader& ph, uint32_t ctid) {
       if (GPT == 1) {
         switch (ph.R) {
-          case 1: run_pass<C, 1, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 2: run_pass<C, 2, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 3: run_pass<C, 3, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          default: run_pass<C, 4, 1>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 1: run_pass<C, 1, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 2: run_pass<C, 2, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 3: run_pass<C, 3, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          default: run_pass<C, 4, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
         }
       } else {
         switch (ph.R) {
-          case 1: run_pass<C, 1, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 2: run_pass<C, 2, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 3: run_pass<C, 3, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          default: run_pass<C, 4, 2>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 1: run_pass<C, 1, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 2: run_pass<C, 2, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 3: run_pass<C, 3, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          default: run_pass<C, 4, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
         }
       }
     };
@@ -69,7 +72,7 @@ static void run_sweep(C* state, const char* blob) {
       const PassHeader& ph = passes[pi];
       if (ph.kind == PASS_REGTILE) {
         for (uint32_t ctid = 0; ctid < EMUL_THREADS; ++ctid) regtile(ph, ctid);
-      } else {
+      } else if (!SO) {
         const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
         if (op.slot != MU_NO_SLOT && !ts[op.slot].active) continue;
         const C* payload = reinterpret_cast<const C*>(blob + op.payload);  // the emulator keeps the whole blob in one buffer
@@ -105,8 +108,9 @@ extern "C" int emul_apply_program(void* state, int nqubits, int dtype, const qb_
   if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
   for (auto& sd : plan.sweeps) {
     char* blob = plan.blob.data() + sd.blob_offset;
-    if (dtype == QB_C128) run_sweep<double2>((double2*)state, blob);
-    else run_sweep<float2>((float2*)state, blob);
+    const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);  // as launch_sweep decides
+    if (dtype == QB_C128) so ? run_sweep<double2, true>((double2*)state, blob) : run_sweep<double2, false>((double2*)state, blob);
+    else so ? run_sweep<float2, true>((float2*)state, blob) : run_sweep<float2, false>((float2*)state, blob);
   }
   return QB_OK;
 }

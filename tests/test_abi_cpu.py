@@ -81,6 +81,12 @@ def test_planner_packs_qft_into_few_sweeps():
         assert stats.bytes_moved == stats.nsweeps * 2 * itemsize * 2.0**n
         stats1, _ = plan_program(n, dtype, ops, fuse=False)
         assert stats1.nsweeps == len(ops)
+    # the QFT stages without the closing SWAPs (the engine turns those into one K8 permutation): 4 sweeps at 32 qubits,
+    # every one a straight-line stage sweep -- what the lean two-team kernel instantiation runs
+    stats, _ = plan_program(32, "complex128", circuits.qft(32, with_swaps=False))
+    assert stats.nsweeps == 4 and stats.nstage_sweeps == 4
+    stats, _ = plan_program(30, "complex128", circuits.qft(30, with_swaps=False))
+    assert stats.nsweeps == 4 and stats.nstage_sweeps == 4
 
 
 def test_planner_follows_light_cones():

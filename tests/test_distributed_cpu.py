@@ -115,6 +115,21 @@ def test_cyclic_layout_qft_plan():
         assert plan.nexchanges == g and plan.global_qubits in (cyclic_layout(n, g), cyclic_layout(n, g)[::-1])
         kinds = [s.kind for s in plan.segments]
         assert kinds == ["local"] + ["exchange"] * g + ["local"]
+    # at the bench size every rank runs stages 0..31 as the same four stage-only sweeps (the phases of global control
+    # qubits that are 1 on a rank fold into the fans instead of staying separate ops)
+    from qibo_b200.engine import plan_program, split_swap_runs
+
+    n, g = 35, 3
+    plan = choose_layout(n, g, circuits.qft(n))
+    for r in (0, 3, 5, 7):
+        local = [o for o in (specialise(p, n - g, r) for p in plan.segments[0].ops) if o is not None]
+        stats, _ = plan_program(n - g, "complex128", local)
+        assert stats.nsweeps == 4 and stats.nstage_sweeps == 4, (r, stats.nsweeps, stats.nstage_sweeps)
+        tail = [o for o in (specialise(p, n - g, r) for p in plan.segments[-1].ops) if o is not None]
+        kinds = [k for k, _ in split_swap_runs(tail, n - g)]
+        assert kinds == ["ops", "perm"]
+        stats, _ = plan_program(n - g, "complex128", split_swap_runs(tail, n - g)[0][1])
+        assert stats.nsweeps == 1
     n, g = 17, 3
     nl = n - g
     plan = Plan(n, g, circuits.qft(n), global_qubits=cyclic_layout(n, g))
