@@ -4,16 +4,22 @@ Re-implements the scheme of ``qibo.models.distcircuit`` (DistributedQubits / Dis
 models/distcircuit.py:9-329) for an executor the reference never shipped
 (``Backend.execute_distributed_circuit`` raises NotImplementedError, backends/abstract.py:2638-2647).
 
-Layout.  W = 2^g ranks; rank r holds the 2^(n-g) amplitudes whose g most significant *physical* bits equal r
-(piece layout ``sorted(global) + local``, distcircuit.py:33-36).  Instead of relabelling the caller's gate
-objects in place (distcircuit.py:236-244) the planner keeps a logical-qubit -> physical-bit map:
+Layout.  W = 2^g ranks; g logical qubits are GLOBAL -- their values spell the rank -- and the other qubits index the
+shard in ascending order (piece layout ``sorted(global) + local``, distcircuit.py:33-36).  Which qubits are global is
+the planner's choice, as in the reference (DistributedQubits, distcircuit.py:287-298): the leading ones (block layout,
+the default), the trailing ones (cyclic layout, what ``_DistributedQFT`` asks for, models/qft.py:66), any set, or
+"auto" = whichever needs the fewest exchanges.  Instead of relabelling the caller's gate objects in place
+(distcircuit.py:236-244) the planner keeps a logical-qubit -> physical-bit map:
 
   * a gate needs a qubit LOCAL only if its matrix mixes that qubit's 0/1 subspaces; control qubits and every
     qubit of a diagonal gate may stay global -- on each rank the gate is specialised to the rank's bit values
     (the reference does the same for global controls, distcircuit.py:316-327);
   * when a mixing target sits on a global bit it is exchanged with a high local bit whose qubit is needed
-    furthest in the future (pairwise half-shard exchange, contiguous chunks of >= 2^20 amplitudes);
-  * uncontrolled SWAP gates are applied as relabelling; the map is made canonical again at the end
+    furthest in the future and, among equals, belongs on that global bit at the end; once a segment is cut, the
+    other global qubits with mixing gates ahead come in too while finished qubits can leave for them, so exchanges
+    sit back to back (pairwise half-shard exchange, contiguous chunks of >= 2^20 amplitudes; a run of them on the
+    leading local bits is ONE all-to-all kernel over NVLink peer memory);
+  * uncontrolled SWAP gates are applied as relabelling; the layout is restored at the end
     (the reference appends reverse swaps for the same purpose, distcircuit.py:267).
 
 The local gate runs go through the same sweep kernels as the single-GPU path (``Engine.apply_program``).
