@@ -203,7 +203,8 @@ def verify_sharded_qft(runner, state, args, eng, dist):
     def path():
         if not runner.alltoall:
             return "pairwise"
-        return "alltoall-push" if runner.alltoall_push else "alltoall-swap"
+        fused = "+perm" if (runner.fuse_perm and runner.alltoall_push) else ""  # experimental QB_A2A_FUSE_PERM=1
+        return ("alltoall-push" if runner.alltoall_push else "alltoall-swap") + fused
 
     for _ in range(3):  # all-to-all out of place -> all-to-all in place -> pairwise exchanges
         attempt = path()
@@ -225,6 +226,8 @@ def verify_sharded_qft(runner, state, args, eng, dist):
         if out["max_rel_err"] < tol or attempt == "pairwise":
             break
         # every rank sees the same all-reduced error, so they switch together
+        if runner.fuse_perm:
+            raise AssertionError(f"QB_A2A_FUSE_PERM=1 (experimental) fails the closed-form check: {out}")
         if runner.alltoall_push:
             runner.alltoall_push = False
         else:

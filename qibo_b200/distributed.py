@@ -86,6 +86,35 @@ def exchange_runs(segments):
     return out
 
 
+def split_trailing_permutation(phys_ops, nlocal: int, k: int, min_swaps: int = 3):
+    """EXPERIMENTAL (opt-in, QB_A2A_FUSE_PERM=1; not measured yet -- DESIGN.md section 8, step 1).  For the local segment
+    that follows a run of k exchanges on the k leading local bits: if it is `gates G` + a closing run of plain SWAPs, the
+    SWAPs only move bits BELOW the k leading local bits and G only touches those k bits (or global ones), then permutation
+    and G commute and the permutation can ride on the all-to-all (every chunk is written permuted).
+    -> (G as PhysOps, dest_of_qubit over the nlocal - k lower local qubits) or None.  Decided on the PLAN's ops, not on a
+    rank's specialised ones, so that every rank takes the same decision."""
+    lo = nlocal - k
+    nswaps = 0
+    for p in reversed(phys_ops):
+        if p.is_diagonal or p.cbits or len(p.tbits) != 2 or not np.array_equal(p.data, _SWAP):
+            break
+        nswaps += 1
+    if nswaps < min_swaps:
+        return None
+    gates, swaps = list(phys_ops[: len(phys_ops) - nswaps]), phys_ops[len(phys_ops) - nswaps :]
+    if any(b < lo for p in gates for b in tuple(p.tbits) + tuple(p.cbits)):
+        return None
+    if any(b >= lo for p in swaps for b in p.tbits):
+        return None
+    dest = list(range(lo))  # sub-qubit s of a chunk <-> bit lo - 1 - s
+    for p in swaps:
+        a, b = lo - 1 - p.tbits[0], lo - 1 - p.tbits[1]
+        dest = [b if d == a else a if d == b else d for d in dest]
+    if dest == list(range(lo)):
+        return None
+    return gates, dest
+
+
 def alltoall_entries(rank_: int, nlocal: int, pairs):
     """The chunk swaps of rank ``rank_`` for a run of exchanges whose local bits are the k leading ones: chunk t (the k
     leading bits of the shard index) trades places with chunk t' of rank r', where every (gbit, lbit) pair swaps one bit
@@ -474,13 +503,23 @@ class ShardedProgram:
         else:
             self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps, global_qubits=global_qubits)
         self.global_qubits, self.local_qubits = self.plan.global_qubits, self.plan.local_qubits
+        self.fuse_perm = os.environ.get("QB_A2A_FUSE_PERM", "0") not in ("", "0")  # experimental, see split_trailing_permutation
         self.segments = []
-        for kind, payload in exchange_runs(self.plan.segments):
+        runs = exchange_runs(self.plan.segments)
+        for i, (kind, payload) in enumerate(runs):
             if kind == "local":
+                prev = self.segments[-1] if self.segments else None
+                if prev is not None and prev[0] == "exchange" and prev[2] is not None:
+                    payload = prev[3]  # its closing permutation rides on the exchange before it
                 local = [o for o in (specialise(p, self.nlocal, self.rank) for p in payload) if o is not None]
                 self.segments.append(("local", local))
             else:
-                self.segments.append(("exchange", list(payload)))
+                pairs, sub_dest, gates = list(payload), None, None
+                if self.fuse_perm and i + 1 < len(runs) and runs[i + 1][0] == "local" and alltoall_push_entries(0, self.nlocal, pairs):
+                    split = split_trailing_permutation(runs[i + 1][1], self.nlocal, len(pairs))
+                    if split is not None:
+                        gates, sub_dest = split
+                self.segments.append(("exchange", pairs, sub_dest, gates))
         # runs of >= alltoall_min exchanges go through the all-to-all kernel (peer-memory shards only)
         self.alltoall = os.environ.get("QB_NO_ALLTOALL", "") in ("", "0")
         self.alltoall_min = int(os.environ.get("QB_ALLTOALL_MIN", "1"))
@@ -588,7 +627,7 @@ class ShardedProgram:
                 if tensor.is_cuda and timed:
                     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     t0.record()
-                self._exchange_run(state, peer, tensor, pairs, out)
+                self._exchange_run(state, peer, tensor, pairs, out, sub_dest=seg[2], timed=timed, compiled=compiled)
                 out.nexchanges += len(pairs)
                 if t0 is not None:
                     t1.record()
@@ -605,10 +644,42 @@ class ShardedProgram:
             prog = self._programs[key] = self.engine.compile(self.nlocal, self.dtype, seg[1])
         return prog
 
-    def _exchange_run(self, state, peer, tensor, pairs, out):
-        """One run of exchanges [(gbit, lbit), ...] on pairwise distinct bits."""
+    def _exchange_run(self, state, peer, tensor, pairs, out, sub_dest=None, timed=False, compiled=True):
+        """One run of exchanges [(gbit, lbit), ...] on pairwise distinct bits.  ``sub_dest`` (experimental): a permutation
+        of the lower local qubits that the plan moved in front of the gates after the exchange -- written by the
+        all-to-all itself when it runs out of place, else applied right after the exchange."""
         use_a2a = peer is not None and self.alltoall and len(pairs) >= self.alltoall_min
         elem = tensor.element_size()
+        if sub_dest is not None:
+            k = len(pairs)
+            entries = alltoall_push_entries(self.rank, self.nlocal, pairs) if (use_a2a and self.alltoall_push and k <= 3) else None
+            if entries is not None:
+                # one K8 launch per chunk, straight into the destination rank's second buffer; peers in order of r ^ r'
+                # so that every rank receives from one sender at a time
+                dst, src0, lo = peer.alt_ptrs, state.data_ptr(), self.nlocal - k
+                peer.fence()
+                for r2, a, b, _, _ in sorted(entries, key=lambda e: e[0] ^ self.rank):
+                    self.engine.permute_raw(src0 + a * elem, dst[r2] + b * elem, lo, self.dtype, sub_dest)
+                peer.fence()
+                peer.flip()
+                out.exchange_bytes += 2 * elem * sum(hi - lo_ for r2, _, _, lo_, hi in entries if r2 != self.rank)
+                out.nexchange_launches += len(entries)
+                return
+            # other transports: exchange as usual, then the permutation as a local segment of its own
+            self._exchange_run(state, peer, tensor, pairs, out)
+            full = list(range(k)) + [k + d for d in sub_dest]
+            from qibo_b200.engine import swaps_for_permutation
+
+            swaps = swaps_for_permutation(full)
+            if self._apply is not None:
+                self._apply(state.tensor if hasattr(state, "tensor") else state, self.nlocal, swaps)
+            else:
+                st = self.engine.apply_program(state, self.nlocal, swaps, timed=timed, alt=peer.alt if peer is not None else None)
+                out.nsweeps += st.nsweeps
+                out.elapsed_ms += st.elapsed_ms
+                out.perm_ms += getattr(st, "perm_ms", 0.0)
+                out.nperm += getattr(st, "nperm", 0)
+            return
         if use_a2a and self.alltoall_push and len(pairs) <= 3:
             entries = alltoall_push_entries(self.rank, self.nlocal, pairs)
             if entries is not None:

@@ -170,6 +170,14 @@ class Engine:
             return e0.elapsed_time(e1)
         return None
 
+    def permute_raw(self, src_ptr: int, dst_ptr: int, nqubits: int, dtype, dest_of_qubit: Sequence[int]):
+        """K8 on raw device pointers (a chunk of a shard as source, possibly a peer-mapped buffer as destination)."""
+        _lib.check(
+            self.lib.qb_permute_qubits(
+                self.handle, ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr), nqubits, _DT[np.dtype(dtype)], _int_array(dest_of_qubit)
+            )
+        )
+
     def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False,
                       alt: Optional[DeviceArray] = None):
         """Apply ``ops`` in order, several gates per HBM sweep.  Runs of >= MIN_SWAP_RUN uncontrolled SWAP gates (the

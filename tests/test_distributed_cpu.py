@@ -196,6 +196,60 @@ def test_alltoall_entries_equal_sequential_exchanges():
     assert [(k, p) for k, p in runs if k == "exchange"] == [("exchange", [(8, 5), (7, 4)]), ("exchange", [(8, 3)]), ("exchange", [(6, 5)])]
 
 
+def test_fused_exchange_permutation_equivalence(monkeypatch):
+    """EXPERIMENTAL path (QB_A2A_FUSE_PERM=1): the closing permutation of the segment after a run of exchanges, written
+    by the all-to-all itself (one K8 per chunk into the destination rank's second buffer) -- all ranks simulated in one
+    process with the product's K8 index math (tests/emul), against exchanges -> gates -> permutation in sequence."""
+    sys.path[:0] = [ROOT, HERE]
+    import emul
+    from helpers import oracle_run, rand_state
+    from qibo_b200 import circuits
+    from qibo_b200.distributed import (alltoall_push_entries, choose_layout, exchange_runs, specialise,
+                                       split_trailing_permutation)
+    from qibo_b200.engine import split_swap_runs
+
+    for n, g in ((13, 2), (14, 3), (12, 1)):
+        W, nl = 1 << g, n - g
+        plan = choose_layout(n, g, circuits.qft(n))
+        runs = exchange_runs(plan.segments)
+        assert [k for k, _ in runs] == ["local", "exchange", "local"]
+        pairs, tail = runs[1][1], runs[2][1]
+        split = split_trailing_permutation(tail, nl, len(pairs))
+        assert split is not None
+        gates, sub_dest = split
+        k, lo = len(pairs), nl - len(pairs)
+        shards = [rand_state(nl, 40 + r) for r in range(W)]
+        # reference: pairwise exchanges in sequence, then the whole tail segment (gates + SWAPs) on every rank
+        ref = [x.copy() for x in shards]
+        for gbit, lbit in pairs:
+            j = gbit - nl
+            new = [x.copy() for x in ref]
+            idx = np.arange(1 << nl)
+            for r in range(W):
+                b = (r >> j) & 1
+                mine = idx[((idx >> lbit) & 1) == 1 - b]
+                new[r][mine] = ref[r ^ (1 << j)][mine ^ (1 << lbit)]
+            ref = new
+        for r in range(W):
+            local = [o for o in (specialise(p, nl, r) for p in tail) if o is not None]
+            ref[r] = oracle_run(ref[r], local, nl)
+        # fused: every chunk lands permuted in the destination's second buffer, then only the gates run
+        second = [np.zeros(1 << nl, dtype=complex) for _ in range(W)]
+        csz = 1 << lo
+        for r in range(W):
+            for r2, a, b_, _, _ in alltoall_push_entries(r, nl, pairs):
+                second[r2][b_ : b_ + csz] = emul.permute_qubits(shards[r][a : a + csz], lo, sub_dest)
+        for r in range(W):
+            local = [o for o in (specialise(p, nl, r) for p in gates) if o is not None]
+            got = oracle_run(second[r], local, nl) if local else second[r]
+            assert np.abs(got - ref[r]).max() < 1e-12, (n, g, r)
+    # the same plan through ShardedProgram on gloo: no peer memory there, so the permutation runs right after the exchange
+    monkeypatch.setenv("QB_A2A_FUSE_PERM", "1")
+    for world in (2, 4):
+        err, nex, planned = _run(world, "qft", 9, seed=6, layout="auto")
+        assert err < 1e-12 and nex == planned == world.bit_length() - 1
+
+
 def test_plan_properties():
     """Device-free planner checks in the spirit of tests/test_models_distcircuit.py:95-103: no mixing target is
     ever on a global bit inside a local segment, and the layout is canonical at the end."""
