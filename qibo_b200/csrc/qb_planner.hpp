@@ -246,11 +246,12 @@ inline void merge_ops(const std::vector<CanonOp>& ops, bool no_fuse, std::vector
           if (it == f.fan.end()) f.fan[b] = entry;
           else it->second.second *= entry.second;
           merged = true;
-        } else if (f.fan.size() == 1 && f.fan.begin()->second.first == cd(1.0, 0.0)) {
-          // re-root a single-entry fan so that the shared bits become the controls
+        } else if (f.fan.size() == 1 && f.fan.begin()->second.first == cd(1.0, 0.0) && f.scalar == cd(1.0, 0.0)) {
+          // re-root a single-entry fan so that the shared bits become the controls (a pure phase on its bit set: only
+          // then is it symmetric in its bits -- a scalar on the control slice breaks that)
           std::vector<int> P0 = fan_set(f), common;
           std::set_intersection(P.begin(), P.end(), P0.begin(), P0.end(), std::back_inserter(common));
-          if (!P.empty() && P.size() + 1 == P0.size() && common.size() == P.size() && f.scalar == cd(1.0, 0.0)) {
+          if (!P.empty() && P.size() + 1 == P0.size() && common.size() == P.size()) {
             // P is the fan's set minus one bit b0: control on P, and b0 selects between the new phase alone and the
             // product (the tail of a QFT on a rank whose global control qubits are 1)
             cd ph0 = f.fan.begin()->second.second;
@@ -522,7 +523,8 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     // and the pass stays a straight-line stage pass.  (A pure phase is symmetric in its qubits.)
     PlanOp rerooted;
     bool force_fan = false;
-    if (pp->kind == CK_PHASE && pp->fan.size() == 1 && pp->fan.begin()->second.first == cd(1.0, 0.0) && pp->cpos.size() == 1 && prev_op &&
+    if (pp->kind == CK_PHASE && pp->fan.size() == 1 && pp->fan.begin()->second.first == cd(1.0, 0.0) && pp->scalar == cd(1.0, 0.0) &&
+        pp->cpos.size() == 1 && prev_op &&
         prev_op->kind == CK_DENSE && prev_op->tpos.size() == 1 && prev_op->cpos.empty()) {
       const int d = prev_op->tpos[0], a = pp->cpos[0], b = pp->fan.begin()->first;
       if (d == a || d == b) {
@@ -541,7 +543,8 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     }
     // A lone phase on the qubit of the one-qubit gate right before it (H(q) U1(q): the last stage of a QFT on a rank whose
     // global control qubits are 1) becomes a fan without factors controlled by that qubit, for the same reason.
-    if (!force_fan && pp->kind == CK_PHASE && pp->fan.size() == 1 && pp->fan.begin()->second.first == cd(1.0, 0.0) && pp->cpos.empty() &&
+    if (!force_fan && pp->kind == CK_PHASE && pp->fan.size() == 1 && pp->fan.begin()->second.first == cd(1.0, 0.0) &&
+        pp->scalar == cd(1.0, 0.0) && pp->cpos.empty() &&
         prev_op && prev_op->kind == CK_DENSE && prev_op->tpos.size() == 1 && prev_op->cpos.empty() &&
         prev_op->tpos[0] == pp->fan.begin()->first && ((sb.tile_mask >> prev_op->tpos[0]) & 1) &&
         rbit_of_local[sb.local_of_pos[prev_op->tpos[0]]] >= 0) {
@@ -608,14 +611,16 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
         else m.tbit[i] = (uint8_t)sb.local_of_pos[pos];
       }
       for (auto& v : p.data) payload.push_back(to_dev<C>(v));
-    } else if (!force_fan && p.fan.size() == 1 && p.fan.begin()->second.first == cd(1.0, 0.0)) {
-      // a lone controlled phase (CZ, CU1, Z, T...): scalar on the slice where all of its bits are 1
+    } else if (!force_fan && p.fan.size() == 1 && p.fan.begin()->second.first == cd(1.0, 0.0) && p.scalar == cd(1.0, 0.0)) {
+      // a lone controlled phase (CZ, CU1, Z, T...): a factor on the slice where all of its bits are 1.  (PlanOp semantics:
+      // phase(x) = [controls set] * scalar * prod_b f_b(x_b) -- with a non-unit scalar the slice where the fan bit is 0
+      // gets a factor too, which only the general fan below applies)
       m.type = MU_PHASE;
       int pos = p.fan.begin()->first;
       if (!((sb.tile_mask >> pos) & 1)) m.ext_cmask |= uint64_t(1) << pos;
       else if (rbit_of_local[sb.local_of_pos[pos]] >= 0) m.creg |= 1u << rbit_of_local[sb.local_of_pos[pos]];
       else m.cthr |= 1u << sb.local_of_pos[pos];
-      *reinterpret_cast<C*>(m.inl) = to_dev<C>(p.scalar * p.fan.begin()->second.second);
+      *reinterpret_cast<C*>(m.inl) = to_dev<C>(p.fan.begin()->second.second);
       if (m.creg == 0) m.handler = MH_PHASE_NC;
       else if (__builtin_popcount(m.creg) == 1) m.handler = (uint8_t)(MH_PHASE_C + __builtin_ctz(m.creg));
       else m.handler = MH_PHASE_M;
@@ -691,8 +696,6 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
   }
   // ---- fuse "1-qubit gate on register bit I" + "fan controlled by bit I alone" into one stage op (one dispatch)
   if (!env_int("QB_NO_STAGE", 0)) {
-    const size_t first_payload = sb.payloads.size() - mops.size(), first_slot_guard = 0;
-    (void)first_slot_guard;
     std::vector<MicroOp> fused;
     std::vector<int> new_index(mops.size(), -1);
     for (size_t q = 0; q < mops.size(); ++q) {
@@ -715,7 +718,9 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       fused.push_back(a);
     }
     if (fused.size() != mops.size()) {
-      for (size_t q = 0; q < mops.size(); ++q) sb.payload_owner[first_payload + q].second = new_index[q];
+      // (by owner, not by position: a micro-op may own several payload entries once ops have been fused)
+      for (auto& po : sb.payload_owner)
+        if (po.first == pass_index && po.second >= 0) po.second = new_index[po.second];
       for (auto& so : sb.slots)
         if (so.first == pass_index && so.second >= 0) so.second = new_index[so.second];
       // a fused pair owns two payload entries (the dense gate's is empty): keep the fan's payload as the op's
@@ -724,7 +729,6 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
   }
   // ---- fuse runs of uncontrolled real one-qubit gates on distinct register bits (they commute) into layer ops
   if (!env_int("QB_NO_LAYER", 0)) {
-    const size_t first_payload = sb.payloads.size() - mops.size();
     std::vector<MicroOp> fused;
     std::vector<int> new_index(mops.size(), -1);
     std::vector<std::vector<C>> extra_payloads;  // payload of each new layer op
@@ -766,7 +770,10 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       q = e;
     }
     if (fused.size() != mops.size()) {
-      for (size_t t = 0; t < mops.size(); ++t) sb.payload_owner[first_payload + t].second = new_index[t];
+      // by owner: after the stage fusion above the pass no longer has one payload entry per micro-op, so positions
+      // counted back from the end of the payload list would be off by the number of fused pairs
+      for (auto& po : sb.payload_owner)
+        if (po.first == pass_index && po.second >= 0) po.second = new_index[po.second];
       for (auto& so : sb.slots)
         if (so.first == pass_index && so.second >= 0) so.second = new_index[so.second];
       for (size_t x = 0; x < extra_payloads.size(); ++x) {  // the members' own payload entries are empty (inline matrices)
@@ -976,6 +983,10 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
   const size_t window = (size_t)env_int("QB_REORDER_WINDOW", 4096);
   std::vector<char> done(N, 0);
   size_t ndone = 0, first = 0;
+  // ops a sweep may take: the blob estimate of the scan below cannot know the passes (one group table per distinct
+  // register set, 1 KiB each for complex64), so a sweep whose program does not fit after all is planned again with
+  // half as many ops
+  int cur_max_ops = max_ops;
   while (ndone < N) {
     while (first < N && done[first]) ++first;
     // ---- list scheduling: walk the remaining ops in program order; an op joins this sweep when it commutes with
@@ -1002,9 +1013,9 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
           if (__builtin_popcountll(nh) > free_high || (nh & ~allowed)) {
             if (allowed == ~uint64_t(0) && out.empty() && q == first) { err = "gate has more target qubits outside the low bits than a tile can hold"; fatal = true; return; }
             ok = false;
-          } else if (!out.empty() && (est + add > (size_t)SWEEP_BLOB_MAX || (int)out.size() >= max_ops || slot_est + slot_add > SWEEP_MAX_SLOTS)) {
+          } else if (!out.empty() && (est + add > (size_t)SWEEP_BLOB_MAX || (int)out.size() >= cur_max_ops || slot_est + slot_add > SWEEP_MAX_SLOTS)) {
             ok = false;
-            if ((int)out.size() >= max_ops) break;
+            if ((int)out.size() >= cur_max_ops) break;
           } else if (est + add > (size_t)SWEEP_BLOB_MAX) {
             err = "single gate does not fit the sweep program buffer";
             fatal = true;
@@ -1194,12 +1205,24 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
         }
       }
     }
-    if ((int)sb.slots.size() > SWEEP_MAX_SLOTS) { err = "internal: too many per-tile slots in one sweep"; return false; }
     sd.stage_only = sb.passes.empty() ? 0 : 1;
     for (auto& ph_ : sb.passes)
       if (ph_.kind != PASS_REGTILE || ph_.stage_mask == 0) sd.stage_only = 0;
-    finish_blob<C>(sb, hdr, plan.blob, sd);
-    if (hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) { err = "internal: sweep program too large"; return false; }
+    const size_t blob_before = plan.blob.size();
+    const bool too_many_slots = (int)sb.slots.size() > SWEEP_MAX_SLOTS;
+    if (!too_many_slots) finish_blob<C>(sb, hdr, plan.blob, sd);
+    if (too_many_slots || hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) {
+      if (chosen.size() <= 1) {
+        err = too_many_slots ? "internal: too many per-tile slots in one sweep" : "internal: sweep program too large";
+        return false;
+      }
+      plan.blob.resize(blob_before);  // plan this sweep again with fewer ops
+      for (size_t q : chosen) done[q] = 0;
+      ndone -= chosen.size();
+      cur_max_ops = (int)chosen.size() / 2;
+      continue;
+    }
+    cur_max_ops = max_ops;
     plan.npasses += sd.npasses;
     plan.ndiag += sd.ndiag;
     if (env_int("QB_PLAN_DEBUG", 0))

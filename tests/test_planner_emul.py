@@ -144,3 +144,71 @@ def test_six_qubit_dense_block(dtype):
     ref = oracle_run(psi, ops, n)
     out, _ = emul.apply_program(psi, n, ops)
     assert np.abs(out - ref).max() < tol(dtype) * (20 if dtype == "complex64" else 1)
+
+
+def _phase_heavy_program(rng, n, ngates):
+    """H / RY next to phases on their own qubits, CU1 / CZ / multi-controlled phases sharing qubits: the shapes the
+    planner's fan merging, re-rooting and stage / layer fusion rewrite."""
+    ops = []
+    for _ in range(ngates):
+        kind = rng.integers(0, 7)
+        if kind == 0:
+            ops.append(Op(orc.gate_matrix("H"), (int(rng.integers(0, n)),)))
+        elif kind == 1:
+            a, b = rng.permutation(n)[:2].tolist()
+            ops.append(Op(orc.gate_matrix("CU1", float(rng.uniform(0, 6))), (a, b)))
+        elif kind == 2:
+            ops.append(Op(np.array([1, np.exp(1j * rng.uniform(0, 6))]), (int(rng.integers(0, n)),), is_diagonal=True))
+        elif kind == 3:
+            a, b = rng.permutation(n)[:2].tolist()
+            ops.append(Op(orc.gate_matrix("CZ"), (a, b)))
+        elif kind == 4:
+            ops.append(Op(np.exp(1j * rng.uniform(0, 6, size=2)), (int(rng.integers(0, n)),), is_diagonal=True))
+        elif kind == 5:
+            qs = rng.permutation(n)[: int(rng.integers(2, 4))].tolist()
+            ops.append(Op(orc.gate_matrix("U1", float(rng.uniform(0, 6))), (qs[0],), tuple(qs[1:])))
+        else:
+            ops.append(Op(orc.gate_matrix("RY", float(rng.uniform(0, 6))), (int(rng.integers(0, n)),)))
+    return ops
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_phase_heavy_programs(seed):
+    rng = np.random.default_rng(seed)
+    for _ in range(12):
+        n = int(rng.integers(4, 15))
+        ops = _phase_heavy_program(rng, n, int(rng.integers(5, 60)))
+        for dtype in ("complex128", "complex64"):
+            psi = rand_state(n, seed, dtype)
+            ref = oracle_run(psi.astype(np.complex128), ops, n)
+            out, _ = emul.apply_program(psi, n, ops)
+            assert np.abs(out - ref).max() < (1e-12 if dtype == "complex128" else 2e-5), (seed, n, dtype)
+
+
+def test_planner_regressions():
+    """Found by the fuzz above.  (1) A phase on exactly a fan's control set is a scalar on the CONTROL slice: a one-entry
+    fan with such a scalar is no longer a lone phase on all of its bits.  (2) A pass with a fused stage op AND a fused
+    layer op: payloads are re-assigned by owner (positions counted from the end of the payload list were off by the
+    number of fused pairs -> wrong tables, out-of-range offsets).  (3) complex64 sweeps whose program outgrows the
+    shared-memory buffer (one 1 KiB group table per distinct register set) are planned again with fewer ops."""
+    g = orc.gate_matrix
+    ph = lambda t: np.array([1, np.exp(1j * t)])  # noqa: E731
+    cases = [
+        (11, [Op(g("CZ"), (6, 5)), Op(ph(0.24), (6,), is_diagonal=True)]),
+        (6, [Op(g("RY", 3.0), (2,)), Op(g("RY", 1.9), (3,)), Op(ph(3.3), (2,), is_diagonal=True), Op(g("H"), (2,)),
+             Op(g("U1", -0.6), (2,), (3,)), Op(g("RY", 3.6), (4,)), Op(ph(1.2), (4,), is_diagonal=True)]),
+        (5, [Op(g("H"), (1,)), Op(ph(0.7), (1,), is_diagonal=True), Op(g("CU1", 0.4), (1, 3)), Op(ph(1.1), (3,), is_diagonal=True),
+             Op(ph(2.1), (1,), is_diagonal=True), Op(g("CZ"), (3, 1)), Op(g("H"), (3,)), Op(ph(0.3), (3,), is_diagonal=True)]),
+    ]
+    for n, ops in cases:
+        for dtype in ("complex128", "complex64"):
+            psi = rand_state(n, 3, dtype)
+            out, _ = emul.apply_program(psi, n, ops)
+            assert np.abs(out - oracle_run(psi.astype(np.complex128), ops, n)).max() < (1e-12 if dtype == "complex128" else 2e-5)
+    for seed in (21, 33, 79, 84):  # "internal: sweep program too large" before the retry
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(5, 15))
+        ops = random_zoo(n, int(rng.integers(10, 70)), 5000 + seed, max_dense=min(5, n))
+        psi = rand_state(n, seed, "complex64")
+        out, _ = emul.apply_program(psi, n, ops)
+        assert np.abs(out - oracle_run(psi.astype(np.complex128), ops, n)).max() < 1e-4
