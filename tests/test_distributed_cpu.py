@@ -250,6 +250,72 @@ def test_fused_exchange_permutation_equivalence(monkeypatch):
         assert err < 1e-12 and nex == planned == world.bit_length() - 1
 
 
+@pytest.mark.parametrize("block", range(4))
+def test_plans_on_random_circuits_all_ranks_simulated(block):
+    """Plan + specialise + exchanges on random circuits, layouts (auto, random global sets, with and without batched
+    exchanges) and world sizes 2/4/8, every rank simulated in this process: local segments by the oracle, exchanges as
+    NumPy half-shard swaps or as the out-of-place all-to-all -- the gathered state equals the oracle's."""
+    sys.path[:0] = [ROOT, HERE]
+    from helpers import oracle_run, rand_state, random_zoo
+    from qibo_b200 import circuits
+    from qibo_b200 import distributed as D
+
+    for seed in range(12 * block, 12 * block + 12):
+        rng = np.random.default_rng(seed)
+        g = int(rng.integers(1, 4))
+        W = 1 << g
+        n = int(rng.integers(g + 3, 10))
+        kind = seed % 4
+        if kind == 0:
+            ops = random_zoo(n, int(rng.integers(5, 40)), seed, max_dense=min(3, n - g))
+        elif kind == 1:
+            ops = circuits.qft(n)
+        elif kind == 2:
+            ops = circuits.random_circuit(n, int(rng.integers(5, 30)), seed)
+        else:
+            ops = circuits.variational(n, 2, rng.random(8 * n) * 6)
+        lay = seed % 3
+        if lay == 0:
+            plan = D.choose_layout(n, g, ops)
+        elif lay == 1:
+            plan = D.Plan(n, g, ops, global_qubits=tuple(rng.permutation(n)[:g].tolist()))
+        else:
+            plan = D.Plan(n, g, ops, batch_exchanges=bool(seed % 2))
+        nl = n - g
+        axes = list(plan.global_qubits) + list(plan.local_qubits)
+        psi = rand_state(n, seed)
+        t = psi.reshape((2,) * n).transpose(axes).reshape(W, 1 << nl)
+        shards = [t[r].copy() for r in range(W)]
+        nex = 0
+        for kind_, payload in D.exchange_runs(plan.segments):
+            if kind_ == "local":
+                for r in range(W):
+                    local = [o for o in (D.specialise(p, nl, r) for p in payload) if o is not None]
+                    if local:
+                        shards[r] = oracle_run(shards[r], local, nl)
+                continue
+            nex += len(payload)
+            if D.alltoall_push_entries(0, nl, payload) is not None and seed % 2:
+                second = [np.zeros(1 << nl, complex) for _ in range(W)]
+                for r in range(W):
+                    for r2, a, b_, lo_, hi_ in D.alltoall_push_entries(r, nl, payload):
+                        second[r2][b_ + lo_ : b_ + hi_] = shards[r][a + lo_ : a + hi_]
+                shards = second
+                continue
+            for gbit, lbit in payload:
+                j = gbit - nl
+                new = [x.copy() for x in shards]
+                idx = np.arange(1 << nl)
+                for r in range(W):
+                    b = (r >> j) & 1
+                    mine = idx[((idx >> lbit) & 1) == 1 - b]
+                    new[r][mine] = shards[r ^ (1 << j)][mine ^ (1 << lbit)]
+                shards = new
+        full = np.stack(shards).reshape((2,) * n).transpose(np.argsort(axes)).reshape(-1)
+        assert np.abs(full - oracle_run(psi, ops, n)).max() < 1e-12, seed
+        assert nex == plan.nexchanges
+
+
 def test_plan_properties():
     """Device-free planner checks in the spirit of tests/test_models_distcircuit.py:95-103: no mixing target is
     ever on a global bit inside a local segment, and the layout is canonical at the end."""
