@@ -207,7 +207,8 @@ class Plan:
     exactly where a late one has to leave from."""
 
     def __init__(self, nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True, high_window: int = 8,
-                 global_qubits: Optional[Sequence[int]] = None, batch_exchanges: bool = True):
+                 global_qubits: Optional[Sequence[int]] = None, batch_exchanges: bool = True,
+                 final_global_qubits: Optional[Sequence[int]] = None):
         self.n, self.g = nqubits, nglobal
         self.nlocal = nqubits - nglobal
         if self.nlocal < 1:
@@ -227,6 +228,20 @@ class Plan:
             home[q] = nlocal - 1 - k
         self.home = tuple(home)
         pos = list(home)
+        # ``final_global_qubits``: leave the state in ANOTHER layout (e.g. run a QFT from the cyclic layout, which needs one
+        # exchange per global qubit, and hand the result to the sharded measurement in the block layout it works on)
+        fq = gq if final_global_qubits is None else tuple(int(q) for q in final_global_qubits)
+        if len(fq) != nglobal or len(set(fq)) != nglobal or any(q < 0 or q >= n for q in fq):
+            raise ValueError(f"final_global_qubits must name {nglobal} distinct qubits, got {fq}")
+        self.final_global_qubits = fq
+        self.final_local_qubits = tuple(q for q in range(n) if q not in fq)
+        if fq != gq:
+            home = [0] * n
+            for j, q in enumerate(fq):
+                home[q] = n - 1 - j
+            for k, q in enumerate(self.final_local_qubits):
+                home[q] = nlocal - 1 - k
+        self.final_home = tuple(home)
         # next dense use of every logical qubit, for the furthest-in-future eviction rule
         needs = [mixing_targets(op) for op in ops]
         swaps = [relabel_swaps and is_plain_swap(op) for op in ops]
@@ -349,12 +364,14 @@ class Plan:
         assert pos == list(home)
 
 
-def choose_layout(nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True) -> Plan:
-    """The plan with the fewest exchanges among the block layout and the two orders of the cyclic one (ties: block)."""
+def choose_layout(nqubits: int, nglobal: int, ops: Sequence[Op], relabel_swaps: bool = True,
+                  final_global_qubits: Optional[Sequence[int]] = None) -> Plan:
+    """The plan with the fewest exchanges among the block layout and the two orders of the cyclic one (ties: block) as
+    the INITIAL layout; the final one is the same unless ``final_global_qubits`` fixes it."""
     cyc = cyclic_layout(nqubits, nglobal)
     best = None
     for gq in (block_layout(nqubits, nglobal), cyc, cyc[::-1]):
-        plan = Plan(nqubits, nglobal, ops, relabel_swaps=relabel_swaps, global_qubits=gq)
+        plan = Plan(nqubits, nglobal, ops, relabel_swaps=relabel_swaps, global_qubits=gq, final_global_qubits=final_global_qubits)
         if best is None or plan.nexchanges < best.nexchanges:
             best = plan
     return best
@@ -486,9 +503,11 @@ class ShardedProgram:
     """A gate queue planned once for (n, world size) and specialised for this rank; ``run`` applies it to a shard."""
 
     def __init__(self, engine, nqubits: int, dtype, ops: Sequence[Op], relabel_swaps: bool = True, apply=None,
-                 staging_elems: int = 1 << 26, global_qubits=None):
+                 staging_elems: int = 1 << 26, global_qubits=None, final_global_qubits=None):
         """``global_qubits``: None = the leading qubits (block layout: rank r holds state[r * 2^nlocal : (r+1) * 2^nlocal]),
-        a sequence of qubits (Plan), or "auto" = whichever of the block / cyclic layouts needs the fewest exchanges."""
+        a sequence of qubits (Plan), or "auto" = whichever of the block / cyclic layouts needs the fewest exchanges.
+        ``final_global_qubits``: the layout the state is left in (default: the one it came in); ``shard_of`` / ``scatter``
+        / ``basis_state`` / ``locate`` speak the initial layout, ``gather`` / ``canonical_index`` the final one."""
         self.engine = engine
         self.world, self.rank = world_size(), rank()
         self.g = int(round(math.log2(self.world)))
@@ -499,10 +518,12 @@ class ShardedProgram:
         if isinstance(global_qubits, str):
             if global_qubits != "auto":
                 raise ValueError(f"unknown layout {global_qubits!r}")
-            self.plan = choose_layout(nqubits, self.g, ops, relabel_swaps=relabel_swaps)
+            self.plan = choose_layout(nqubits, self.g, ops, relabel_swaps=relabel_swaps, final_global_qubits=final_global_qubits)
         else:
-            self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps, global_qubits=global_qubits)
+            self.plan = Plan(nqubits, self.g, ops, relabel_swaps=relabel_swaps, global_qubits=global_qubits,
+                             final_global_qubits=final_global_qubits)
         self.global_qubits, self.local_qubits = self.plan.global_qubits, self.plan.local_qubits
+        self.final_global_qubits, self.final_local_qubits = self.plan.final_global_qubits, self.plan.final_local_qubits
         self.fuse_perm = os.environ.get("QB_A2A_FUSE_PERM", "0") not in ("", "0")  # experimental, see split_trailing_permutation
         self.segments = []
         runs = exchange_runs(self.plan.segments)
@@ -544,12 +565,13 @@ class ShardedProgram:
         return r, loc
 
     def canonical_index(self, rank_: int, loc: int) -> int:
-        """Inverse of ``locate``."""
+        """Canonical index of amplitude ``loc`` of rank ``rank_`` AFTER the program (the final layout; the inverse of
+        ``locate`` when the layout does not change)."""
         index = 0
-        for j, q in enumerate(self.global_qubits):
+        for j, q in enumerate(self.final_global_qubits):
             index |= ((rank_ >> (self.g - 1 - j)) & 1) << (self.n - 1 - q)
-        nl = len(self.local_qubits)
-        for k, q in enumerate(self.local_qubits):
+        nl = len(self.final_local_qubits)
+        for k, q in enumerate(self.final_local_qubits):
             index |= ((loc >> (nl - 1 - k)) & 1) << (self.n - 1 - q)
         return index
 
@@ -724,9 +746,9 @@ class ShardedProgram:
         parts = [torch.empty_like(tensor) for _ in range(self.world)]
         dist.all_gather(parts, tensor)
         full = torch.cat(parts).cpu().numpy()
-        if self.global_qubits == tuple(range(self.g)):
+        if self.final_global_qubits == tuple(range(self.g)):
             return full
-        inv = np.argsort(self._axes())
+        inv = np.argsort(list(self.final_global_qubits) + list(self.final_local_qubits))
         return np.ascontiguousarray(full.reshape((2,) * self.n).transpose(inv)).reshape(-1)
 
 
@@ -760,7 +782,15 @@ def execute_circuit(backend, circuit, initial_state=None, nshots=None):
         ops.extend(backend._gate_ops(gate, n))
     gather_max = int(os.environ.get("QB_GATHER_MAX_QUBITS", 30))
     # the sharded measurement path (dist_measure.py) works on the block layout; a state that is gathered may use any
-    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops, global_qubits="auto" if n <= gather_max else None)
+    # ... so a large register starts in whichever layout needs the fewest exchanges (|0...0> looks the same in all of them)
+    # and is handed over in the block layout; a user-supplied initial state is scattered in the block layout
+    if n <= gather_max:
+        layout = dict(global_qubits="auto")
+    elif initial_state is None:
+        layout = dict(global_qubits="auto", final_global_qubits=block_layout(n, int(round(math.log2(world_size())))))
+    else:
+        layout = {}
+    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops, **layout)
     if initial_state is None:
         shard = prog.basis_state(0)
     else:

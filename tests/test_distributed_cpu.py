@@ -48,7 +48,8 @@ def _worker(rank, world, port, case, n, seed, layout, out):
         else:
             ops = random_zoo(n, 40, seed, max_dense=3)
         psi = rand_state(n, seed)
-        prog = ShardedProgram(None, n, "complex128", ops, apply=_oracle_apply, staging_elems=8, global_qubits=layout)
+        kw = layout if isinstance(layout, dict) else dict(global_qubits=layout)
+        prog = ShardedProgram(None, n, "complex128", ops, apply=_oracle_apply, staging_elems=8, **kw)
         nl = prog.nlocal
         if layout is None:
             assert np.array_equal(prog.shard_of(psi), psi[rank << nl : (rank + 1) << nl])
@@ -89,7 +90,9 @@ def test_sharded_program_matches_oracle(world, case):
 
 
 @pytest.mark.parametrize("world,case,layout", [(2, "qft", "auto"), (4, "qft", "auto"), (4, "zoo", "auto"), (4, "qft", (5, 2)),
-                                               (2, "variational", (3,)), (4, "random", (7, 0))])
+                                               (2, "variational", (3,)), (4, "random", (7, 0)),
+                                               (4, "qft", dict(global_qubits="auto", final_global_qubits=(0, 1))),
+                                               (2, "zoo", dict(global_qubits=(4,), final_global_qubits=(1,)))])
 def test_sharded_program_other_layouts(world, case, layout):
     """Global qubits other than the leading ones (cyclic layout for the QFT, arbitrary sets): shard_of / gather map the
     canonical state onto the ranks, and the plan returns to the same layout."""
@@ -97,7 +100,9 @@ def test_sharded_program_other_layouts(world, case, layout):
     assert err < 1e-12
     assert nex == planned
     if case == "qft" and layout == "auto":
-        assert planned == world.bit_length() - 1  # one exchange per global qubit, as the reference's _DistributedQFT
+        assert planned == world.bit_length() - 1
+    if case == "qft" and isinstance(layout, dict):  # in through the cyclic layout, out in the block layout: two all-to-alls
+        assert planned == 2 * (world.bit_length() - 1)  # one exchange per global qubit, as the reference's _DistributedQFT
 
 
 def test_cyclic_layout_qft_plan():
@@ -277,10 +282,13 @@ def test_plans_on_random_circuits_all_ranks_simulated(block):
         lay = seed % 3
         if lay == 0:
             plan = D.choose_layout(n, g, ops)
-        elif lay == 1:
-            plan = D.Plan(n, g, ops, global_qubits=tuple(rng.permutation(n)[:g].tolist()))
+        elif lay == 1:  # any set of global qubits, and another one to leave the state in
+            plan = D.Plan(n, g, ops, global_qubits=tuple(rng.permutation(n)[:g].tolist()),
+                          final_global_qubits=tuple(rng.permutation(n)[:g].tolist()) if seed % 2 else None)
         else:
             plan = D.Plan(n, g, ops, batch_exchanges=bool(seed % 2))
+        if seed % 5 == 0:  # fewest exchanges on the way in, block layout on the way out (what the sharded measurement takes)
+            plan = D.choose_layout(n, g, ops, final_global_qubits=D.block_layout(n, g))
         nl = n - g
         axes = list(plan.global_qubits) + list(plan.local_qubits)
         psi = rand_state(n, seed)
@@ -311,7 +319,8 @@ def test_plans_on_random_circuits_all_ranks_simulated(block):
                     mine = idx[((idx >> lbit) & 1) == 1 - b]
                     new[r][mine] = shards[r ^ (1 << j)][mine ^ (1 << lbit)]
                 shards = new
-        full = np.stack(shards).reshape((2,) * n).transpose(np.argsort(axes)).reshape(-1)
+        final_axes = list(plan.final_global_qubits) + list(plan.final_local_qubits)
+        full = np.stack(shards).reshape((2,) * n).transpose(np.argsort(final_axes)).reshape(-1)
         assert np.abs(full - oracle_run(psi, ops, n)).max() < 1e-12, seed
         assert nex == plan.nexchanges
 
