@@ -28,6 +28,26 @@ def test_library_exports_every_declared_symbol():
     assert lib.qb_version() == 100
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++ in the signatures) and a C program that calls an entry
+    point links against the shared library."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "qibo_b200.h"\n'
+                   "int main(void) { qb_program p = 0; qb_handle h = 0; (void)p; (void)h; return qb_version() == 100 ? 0 : 1; }\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", str(src), "-I", os.path.join(root, "include"),
+                    "-L", libdir, "-lqibo_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_struct_layout_matches_header():
     # qb_op: 2 + 6 + 32 + 2 int32 then a pointer; qb_program_stats: 4 int32, double, 2 float
     assert ctypes.sizeof(_lib.QbOp) == 4 * (2 + 6 + 32 + 2) + 8
