@@ -288,11 +288,12 @@ def run_gpu(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    sweep_ms, nsweeps, xch_ms, xch_bytes, nxch, perm_ms, nperm, nxl = 0.0, 0, 0.0, 0, 0, 0.0, 0, 0
+    sweep_ms, nsweeps, xch_ms, xch_bytes, nxch, perm_ms, nperm, nxl, nstage = 0.0, 0, 0.0, 0, 0, 0.0, 0, 0, 0
     for _ in range(args.steps):
         stats = step()
         sweep_ms += stats.elapsed_ms
         nsweeps += stats.nsweeps
+        nstage += getattr(stats, "nstage_sweeps", 0)
         perm_ms += getattr(stats, "perm_ms", 0.0)
         nperm += getattr(stats, "nperm", 0)
         xch_ms += getattr(stats, "exchange_ms", 0.0)
@@ -400,7 +401,8 @@ def run_gpu(args):
             "config": {
                 "workload": f"QFT({n}) {args.dtype}, {n_gates(n)} gates, zero initial state and compiled gate program resident in HBM, "
                 f"{2 ** nlocal * itemsize / 2 ** 30:.0f} GiB per GPU", "nqubits": n, "global_qubits": g,
-                "sweeps_per_step": nsweeps // args.steps, "l2": "state (>= 16 GiB) is far larger than the 126 MB L2",
+                "sweeps_per_step": nsweeps // args.steps,
+                **({"stage_only_sweeps_per_step": nstage // args.steps} if world == 1 else {}), "l2": "state (>= 16 GiB) is far larger than the 126 MB L2",
                 "parallelism": f"global-qubit sharding x{world}" if world > 1 else "single GPU",
                 **({"layout": f"global qubits {list(runner.global_qubits)} (--layout {args.layout}); rank = their bits, shard index = "
                     "the other qubits in ascending order"} if world > 1 else {}),
