@@ -220,7 +220,7 @@ def verify_sharded_qft(runner, state, args, eng, dist):
             phase = (x * k) % (1 << n)
             want = cmath.exp(2j * cmath.pi * (phase / float(1 << n))) / (2.0 ** (n / 2))
             err = max(err, abs(complex(v) - want) * 2.0 ** (n / 2))
-        t = torch.tensor([err], device="cuda", dtype=torch.float64)
+        t = torch.tensor([err], device=st.tensor.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out = {"basis_state": x, "samples_per_rank": len(sample), "max_rel_err": float(t.item()), "exchange_path": attempt}
         if out["max_rel_err"] < tol or attempt == "pairwise":

@@ -325,6 +325,87 @@ def test_plans_on_random_circuits_all_ranks_simulated(block):
         assert nex == plan.nexchanges
 
 
+def _verify_worker(rank, world, port, n, layout, break_it, out):
+    sys.path[:0] = [ROOT, HERE]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+
+        import bench
+        from qibo_b200 import circuits
+        from qibo_b200.distributed import ShardedProgram
+
+        calls = {"n": 0}
+
+        def apply(tensor, nlocal, ops):
+            _oracle_apply(tensor, nlocal, ops)
+            calls["n"] += 1
+            if break_it and rank == 1:
+                tensor[3] += 1e-3  # a wrong amplitude on one rank must fail the check on every rank, on every transport
+
+        prog = ShardedProgram(None, n, "complex128", circuits.qft(n), apply=apply, staging_elems=8, global_qubits=layout)
+        state = SimpleNamespace(tensor=torch.zeros(1 << prog.nlocal, dtype=torch.complex128))
+        args = SimpleNamespace(dtype="complex128")
+        try:
+            res = bench.verify_sharded_qft(prog, state, args, None, dist)
+        except AssertionError as e:
+            res = {"failed": str(e)}
+        r0, loc0 = prog.locate(0)
+        ok_reset = bool(state.tensor.abs().sum().item() == (1.0 if r0 == rank else 0.0)) and bool(r0 != rank or state.tensor[loc0] == 1)
+        if rank == 0:
+            out.put((res, ok_reset))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,layout,break_it", [(2, "auto", False), (4, "auto", False), (4, None, False), (2, "auto", True)])
+def test_bench_closed_form_check(world, layout, break_it):
+    """bench.py's pre-timing check of a sharded QFT (closed form exp(2 pi i x k / 2^n) / sqrt(2^n) at sample amplitudes of
+    every rank) on gloo with the oracle as the shard executor: passes on a correct run, fails on every rank when one rank
+    holds a wrong amplitude, and leaves |0...0> behind."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_verify_worker, args=(r, world, port, 10, layout, break_it, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res, ok_reset = out.get()
+    if break_it:
+        assert "failed" in res
+    else:
+        assert res["max_rel_err"] < 1e-12 and res["samples_per_rank"] >= 2 and ok_reset
+        assert res["exchange_path"].startswith("alltoall")  # (no peer memory on gloo: the name of the configured path)
+
+
+def test_locate_and_canonical_index_round_trip():
+    """ShardedProgram.locate (initial layout) and canonical_index (final layout) are inverse bit shuffles -- bench.py's
+    closed-form check of the sharded QFT relies on them."""
+    sys.path[:0] = [ROOT, HERE]
+    from types import SimpleNamespace
+
+    from qibo_b200.distributed import ShardedProgram
+
+    rng = np.random.default_rng(2)
+    for n, g in ((7, 2), (9, 3), (6, 1), (35, 3)):
+        for _ in range(4):
+            gq = tuple(rng.permutation(n)[:g].tolist())
+            lq = tuple(q for q in range(n) if q not in gq)
+            ns = SimpleNamespace(n=n, g=g, global_qubits=gq, local_qubits=lq, final_global_qubits=gq, final_local_qubits=lq)
+            for index in [0, (1 << n) - 1] + [int(x) for x in rng.integers(0, 1 << n, size=20)]:
+                r, loc = ShardedProgram.locate(ns, index)
+                assert 0 <= r < (1 << g) and 0 <= loc < (1 << (n - g))
+                assert ShardedProgram.canonical_index(ns, r, loc) == index
+    # block layout: rank = leading bits, shard index = the rest; cyclic layout: rank = trailing bits
+    ns = SimpleNamespace(n=5, g=2, global_qubits=(0, 1), local_qubits=(2, 3, 4), final_global_qubits=(0, 1), final_local_qubits=(2, 3, 4))
+    assert ShardedProgram.locate(ns, 0b10110) == (0b10, 0b110)
+    ns = SimpleNamespace(n=5, g=2, global_qubits=(3, 4), local_qubits=(0, 1, 2), final_global_qubits=(3, 4), final_local_qubits=(0, 1, 2))
+    assert ShardedProgram.locate(ns, 0b10110) == (0b10, 0b101)
+
+
 def test_plan_properties():
     """Device-free planner checks in the spirit of tests/test_models_distcircuit.py:95-103: no mixing target is
     ever on a global bit inside a local segment, and the layout is canonical at the end."""
