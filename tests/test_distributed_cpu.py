@@ -381,6 +381,82 @@ def test_bench_closed_form_check(world, layout, break_it):
         assert res["exchange_path"].startswith("alltoall")  # (no peer memory on gloo: the name of the configured path)
 
 
+class _FakeEngine:
+    """TEST INFRASTRUCTURE: stands in for qibo_b200.engine.Engine on CPU shards (oracle arithmetic) so that the plumbing of
+    ShardedProgram.run -- compiled programs on first use, the uncompiled e2e path, statistics -- runs without a GPU."""
+
+    def __init__(self):
+        self.compiled, self.launched, self.applied = 0, 0, 0
+
+    def compile(self, nqubits, dtype, ops):
+        from types import SimpleNamespace
+
+        self.compiled += 1
+        return SimpleNamespace(nqubits=nqubits, dtype=np.dtype(dtype), ops=list(ops))
+
+    def _stats(self, ops):
+        from types import SimpleNamespace
+
+        return SimpleNamespace(nsweeps=1, elapsed_ms=0.5, perm_ms=0.0, nperm=0, nops=len(ops))
+
+    def run_program(self, prog, state, timed=False, alt=None):
+        assert alt is None  # only peer-memory shards carry a second buffer
+        _oracle_apply(state.tensor, prog.nqubits, prog.ops)
+        self.launched += 1
+        return self._stats(prog.ops)
+
+    def apply_program(self, state, nqubits, ops, timed=False, alt=None):
+        _oracle_apply(state.tensor, nqubits, ops)
+        self.applied += 1
+        return self._stats(ops)
+
+
+def _engine_worker(rank, world, port, n, out):
+    sys.path[:0] = [ROOT, HERE]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+
+        from helpers import oracle_run, rand_state
+        from qibo_b200 import circuits
+        from qibo_b200.distributed import ShardedProgram
+
+        ops = circuits.qft(n)
+        eng = _FakeEngine()
+        prog = ShardedProgram(eng, n, "complex128", ops, staging_elems=8, global_qubits="auto")
+        psi = rand_state(n, 9)
+        state = SimpleNamespace(tensor=torch.from_numpy(prog.shard_of(psi).copy()))
+        s1 = prog.run(state)  # compiles every local segment once ...
+        s2 = prog.run(state, timed=False)  # ... and only launches afterwards
+        nlocal_segments = sum(1 for seg in prog.segments if seg[0] == "local" and seg[1])
+        assert eng.compiled == nlocal_segments and eng.launched == 2 * nlocal_segments and eng.applied == 0
+        s3 = prog.run(state, timed=False, compiled=False)  # the e2e leg: host gate matrices on every call
+        assert eng.applied == nlocal_segments and eng.compiled == nlocal_segments
+        ref = oracle_run(oracle_run(oracle_run(psi, ops, n), ops, n), ops, n)
+        err = float(np.abs(prog.gather(state) - ref).max())
+        assert s1.nsweeps == s2.nsweeps == s3.nsweeps == nlocal_segments and s1.nexchanges == prog.plan.nexchanges
+        assert s1.nexchange_launches == s1.nexchanges and s1.exchange_bytes > 0  # pairwise exchanges on gloo
+        if rank == 0:
+            out.put(err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_program_engine_plumbing(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_engine_worker, args=(r, world, port, 9, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get() < 1e-12
+
+
 def test_locate_and_canonical_index_round_trip():
     """ShardedProgram.locate (initial layout) and canonical_index (final layout) are inverse bit shuffles -- bench.py's
     closed-form check of the sharded QFT relies on them."""
