@@ -764,6 +764,18 @@ class RunStats:
         self.exchange_bytes = 0
 
 
+def api_layout(nqubits: int, gather_max: int, has_initial_state: bool, world: int) -> dict:
+    """Layout arguments of the ShardedProgram behind ``execute_distributed_circuit``: a state that is gathered may use
+    any layout (the one with the fewest exchanges); a larger register goes to the sharded measurement, which works on the
+    block layout -- it starts in the cheapest layout when it starts from |0...0> (which looks the same in all of them) and
+    is handed over in the block layout; a user-supplied initial state is scattered in the block layout."""
+    if nqubits <= gather_max:
+        return dict(global_qubits="auto")
+    if not has_initial_state:
+        return dict(global_qubits="auto", final_global_qubits=block_layout(nqubits, int(round(math.log2(world)))))
+    return {}
+
+
 def execute_circuit(backend, circuit, initial_state=None, nshots=None):
     """``Backend.execute_distributed_circuit`` under torchrun: every rank calls it with the same circuit."""
     from qibo.config import raise_error
@@ -782,15 +794,7 @@ def execute_circuit(backend, circuit, initial_state=None, nshots=None):
         ops.extend(backend._gate_ops(gate, n))
     gather_max = int(os.environ.get("QB_GATHER_MAX_QUBITS", 30))
     # the sharded measurement path (dist_measure.py) works on the block layout; a state that is gathered may use any
-    # ... so a large register starts in whichever layout needs the fewest exchanges (|0...0> looks the same in all of them)
-    # and is handed over in the block layout; a user-supplied initial state is scattered in the block layout
-    if n <= gather_max:
-        layout = dict(global_qubits="auto")
-    elif initial_state is None:
-        layout = dict(global_qubits="auto", final_global_qubits=block_layout(n, int(round(math.log2(world_size())))))
-    else:
-        layout = {}
-    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops, **layout)
+    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops, **api_layout(n, gather_max, initial_state is not None, world_size()))
     if initial_state is None:
         shard = prog.basis_state(0)
     else:

@@ -457,6 +457,22 @@ def test_sharded_program_engine_plumbing(world):
     assert out.get() < 1e-12
 
 
+def test_api_layout_choice():
+    sys.path[:0] = [ROOT, HERE]
+    from qibo_b200 import circuits
+    from qibo_b200.distributed import Plan, api_layout, block_layout, choose_layout
+
+    assert api_layout(12, 30, False, 4) == dict(global_qubits="auto")
+    assert api_layout(12, 30, True, 4) == dict(global_qubits="auto")
+    assert api_layout(35, 30, False, 8) == dict(global_qubits="auto", final_global_qubits=(0, 1, 2))
+    assert api_layout(35, 30, True, 8) == {}
+    # what the large-register path buys for a QFT: two runs of exchanges (all-to-alls) instead of seven scattered ones
+    ops = circuits.qft(35)
+    through = choose_layout(35, 3, ops, final_global_qubits=block_layout(35, 3))
+    assert through.final_global_qubits == (0, 1, 2) and through.nexchanges == 6
+    assert Plan(35, 3, ops).nexchanges == 7
+
+
 def test_locate_and_canonical_index_round_trip():
     """ShardedProgram.locate (initial layout) and canonical_index (final layout) are inverse bit shuffles -- bench.py's
     closed-form check of the sharded QFT relies on them."""
