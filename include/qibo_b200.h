@@ -68,6 +68,11 @@ int qb_free(qb_handle h, void* dptr);
 /* kind: 0 host->device, 1 device->host, 2 device->device.  Replaces Backend.cast / to_numpy
  * (backends/numpy.py:38-64, 98-107) for the state buffer. */
 int qb_memcpy(qb_handle h, void* dst, const void* src, size_t bytes, int kind);
+/* Same copy, enqueued and NOT waited for, on `cuda_stream` (a cudaStream_t; NULL = the handle's stream).  kind 2 also
+ * copies between a local buffer and a peer-mapped one (qb_ipc_open_handle): the DMA engines move the bytes over NVLink
+ * without occupying an SM -- the transport of the chunk-pipelined global<->local exchange (models/distcircuit.py:185-268
+ * is the reference's one-swap-at-a-time scheme). */
+int qb_memcpy_async(qb_handle h, void* dst, const void* src, size_t bytes, int kind, void* cuda_stream);
 
 /* ---- K6: state construction (abstract.py:2243-2273 zero_state, :2199-2241 plus/minus_state) ------- */
 int qb_state_set_basis(qb_handle h, void* state, int nqubits, int dtype, uint64_t index);

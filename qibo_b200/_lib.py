@@ -56,6 +56,7 @@ PROTOTYPES = {
     "qb_malloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "qb_free": (c_int, [c_void_p, c_void_p]),
     "qb_memcpy": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "qb_memcpy_async": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "qb_state_set_basis": (c_int, [c_void_p, c_void_p, c_int, c_int, c_uint64]),
     "qb_state_fill": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double]),
     "qb_state_cast": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_uint64]),

@@ -211,6 +211,14 @@ int qb_memcpy(qb_handle h, void* dst, const void* src, size_t bytes, int kind) {
   return QB_OK;
 }
 
+int qb_memcpy_async(qb_handle h, void* dst, const void* src, size_t bytes, int kind, void* cuda_stream) {
+  if (!h || (!dst && bytes) || (!src && bytes) || kind < 0 || kind > 2) return fail(QB_ERR_INVALID, "bad copy arguments");
+  DeviceGuard guard(h->device);
+  cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  QB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, cuda_stream ? (cudaStream_t)cuda_stream : h->stream));
+  return QB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K6
 // ---------------------------------------------------------------------------------------------------

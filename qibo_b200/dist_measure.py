@@ -55,6 +55,9 @@ class EngineLocal:
     def norm2(self, shard):
         return self.engine.norm2(shard)
 
+    def vdot(self, a, b, nlocal):
+        return self.engine.vdot(a, b, nlocal)
+
     def scale(self, shard, nlocal, factor):
         self.engine.apply_op(shard, nlocal, Op(np.array([factor, factor]), (0,), is_diagonal=True))
 
@@ -82,6 +85,28 @@ class ShardMeasure:
         if len(set(qubits)) != len(qubits) or any(q < 0 or q >= self.n for q in qubits):
             raise ValueError(f"bad measured qubits {qubits}")
         return qubits, [q - self.g for q in qubits if q >= self.g]
+
+    # ---- scalars ------------------------------------------------------------------------------------------------------
+    def global_norm2(self, shard) -> float:
+        """<psi|psi> over all shards (callbacks.Norm, callbacks.py:161-174)."""
+        t = torch.tensor([self.local.norm2(shard)], dtype=torch.float64, device=self.local.device(shard))
+        return float(self._all_reduce(t).item())
+
+    def global_vdot(self, a, b) -> complex:
+        """<a|b> over all shards (Backend.overlap_statevector, abstract.py:2180-2190)."""
+        v = complex(self.local.vdot(a, b, self.nlocal))
+        t = torch.tensor([v.real, v.imag], dtype=torch.float64, device=self.local.device(b))
+        self._all_reduce(t)
+        return complex(float(t[0].item()), float(t[1].item()))
+
+    def gather(self, shard) -> np.ndarray:
+        """The full state in canonical order as a host array on every rank (block layout; small registers only)."""
+        tensor = shard.tensor.clone()
+        if self.world == 1:
+            return tensor.cpu().numpy()
+        parts = [torch.empty_like(tensor) for _ in range(self.world)]
+        dist.all_gather(parts, tensor, group=self.group)
+        return torch.cat(parts).cpu().numpy()
 
     # ---- probabilities ----------------------------------------------------------------------------------------------
     def probabilities(self, shard, qubits: Sequence[int]):

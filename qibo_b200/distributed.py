@@ -449,6 +449,7 @@ class PeerShard:
         import torch.distributed as dist
 
         self.engine = engine
+        self.rank = dist.get_rank()
         # two exported buffers: the out-of-place permutation kernel (K8) writes into the other one and the shard moves
         # there -- on every rank at the same point of the plan (SWAP runs are never specialised away), so each rank knows
         # which of a peer's two mappings is current without asking
@@ -470,11 +471,9 @@ class PeerShard:
     @property
     def alt_ptrs(self):
         """rank -> device pointer of that rank's SECOND (not current) buffer in this process, this rank included."""
-        import torch.distributed as dist
-
         other = 1 - self.current
         out = {r: p[other] for r, p in self._peer_ptrs.items()}
-        out[dist.get_rank()] = self.alt.data_ptr()
+        out[self.rank] = self.alt.data_ptr()
         return out
 
     def flip(self):
@@ -499,17 +498,41 @@ class PeerShard:
         return self.array.tensor
 
 
+class LocalPeerShard(PeerShard):
+    """One of W shards that all live on ONE GPU (SingleDeviceGroup): the "peer" pointers are the sibling shards' buffers in
+    the same address space, so the real exchange kernels (k7_alltoall_push / k7_alltoall_p2p / k7_swap_half_p2p) and the
+    per-rank plans run end to end without NVLink -- the fences are no-ops because the ranks take turns on one stream."""
+
+    def __init__(self, engine, nlocal: int, dtype, rank_: int):
+        self.engine, self.rank = engine, rank_
+        self.array = engine.empty((1 << nlocal,), dtype)
+        self.alt = engine.empty((1 << nlocal,), dtype)
+        self._base = (self.array.data_ptr(), self.alt.data_ptr())
+        self._peer_ptrs = {}
+
+    @staticmethod
+    def link(shards):
+        for s in shards:
+            s._peer_ptrs = {t.rank: t._base for t in shards if t is not s}
+
+    def fence(self):
+        pass
+
+
 class ShardedProgram:
     """A gate queue planned once for (n, world size) and specialised for this rank; ``run`` applies it to a shard."""
 
     def __init__(self, engine, nqubits: int, dtype, ops: Sequence[Op], relabel_swaps: bool = True, apply=None,
-                 staging_elems: int = 1 << 26, global_qubits=None, final_global_qubits=None):
+                 staging_elems: int = 1 << 26, global_qubits=None, final_global_qubits=None, world_: Optional[int] = None,
+                 rank_: Optional[int] = None):
         """``global_qubits``: None = the leading qubits (block layout: rank r holds state[r * 2^nlocal : (r+1) * 2^nlocal]),
         a sequence of qubits (Plan), or "auto" = whichever of the block / cyclic layouts needs the fewest exchanges.
         ``final_global_qubits``: the layout the state is left in (default: the one it came in); ``shard_of`` / ``scatter``
         / ``basis_state`` / ``locate`` speak the initial layout, ``gather`` / ``canonical_index`` the final one."""
         self.engine = engine
-        self.world, self.rank = world_size(), rank()
+        # (world_, rank_): play rank `rank_` of `world_` without a process group (SingleDeviceGroup, tests)
+        self.world = world_size() if world_ is None else int(world_)
+        self.rank = rank() if rank_ is None else int(rank_)
         self.g = int(round(math.log2(self.world)))
         if 1 << self.g != self.world:
             raise ValueError("the number of ranks must be a power of two")
@@ -525,6 +548,9 @@ class ShardedProgram:
         self.global_qubits, self.local_qubits = self.plan.global_qubits, self.plan.local_qubits
         self.final_global_qubits, self.final_local_qubits = self.plan.final_global_qubits, self.plan.final_local_qubits
         self.fuse_perm = os.environ.get("QB_A2A_FUSE_PERM", "0") not in ("", "0")  # experimental, see split_trailing_permutation
+        # chunk-pipelined exchange (DMA copies over peer memory overlapped with the local sweeps before them)
+        self.pipeline = os.environ.get("QB_NO_PIPELINE", "") in ("", "0")
+        self._copy_stream = None
         self.segments = []
         runs = exchange_runs(self.plan.segments)
         for i, (kind, payload) in enumerate(runs):
@@ -540,7 +566,17 @@ class ShardedProgram:
                     split = split_trailing_permutation(runs[i + 1][1], self.nlocal, len(pairs))
                     if split is not None:
                         gates, sub_dest = split
-                self.segments.append(("exchange", pairs, sub_dest, gates))
+                piped = None
+                if self.pipeline and sub_dest is None and len(pairs) <= 3 and alltoall_push_entries(0, self.nlocal, pairs):
+                    # the tail of the local segment in front of the exchange that leaves the k leading local qubits alone
+                    # runs chunk by chunk, each chunk leaving as soon as it is done (_pipelined_exchange)
+                    piped = PipedOps([], [])
+                    if self.segments and self.segments[-1][0] == "local":
+                        head, tail = split_for_pipeline(self.nlocal, self.dtype, self.segments[-1][1], len(pairs))
+                        if tail is not None:
+                            self.segments[-1] = ("local", head)
+                            piped = tail
+                self.segments.append(("exchange", pairs, sub_dest, gates, piped))
         # runs of >= alltoall_min exchanges go through the all-to-all kernel (peer-memory shards only)
         self.alltoall = os.environ.get("QB_NO_ALLTOALL", "") in ("", "0")
         self.alltoall_min = int(os.environ.get("QB_ALLTOALL_MIN", "1"))
@@ -621,50 +657,118 @@ class ShardedProgram:
     def run(self, state, timed: bool = True, compiled: bool = True):
         """Apply the program to this rank's shard (DeviceArray, or a torch tensor with the test hook).  ``compiled``: the
         local segments run as device-resident compiled programs (planned on first use); False sends the host gate
-        matrices through qb_apply_program on every call."""
+        matrices through qb_apply_program on every call.  ``timed``: CUDA events are recorded around every segment
+        WITHOUT synchronising the host (the step loop never waits for the GPU); ``RunStats.resolve()`` reads them after
+        the caller's own synchronisation -- the properties of the returned stats do that on first access."""
+        out = RunStats()
+        for index in range(len(self.segments)):
+            self.run_segment(index, state, out, timed=timed, compiled=compiled)
+        return out
+
+    def run_segment(self, index: int, state, out: "RunStats", timed: bool = False, compiled: bool = True):
+        """One segment of the plan on this rank's shard.  Every rank runs segment ``index`` before any rank runs
+        ``index + 1`` (the fences inside the exchanges enforce it across processes; SingleDeviceGroup does it by taking
+        turns)."""
         peer = state if isinstance(state, PeerShard) else None
         if peer is not None:
             state = peer.array
-        out = RunStats()
-        for seg in self.segments:
-            tensor = state.tensor if hasattr(state, "tensor") else state  # (a permutation re-points the DeviceArray)
-            if seg[0] == "local":
-                if not seg[1]:
-                    continue
-                if self._apply is not None:
-                    self._apply(tensor, self.nlocal, seg[1])
-                else:
-                    alt = peer.alt if peer is not None else None
-                    if compiled:
-                        st = self.engine.run_program(self._compiled(seg), state, timed=timed, alt=alt)
-                    else:
-                        st = self.engine.apply_program(state, self.nlocal, seg[1], timed=timed, alt=alt)
-                    out.nsweeps += st.nsweeps
-                    out.elapsed_ms += st.elapsed_ms
-                    out.perm_ms += getattr(st, "perm_ms", 0.0)
-                    out.nperm += getattr(st, "nperm", 0)
-            else:
-                pairs = seg[1]
-                t0 = None
-                if tensor.is_cuda and timed:
-                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    t0.record()
-                self._exchange_run(state, peer, tensor, pairs, out, sub_dest=seg[2], timed=timed, compiled=compiled)
-                out.nexchanges += len(pairs)
-                if t0 is not None:
-                    t1.record()
-                    t1.synchronize()
-                    out.exchange_ms += t0.elapsed_time(t1)
-        return out
+        seg = self.segments[index]
+        spans = out.spans if timed else None
+        tensor = state.tensor if hasattr(state, "tensor") else state  # (a permutation re-points the DeviceArray)
+        if seg[0] == "local":
+            if seg[1]:
+                self._run_local(seg, seg[1], state, peer, out, spans, compiled)
+            return
+        pairs = seg[1]
+        piped = seg[4] if len(seg) > 4 else None
+        ev = _span_begin(spans, tensor)
+        if piped is not None and not self._pipelined_exchange(state, peer, pairs, piped, out, compiled):
+            # transport without chunk pipelining (NCCL staging, CPU test hook): the deferred ops run on the whole shard
+            if piped.nlocal_ops:
+                self._run_local(piped.full_key, piped.nlocal_ops, state, peer, out, None, compiled)
+            piped = None
+        if piped is None:
+            self._exchange_run(state, peer, tensor, pairs, out, sub_dest=seg[2], timed=timed, compiled=compiled)
+        out.nexchanges += len(pairs)
+        _span_end(spans, ev, "exchange", 1)
 
-    def _compiled(self, seg):
+    def _run_local(self, key, ops, state, peer, out, spans, compiled):
+        tensor = state.tensor if hasattr(state, "tensor") else state
+        if self._apply is not None:
+            self._apply(tensor, self.nlocal, ops)
+            return
+        alt = peer.alt if peer is not None else None
+        if compiled:
+            st = self.engine.run_program(self._compiled(key, ops), state, alt=alt, spans=spans)
+        else:
+            st = self.engine.apply_program(state, self.nlocal, ops, alt=alt, spans=spans)
+        out.nsweeps += st.nsweeps
+        out.nperm += getattr(st, "nperm", 0)
+
+    def _compiled(self, key, ops=None, nqubits=None):
         """The local segment compiled for this rank's engine, on first use (qb_program_create): later runs of the plan
         launch kernels only."""
-        key = id(seg)
-        prog = self._programs.get(key)
+        k = id(key)
+        prog = self._programs.get(k)
         if prog is None:
-            prog = self._programs[key] = self.engine.compile(self.nlocal, self.dtype, seg[1])
+            prog = self._programs[k] = self.engine.compile(self.nlocal if nqubits is None else nqubits, self.dtype,
+                                                           key[1] if ops is None else ops)
         return prog
+
+    # ---- the exchange overlapped with the local sweeps before it ----------------------------------------------------
+    def _pipelined_exchange(self, state, peer, pairs, piped: "PipedOps", out, compiled) -> bool:
+        """A run of exchanges on the k leading local bits, out of place, chunk by chunk (chunk = the k leading bits of the
+        shard index, which is also what the all-to-all moves): the gates that precede the exchange and touch none of the
+        k leading local qubits (``piped.ops``, already re-indexed to the chunk's nlocal - k qubits) run on one chunk at a
+        time on the compute stream; as soon as a chunk is done it leaves for the destination rank's second buffer on the
+        copy stream -- a DMA copy over NVLink peer memory that occupies no SM -- while the next chunk is being swept.
+        Remote chunks go first, in order of rank XOR distance (every rank then receives from one sender at a time), the
+        chunk that stays on this rank last.  Returns False when this transport is not available (no peer-mapped shard)."""
+        if peer is None or self._apply is not None or not (self.alltoall and self.alltoall_push and self.pipeline):
+            return False
+        entries = alltoall_push_entries(self.rank, self.nlocal, pairs)
+        if entries is None:
+            return False
+        k = len(pairs)
+        sub_n = self.nlocal - k
+        elem = state.tensor.element_size()
+        eng = self.engine
+        main = torch.cuda.current_stream(state.tensor.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=state.tensor.device)
+        copy = self._copy_stream
+        prog = None
+        if piped.ops:
+            prog = self._compiled(piped, piped.ops, nqubits=sub_n) if compiled else None
+        dst = peer.alt_ptrs
+        src0 = state.data_ptr()
+        peer.fence()  # every rank is done reading what is now its second buffer
+        order = sorted(entries, key=lambda e: ((e[0] ^ self.rank) == 0, e[0] ^ self.rank))
+        from qibo_b200.array import DeviceArray
+
+        for r2, a, b, lo, hi in order:
+            if piped.ops:
+                view = DeviceArray(state.tensor[a : a + (1 << sub_n)])
+                if prog is not None:
+                    st = eng.run_program(prog, view)
+                else:
+                    st = eng.apply_program(view, sub_n, piped.ops)
+                out.nsweeps += st.nsweeps
+                out.nchunk_sweeps += st.nsweeps
+            done = torch.cuda.Event()
+            done.record(main)
+            copy.wait_event(done)
+            eng.memcpy_async(dst[r2] + b * elem, src0 + a * elem, (hi - lo) * elem, copy.cuda_stream)
+            if r2 != self.rank:
+                out.exchange_bytes += 2 * elem * (hi - lo)
+        landed = torch.cuda.Event()
+        landed.record(copy)
+        main.wait_event(landed)
+        peer.fence()  # every rank's chunks have landed
+        peer.flip()
+        out.nexchange_launches += len(order)
+        out.pipelined += 1
+        return True
 
     def _exchange_run(self, state, peer, tensor, pairs, out, sub_dest=None, timed=False, compiled=True):
         """One run of exchanges [(gbit, lbit), ...] on pairwise distinct bits.  ``sub_dest`` (experimental): a permutation
@@ -696,10 +800,8 @@ class ShardedProgram:
             if self._apply is not None:
                 self._apply(state.tensor if hasattr(state, "tensor") else state, self.nlocal, swaps)
             else:
-                st = self.engine.apply_program(state, self.nlocal, swaps, timed=timed, alt=peer.alt if peer is not None else None)
+                st = self.engine.apply_program(state, self.nlocal, swaps, alt=peer.alt if peer is not None else None)
                 out.nsweeps += st.nsweeps
-                out.elapsed_ms += st.elapsed_ms
-                out.perm_ms += getattr(st, "perm_ms", 0.0)
                 out.nperm += getattr(st, "nperm", 0)
             return
         if use_a2a and self.alltoall_push and len(pairs) <= 3:
@@ -737,6 +839,13 @@ class ShardedProgram:
                 out.exchange_bytes += exchange_half(tensor, self.nlocal, gbit, lbit, self._stage(tensor))
             out.nexchange_launches += 1
 
+    def assemble(self, concatenated: np.ndarray) -> np.ndarray:
+        """All shards in rank order -> the full state in canonical order (the FINAL layout of the program)."""
+        if self.final_global_qubits == tuple(range(self.g)):
+            return concatenated
+        inv = np.argsort(list(self.final_global_qubits) + list(self.final_local_qubits))
+        return np.ascontiguousarray(concatenated.reshape((2,) * self.n).transpose(inv)).reshape(-1)
+
     def gather(self, state) -> np.ndarray:
         """Full state in canonical order on every rank (small n only)."""
         import torch.distributed as dist
@@ -745,30 +854,145 @@ class ShardedProgram:
         tensor = tensor.clone()
         parts = [torch.empty_like(tensor) for _ in range(self.world)]
         dist.all_gather(parts, tensor)
-        full = torch.cat(parts).cpu().numpy()
-        if self.final_global_qubits == tuple(range(self.g)):
-            return full
-        inv = np.argsort(list(self.final_global_qubits) + list(self.final_local_qubits))
-        return np.ascontiguousarray(full.reshape((2,) * self.n).transpose(inv)).reshape(-1)
+        return self.assemble(torch.cat(parts).cpu().numpy())
+
+
+class PipedOps:
+    """The tail of a local segment that rides on the exchange after it: ``ops`` act on the nlocal - k lower local qubits
+    of one chunk (re-indexed), ``nlocal_ops`` are the same gates in shard numbering (transports without pipelining)."""
+
+    def __init__(self, ops, nlocal_ops):
+        self.ops, self.nlocal_ops = ops, nlocal_ops
+        self.full_key = ("full", nlocal_ops)
+
+    def __getitem__(self, i):  # (_compiled keys a segment by identity and reads its ops from [1])
+        return (None, self.ops)[i]
+
+
+def split_for_pipeline(nlocal: int, dtype, ops: Sequence[Op], k: int):
+    """Split a rank's local segment in front of an exchange on the k leading local bits into (head, tail): ``tail`` = the
+    gates that touch none of the k leading local qubits and sit, in the sweep planner's own schedule, in sweeps after the
+    last sweep that does -- they can run chunk by chunk.  Both keep program order; the ops that moved commute with what
+    they moved past (they belong to different sweeps of a valid schedule).  -> (head ops, PipedOps or None)."""
+    from qibo_b200.engine import is_plain_swap as engine_plain_swap
+    from qibo_b200.engine import plan_program
+
+    if not ops or k < 1 or nlocal - k < 4:
+        return list(ops), None
+    if any(engine_plain_swap(o) for o in ops):
+        return list(ops), None  # SWAP runs become out-of-place permutations of the whole shard
+    touch = [any(q < k for q in tuple(o.targets) + tuple(o.controls)) for o in ops]
+    _, sweep_of_op = plan_program(nlocal, dtype, ops)
+    last = max((s for s, t in zip(sweep_of_op, touch) if t and s >= 0), default=-1)
+    head = [o for o, s in zip(ops, sweep_of_op) if s <= last]
+    tail = [o for o, s in zip(ops, sweep_of_op) if s > last]
+    if not tail:
+        return list(ops), None
+    shifted = [Op(o.data, tuple(q - k for q in o.targets), tuple(q - k for q in o.controls), is_diagonal=o.is_diagonal) for o in tail]
+    return head, PipedOps(shifted, tail)
+
+
+def _span_begin(spans, tensor):
+    if spans is None or not getattr(tensor, "is_cuda", False):
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _span_end(spans, e0, kind, count):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    spans.append((kind, e0, e1, count))
 
 
 class RunStats:
+    """Counters of one ``ShardedProgram.run`` plus the CUDA-event spans recorded around its segments.  The spans are read
+    lazily (``resolve``): nothing in the step loop waits for the GPU."""
+
     def __init__(self):
         self.nsweeps = 0
-        self.elapsed_ms = 0.0  # CUDA-event time of the local sweeps
-        self.perm_ms = 0.0  # of which: K8 permutation launches
+        self.nchunk_sweeps = 0  # of which: launches on one chunk of the shard (pipelined exchange)
         self.nperm = 0
         self.nexchanges = 0
-        self.nexchange_launches = 0  # kernels (or NCCL rounds): a run of exchanges done as one all-to-all counts once
-        self.exchange_ms = 0.0
+        self.nexchange_launches = 0  # kernels / DMA copies (or NCCL rounds): a run of exchanges done as one all-to-all counts once
         self.exchange_bytes = 0
+        self.pipelined = 0
+        self.spans = []  # (kind, event0, event1, launches): "sweep" | "perm" | "exchange"
+        self._ms = None
+
+    def resolve(self):
+        if self._ms is None:
+            ms = {"sweep": 0.0, "perm": 0.0, "exchange": 0.0}
+            for kind, e0, e1, _ in self.spans:
+                e1.synchronize()
+                ms[kind] += e0.elapsed_time(e1)
+            self._ms = ms
+        return self._ms
+
+    @property
+    def elapsed_ms(self):  # CUDA-event time of the local sweeps incl. the K8 launches
+        m = self.resolve()
+        return m["sweep"] + m["perm"]
+
+    @property
+    def perm_ms(self):
+        return self.resolve()["perm"]
+
+    @property
+    def exchange_ms(self):  # a pipelined exchange includes the chunk sweeps it overlaps with
+        return self.resolve()["exchange"]
 
 
-def api_layout(nqubits: int, gather_max: int, has_initial_state: bool, world: int) -> dict:
+class SingleDeviceGroup:
+    """All W = 2^g shards of an n-qubit register on ONE GPU, every "rank" with its own plan, specialised ops and compiled
+    programs, taking turns segment by segment on one stream.  The exchange kernels get the sibling shards' buffers as
+    peer pointers, so the whole multi-GPU data path -- Plan, specialise, K7 all-to-all (out of place / in place), pairwise
+    half swaps, the chunk-pipelined DMA exchange, buffer flips -- runs and can be checked on a single-GPU box."""
+
+    def __init__(self, engine, nqubits: int, world: int, dtype, ops: Sequence[Op], **kw):
+        self.world, self.n = world, nqubits
+        self.programs = [ShardedProgram(engine, nqubits, dtype, ops, world_=world, rank_=r, **kw) for r in range(world)]
+        self.nlocal = self.programs[0].nlocal
+        self.shards = [LocalPeerShard(engine, self.nlocal, dtype, r) for r in range(world)]
+        LocalPeerShard.link(self.shards)
+
+    def configure(self, **flags):
+        for p in self.programs:
+            for k, v in flags.items():
+                if not hasattr(p, k):
+                    raise AttributeError(k)
+                setattr(p, k, v)
+
+    def scatter(self, full: np.ndarray):
+        for p, s in zip(self.programs, self.shards):
+            s.tensor.copy_(torch.from_numpy(p.shard_of(full).astype(p.dtype)))
+
+    def run(self, compiled: bool = True):
+        stats = [RunStats() for _ in self.programs]
+        nseg = len(self.programs[0].segments)
+        assert all(len(p.segments) == nseg for p in self.programs)
+        for index in range(nseg):
+            for p, s, st in zip(self.programs, self.shards, stats):
+                p.run_segment(index, s, st, compiled=compiled)
+        return stats
+
+    def gather(self) -> np.ndarray:
+        torch.cuda.synchronize()
+        return self.programs[0].assemble(torch.cat([s.tensor for s in self.shards]).cpu().numpy())
+
+
+def api_layout(nqubits: int, gather_max: int, has_initial_state: bool, world: int, has_special: bool = False) -> dict:
     """Layout arguments of the ShardedProgram behind ``execute_distributed_circuit``: a state that is gathered may use
     any layout (the one with the fewest exchanges); a larger register goes to the sharded measurement, which works on the
     block layout -- it starts in the cheapest layout when it starts from |0...0> (which looks the same in all of them) and
-    is handed over in the block layout; a user-supplied initial state is scattered in the block layout."""
+    is handed over in the block layout; a user-supplied initial state is scattered in the block layout.  Circuits with
+    special gates (callbacks, collapsing measurements) keep the block layout between their gate runs: the sharded
+    reductions of dist_measure.py work on it."""
+    if has_special:
+        return {}
     if nqubits <= gather_max:
         return dict(global_qubits="auto")
     if not has_initial_state:
@@ -776,55 +1000,163 @@ def api_layout(nqubits: int, gather_max: int, has_initial_state: bool, world: in
     return {}
 
 
-def execute_circuit(backend, circuit, initial_state=None, nshots=None):
-    """``Backend.execute_distributed_circuit`` under torchrun: every rank calls it with the same circuit."""
+class ShardedState:
+    """Handle on a state that is too large to replicate (more than QB_GATHER_MAX_QUBITS qubits): every rank holds its
+    2^(n-g) amplitudes of the block layout in ``tensor`` (rank r = the g leading qubits).  What ``QuantumState`` offers
+    on a full state (result.py:31-163) is answered by reductions across the ranks instead."""
+
+    def __init__(self, backend, shard, nqubits: int):
+        from qibo_b200.dist_measure import EngineLocal, ShardMeasure
+
+        self.backend, self.shard, self.nqubits = backend, shard, nqubits
+        self.measure = ShardMeasure(nqubits, EngineLocal(backend.engine_gpu))
+        self.rank, self.world = self.measure.rank, self.measure.world
+
+    @property
+    def tensor(self):
+        return self.shard.tensor
+
+    def probabilities(self, qubits=None):
+        """Marginal over ``qubits`` in the caller's order, replicated on every rank (DeviceArray); all qubits in order
+        (the default): this rank's slice of the 2^n probabilities."""
+        from qibo_b200.array import DeviceArray
+
+        qubits = list(range(self.nqubits)) if qubits is None else [int(q) for q in qubits]
+        probs, _ = self.measure.probabilities(self.shard, qubits)
+        return DeviceArray(probs)
+
+    def samples(self, nshots: int, qubits=None, binary: bool = True):
+        """Shots over ``qubits`` (default: all) drawn from the global legacy RNG, identical on every rank (which must
+        share the seed, ``Backend.set_seed``)."""
+        qubits = list(range(self.nqubits)) if qubits is None else [int(q) for q in qubits]
+        probs, sharded = self.measure.probabilities(self.shard, qubits)
+        uniforms = np.random.random_sample(int(nshots))
+        out = self.measure.sample(probs, uniforms, sharded).cpu().numpy()
+        return self.backend.samples_to_binary(out, len(qubits)) if binary else out
+
+    def norm(self) -> float:
+        return float(np.sqrt(self.measure.global_norm2(self.shard)))
+
+    def state(self, numpy: bool = False):
+        from qibo.config import raise_error
+
+        raise_error(NotImplementedError, f"a {self.nqubits}-qubit state is not replicated on every rank; use .tensor (this rank's "
+                    "shard), .probabilities(qubits) or .samples(nshots)")
+
+    def __repr__(self):
+        return f"ShardedState(nqubits={self.nqubits}, rank={self.rank}/{self.world}, shard={tuple(self.shard.tensor.shape)})"
+
+
+def _apply_special(backend, gate, shard, n, measure, gather_max):
+    """Gates that must see the whole state (distcircuit.py:278-284): collapsing measurements and callbacks, on the sharded
+    state in the block layout.  M(collapse=True) -> marginal (all-reduce), one shot from the global RNG (same seed on
+    every rank), projection + global renormalisation (gates/measurements.py:189-205).  Callbacks: Norm and Overlap are
+    reductions over the ranks; every other callback receives the gathered state while it fits."""
     from qibo.config import raise_error
-    from qibo.result import CircuitResult, QuantumState
 
     from qibo_b200.array import DeviceArray
 
+    name = gate.__class__.__name__
+    if name == "M":
+        gate.result.backend = backend
+        if not gate.collapse:
+            return
+        qubits = sorted(gate.target_qubits)
+        probs, _ = measure.probabilities(shard, qubits)
+        shot = gate.result.add_shot(DeviceArray(probs), backend=backend)
+        measure.collapse(shard, qubits, int(np.asarray(shot).ravel()[0]))
+        return
+    if name == "CallbackGate":
+        cb = gate.callback
+        cb.nqubits = n
+        kind = cb.__class__.__name__
+        if kind == "Norm":
+            cb.append(float(np.sqrt(measure.global_norm2(shard))))
+            return
+        if kind == "Overlap":
+            target = backend.to_numpy(cb.state) if isinstance(cb.state, DeviceArray) else np.asarray(cb.state)
+            nl = measure.nlocal
+            mine = backend.engine_gpu.upload(np.ascontiguousarray(target[measure.rank << nl : (measure.rank + 1) << nl]).astype(shard.dtype))
+            cb.append(abs(measure.global_vdot(mine, shard)))
+            return
+        if n > gather_max:
+            raise_error(NotImplementedError, f"callback {kind} needs the full state, which is not gathered above {gather_max} qubits")
+        full = backend.engine_gpu.upload(measure.gather(shard))
+        gate.apply(backend, full, n)
+        return
+    raise_error(NotImplementedError, f"{name} is not supported inside distributed circuits")
+
+
+def execute_circuit(backend, circuit, initial_state=None, nshots=None):
+    """``Backend.execute_distributed_circuit`` under torchrun: every rank calls it with the same circuit (and the same
+    RNG seed).  The queue is cut at the special gates (distcircuit.py:278-284: callbacks and collapsing measurements see
+    the full state); each run of plain gates is one ShardedProgram."""
+    from qibo.config import raise_error
+    from qibo.result import CircuitResult, MeasurementOutcomes, QuantumState
+
+    from qibo_b200.array import DeviceArray
+    from qibo_b200.dist_measure import EngineLocal, ShardMeasure
+
     n = circuit.nqubits
-    ops = []
+    runs, cur = [], []  # [("ops", [Op]) | ("special", gate)]
     for gate in circuit.queue:
-        if not backend._is_plain(gate):
-            if gate.__class__.__name__ == "M" and not gate.collapse:
-                gate.result.backend = backend
-                continue
-            raise_error(NotImplementedError, "callbacks / collapsing measurements need the full state: not available across ranks")
-        ops.extend(backend._gate_ops(gate, n))
+        if backend._is_plain(gate):
+            cur.extend(backend._gate_ops(gate, n))
+            continue
+        if gate.__class__.__name__ == "M" and not gate.collapse:
+            gate.result.backend = backend
+            continue
+        if cur:
+            runs.append(("ops", cur))
+            cur = []
+        runs.append(("special", gate))
+    if cur:
+        runs.append(("ops", cur))
+    has_special = any(kind == "special" for kind, _ in runs)
     gather_max = int(os.environ.get("QB_GATHER_MAX_QUBITS", 30))
-    # the sharded measurement path (dist_measure.py) works on the block layout; a state that is gathered may use any
-    prog = ShardedProgram(backend.engine_gpu, n, backend._cdtype, ops, **api_layout(n, gather_max, initial_state is not None, world_size()))
-    if initial_state is None:
-        shard = prog.basis_state(0)
-    else:
-        host = backend.to_numpy(initial_state) if isinstance(initial_state, DeviceArray) else np.asarray(initial_state)
-        shard = prog.scatter(host)
-    prog.run(shard, timed=False)
+    eng = backend.engine_gpu
+    layout = api_layout(n, gather_max, initial_state is not None, world_size(), has_special)
+    measure = ShardMeasure(n, EngineLocal(eng))
+    shard, prog = None, None
+    first = True
+    for kind, payload in runs or [("ops", [])]:
+        if kind == "ops":
+            prog = ShardedProgram(eng, n, backend._cdtype, payload, **layout)
+            if first:
+                if initial_state is None:
+                    shard = prog.basis_state(0)
+                else:
+                    host = backend.to_numpy(initial_state) if isinstance(initial_state, DeviceArray) else np.asarray(initial_state)
+                    shard = prog.scatter(host)
+            prog.run(shard, timed=False)
+        else:
+            if first:
+                prog = ShardedProgram(eng, n, backend._cdtype, [], **layout)
+                if initial_state is None:
+                    shard = prog.basis_state(0)
+                else:
+                    host = backend.to_numpy(initial_state) if isinstance(initial_state, DeviceArray) else np.asarray(initial_state)
+                    shard = prog.scatter(host)
+            _apply_special(backend, payload, shard, n, measure, gather_max)
+        first = False
     if n > gather_max:
         # too large to replicate: measurement outcomes come from the sharded state (dist_measure.py) -- marginal over the
         # measured qubits (all-reduce), then inverse-CDF sampling with the global legacy RNG as sample_shots does
-        # (abstract.py:2774-2781).  Without measurements there is nothing a single process could hold.
+        # (abstract.py:2774-2781); without measurements the caller gets a handle on the sharded state.
         if not circuit.measurements:
-            raise_error(NotImplementedError, f"gathering a state of more than {gather_max} qubits on every rank is not supported; "
-                        "measure it or use ShardedProgram / ShardMeasure")
-        from qibo.result import MeasurementOutcomes
-
-        from qibo_b200.dist_measure import EngineLocal, ShardMeasure
-
+            circuit._final_state = ShardedState(backend, shard, n)
+            return circuit._final_state
         qubits = []
-        for m in circuit.measurements:
-            qubits.extend(q for q in m.qubits if q not in qubits)
-        qubits = sorted(qubits)  # measurement_gate.qubits order (result.py:204)
-        sm = ShardMeasure(n, EngineLocal(backend.engine_gpu))
-        probs, sharded = sm.probabilities(shard, qubits)
+        for m in circuit.measurements:  # order of the joint measurement gate: the qubits as they were added (result.py:444-458)
+            qubits.extend(q for q in m.target_qubits if q not in qubits)
+        probs, sharded = measure.probabilities(shard, qubits)
         nshots = 1000 if nshots is None else nshots
         uniforms = np.random.random_sample(nshots)  # every rank must hold the same seed (Backend.set_seed)
-        samples = sm.sample(probs, uniforms, sharded).cpu().numpy()
+        samples = measure.sample(probs, uniforms, sharded).cpu().numpy()
         binary = backend.samples_to_binary(samples, len(qubits))
         circuit._final_state = MeasurementOutcomes(circuit.measurements, backend=backend, samples=binary, nshots=nshots)
         return circuit._final_state
-    full = backend.engine_gpu.upload(prog.gather(shard))
+    full = eng.upload(prog.gather(shard))
     if circuit.measurements:
         circuit._final_state = CircuitResult(full, circuit.measurements, backend=backend, nshots=1000 if nshots is None else nshots)
     else:

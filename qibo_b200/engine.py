@@ -142,13 +142,14 @@ class Engine:
         del keep
         return stats
 
-    def permute_qubits(self, state: DeviceArray, nqubits: int, dest_of_qubit: Sequence[int], timed: bool = False, alt: Optional[DeviceArray] = None):
+    def permute_qubits(self, state: DeviceArray, nqubits: int, dest_of_qubit: Sequence[int], timed: bool = False, alt: Optional[DeviceArray] = None,
+                       spans: Optional[list] = None):
         """K8: out-of-place qubit permutation in one sweep; the DeviceArray is re-pointed at the result buffer.  ``alt``:
         a second buffer of the same shape to permute into -- the two DeviceArrays then trade buffers (shards that other
         ranks have mapped through CUDA IPC ping-pong between two exported buffers this way); an IPC-exported buffer
         without ``alt`` gets its result copied back in place.  Returns elapsed ms or None."""
         scratch = torch.empty_like(state.tensor) if alt is None else alt.tensor
-        if timed:
+        if timed or spans is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         _lib.check(
@@ -164,7 +165,10 @@ class Engine:
             state.tensor.copy_(scratch)
         else:
             state.tensor = scratch
-        if timed:
+        if spans is not None:
+            e1.record()
+            spans.append(("perm", e0, e1, 1))
+        elif timed:
             e1.record()
             e1.synchronize()
             return e0.elapsed_time(e1)
@@ -179,10 +183,12 @@ class Engine:
         )
 
     def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False,
-                      alt: Optional[DeviceArray] = None):
+                      alt: Optional[DeviceArray] = None, spans: Optional[list] = None):
         """Apply ``ops`` in order, several gates per HBM sweep.  Runs of >= MIN_SWAP_RUN uncontrolled SWAP gates (the
         bit reversal ending a QFT) become ONE out-of-place permutation sweep when a scratch buffer fits in memory.
-        Returns the planner/timing statistics."""
+        Returns the planner/timing statistics.  ``timed``: CUDA-event time per segment, read back at once (the host waits
+        for the GPU); ``spans``: a list that receives (kind, event0, event1, launches) per segment instead -- nothing
+        waits, the caller reads the events after its own synchronisation."""
         total = _lib.QbProgramStats()
         total.nops = len(ops)
         total.perm_ms, total.nperm = 0.0, 0  # K8 launches inside this program (reported apart from the sweep kernel)
@@ -190,7 +196,7 @@ class Engine:
         for kind, payload in segments:
             if kind == "perm":
                 try:
-                    ms = self.permute_qubits(state, nqubits, payload, timed=timed, alt=alt)
+                    ms = self.permute_qubits(state, nqubits, payload, timed=timed, alt=alt, spans=spans)
                 except torch.cuda.OutOfMemoryError:
                     ms = None
                     payload = swaps_for_permutation(payload)
@@ -203,7 +209,10 @@ class Engine:
                     total.perm_ms += ms or 0.0
                     total.nperm += 1
                     continue
+            e0 = _record_event() if spans is not None else None
             st = self._apply_sweeps(state, nqubits, payload, fuse, timed)
+            if e0 is not None:
+                spans.append(("sweep", e0, _record_event(), st.nsweeps))
             total.nsweeps += st.nsweeps
             total.ndense_passes += st.ndense_passes
             total.ndiag_ops += st.ndiag_ops
@@ -222,8 +231,10 @@ class Engine:
         ``run_program`` then costs kernel launches only -- no canonicalisation, planning or program upload per call."""
         return CompiledProgram(self, nqubits, dtype, ops, fuse)
 
-    def run_program(self, prog: "CompiledProgram", state: DeviceArray, timed: bool = False, alt: Optional[DeviceArray] = None):
-        """Apply a compiled program to ``state`` (same nqubits / dtype / device as it was compiled for)."""
+    def run_program(self, prog: "CompiledProgram", state: DeviceArray, timed: bool = False, alt: Optional[DeviceArray] = None,
+                    spans: Optional[list] = None):
+        """Apply a compiled program to ``state`` (same nqubits / dtype / device as it was compiled for).  ``timed`` /
+        ``spans`` as in ``apply_program``."""
         if np.dtype(state.dtype) != prog.dtype or state.size != (1 << prog.nqubits):
             raise ValueError(f"program compiled for {prog.nqubits} qubits of {prog.dtype}, got a state of {state.size} x {state.dtype}")
         total = _lib.QbProgramStats()
@@ -233,7 +244,7 @@ class Engine:
         for kind, payload in prog.segments:
             if kind == "perm":
                 try:
-                    ms = self.permute_qubits(state, prog.nqubits, payload, timed=timed, alt=alt)
+                    ms = self.permute_qubits(state, prog.nqubits, payload, timed=timed, alt=alt, spans=spans)
                 except torch.cuda.OutOfMemoryError:  # no room for the scratch buffer: in place, as SWAP gates
                     st = self._apply_sweeps(state, prog.nqubits, swaps_for_permutation(payload), True, timed)
                     total.nsweeps += st.nsweeps
@@ -248,7 +259,10 @@ class Engine:
                 total.nperm += 1
                 continue
             st = _lib.QbProgramStats()
+            e0 = _record_event() if spans is not None else None
             _lib.check(self.lib.qb_program_run(self.handle, payload, state.data_ptr(), flags, ctypes.byref(st)))
+            if e0 is not None:
+                spans.append(("sweep", e0, _record_event(), st.nsweeps))
             total.nsweeps += st.nsweeps
             total.ndense_passes += st.ndense_passes
             total.ndiag_ops += st.ndiag_ops
@@ -366,10 +380,31 @@ class Engine:
         fn = self.lib.qb_alltoall_push_p2p if push else self.lib.qb_alltoall_p2p
         _lib.check(fn(self.handle, state.data_ptr(), _DT[state.dtype], k, ptrs, *cols))
 
+    def memcpy_async(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: int = 0):
+        """Device-to-device DMA copy (also across peer-mapped buffers) on ``stream`` (a cudaStream_t; 0 = the engine's)."""
+        _lib.check(self.lib.qb_memcpy_async(self.handle, ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), int(nbytes), 2,
+                                            ctypes.c_void_p(stream or None)))
+
     def mem_info(self):
         free, total = ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(self.lib.qb_mem_info(self.handle, ctypes.byref(free), ctypes.byref(total)))
         return free.value, total.value
+
+
+def _record_event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def resolve_spans(spans):
+    """-> {"sweep": (ms, launches), "perm": (ms, launches), ...} of a span list (waits for the last event of each)."""
+    out = {}
+    for kind, e0, e1, count in spans:
+        e1.synchronize()
+        ms, n = out.get(kind, (0.0, 0))
+        out[kind] = (ms + e0.elapsed_time(e1), n + count)
+    return out
 
 
 class _RawCuda:

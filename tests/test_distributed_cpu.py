@@ -399,13 +399,13 @@ class _FakeEngine:
 
         return SimpleNamespace(nsweeps=1, elapsed_ms=0.5, perm_ms=0.0, nperm=0, nops=len(ops))
 
-    def run_program(self, prog, state, timed=False, alt=None):
+    def run_program(self, prog, state, timed=False, alt=None, spans=None):
         assert alt is None  # only peer-memory shards carry a second buffer
         _oracle_apply(state.tensor, prog.nqubits, prog.ops)
         self.launched += 1
         return self._stats(prog.ops)
 
-    def apply_program(self, state, nqubits, ops, timed=False, alt=None):
+    def apply_program(self, state, nqubits, ops, timed=False, alt=None, spans=None):
         _oracle_apply(state.tensor, nqubits, ops)
         self.applied += 1
         return self._stats(ops)
@@ -429,7 +429,10 @@ def _engine_worker(rank, world, port, n, out):
         state = SimpleNamespace(tensor=torch.from_numpy(prog.shard_of(psi).copy()))
         s1 = prog.run(state)  # compiles every local segment once ...
         s2 = prog.run(state, timed=False)  # ... and only launches afterwards
-        nlocal_segments = sum(1 for seg in prog.segments if seg[0] == "local" and seg[1])
+        # (the tail of a local segment that would ride on a chunk-pipelined exchange runs as a program of its own on
+        # transports without peer memory)
+        nlocal_segments = sum(1 for seg in prog.segments if seg[0] == "local" and seg[1]) + sum(
+            1 for seg in prog.segments if seg[0] == "exchange" and seg[4] is not None and seg[4].nlocal_ops)
         assert eng.compiled == nlocal_segments and eng.launched == 2 * nlocal_segments and eng.applied == 0
         s3 = prog.run(state, timed=False, compiled=False)  # the e2e leg: host gate matrices on every call
         assert eng.applied == nlocal_segments and eng.compiled == nlocal_segments
@@ -642,3 +645,50 @@ def test_sharded_measurement_matches_oracle(world):
     err, mismatch = out.get()
     assert err < 1e-12
     assert mismatch <= 2  # a uniform within rounding of a rank boundary of the CDF may land on the neighbouring bin
+
+
+def test_pipelined_exchange_splits_the_qft():
+    """What the chunk pipeline does to the sharded QFT: the sweeps after the first one touch none of the leading local
+    qubits, so they ride on the exchange chunk by chunk (host logic; the numbers are checked above)."""
+    from qibo_b200 import circuits
+    from qibo_b200.distributed import ShardedProgram
+
+    prog = ShardedProgram(None, 24, "complex128", circuits.qft(24), global_qubits="auto", world_=8, rank_=5)
+    kinds = [seg[0] for seg in prog.segments]
+    assert kinds.count("exchange") == 1
+    x = prog.segments[kinds.index("exchange")]
+    assert len(x[1]) == 3 and x[4] is not None and len(x[4].ops) > 100
+    assert all(min(op.targets + op.controls) >= 0 for op in x[4].ops)
+    head = prog.segments[kinds.index("exchange") - 1][1]
+    assert len(head) > 0
+
+
+@pytest.mark.parametrize("case,n,world", [("qft", 17, 8), ("qft", 15, 2), ("variational", 16, 4), ("zoo", 16, 4)])
+def test_pipelined_tail_is_chunk_separable(case, n, world):
+    """The ops that ride on a chunk-pipelined exchange, applied chunk by chunk in the chunk's own qubit numbering, equal
+    the same ops applied to the whole shard (oracle arithmetic, every rank)."""
+    sys.path[:0] = [ROOT, HERE]
+    from helpers import ops_from_named, oracle_run, rand_state, random_zoo
+    from oracle import numpy_oracle as orc
+    from qibo_b200.distributed import ShardedProgram
+
+    if case == "qft":
+        ops = ops_from_named(orc.qft_ops(n))
+    elif case == "variational":
+        ops = ops_from_named(orc.variational_ops(n, 3, np.random.default_rng(1).random(6 * n) * 6))
+    else:
+        ops = random_zoo(n, 60, 5, max_dense=3)
+    seen = 0
+    for r in range(world):
+        prog = ShardedProgram(None, n, "complex128", ops, global_qubits="auto", world_=world, rank_=r)
+        for seg in prog.segments:
+            if seg[0] != "exchange" or seg[4] is None or not seg[4].ops:
+                continue
+            k, nl = len(seg[1]), prog.nlocal
+            psi = rand_state(nl, 3 + r)
+            whole = oracle_run(psi, seg[4].nlocal_ops, nl)
+            csz = 1 << (nl - k)
+            parts = [oracle_run(psi[c * csz : (c + 1) * csz].copy(), seg[4].ops, nl - k) for c in range(1 << k)]
+            assert np.abs(np.concatenate(parts) - whole).max() < 1e-13
+            seen += 1
+    assert seen > 0 or case != "qft"  # (layered circuits touch every qubit in every sweep: nothing to pipeline)

@@ -261,3 +261,64 @@ def test_execute_distributed_circuit_dropin():
     err, diff = out.get()
     assert err < 1e-12
     assert diff <= 4  # a uniform within rounding of a CDF edge may move one shot to the neighbouring outcome
+
+
+# ---------------------------------------------------------------------------------------- one GPU, all shards
+def _group_case(case, n):
+    from helpers import ops_from_named, random_zoo
+    from oracle import numpy_oracle as orc
+
+    if case == "qft":
+        return ops_from_named(orc.qft_ops(n))
+    if case == "variational":
+        return ops_from_named(orc.variational_ops(n, 2, np.random.default_rng(1).random(4 * n) * 6))
+    return random_zoo(n, 50, 5, max_dense=4)
+
+
+_GROUP_COMBOS = [("qft", 18, "complex128", w, "auto", t) for w in (2, 4, 8) for t in ("pipelined", "push", "inplace", "pairwise")] + [
+    ("qft", 19, "complex64", 8, "auto", "pipelined"), ("qft", 19, "complex64", 4, None, "push"),
+    ("variational", 17, "complex64", 4, "auto", "pipelined"), ("variational", 17, "complex64", 2, None, "inplace"),
+    ("zoo", 17, "complex128", 8, "auto", "pipelined"), ("zoo", 17, "complex128", 4, None, "pairwise"),
+    ("zoo", 17, "complex128", 2, "auto", "push"), ("qft", 18, "complex128", 8, None, "pipelined"),
+    ("qft", 18, "complex128", 4, None, "inplace"),
+]
+_REFS = {}
+
+
+def _group_reference(case, n, dtype):
+    from helpers import oracle_run, rand_state
+
+    key = (case, n, dtype)
+    if key not in _REFS:
+        ops = _group_case(case, n)
+        psi = rand_state(n, 11, dtype)
+        ref = oracle_run(psi, ops, n)
+        _REFS[key] = (ops, psi, ref, oracle_run(ref, ops, n))
+    return _REFS[key]
+
+
+@pytest.mark.parametrize("case,n,dtype,world,layout,transport", _GROUP_COMBOS)
+def test_all_shards_on_one_gpu(case, n, dtype, world, layout, transport):
+    """Multi-GPU parity on a ONE-GPU box: all W shards of the register live on device 0 and every "rank" runs its own plan
+    (distributed.SingleDeviceGroup) -- Plan, per-rank specialisation, compiled local programs, the REAL exchange kernels
+    (k7_alltoall_push, k7_alltoall_p2p, k7_swap_half_p2p) and the chunk-pipelined DMA exchange, with the sibling shards'
+    buffers as peer pointers -- against the oracle on the gathered state.  Run twice: the second run starts from the
+    flipped buffers and sends the host gate matrices in again (the uncompiled path)."""
+    from qibo_b200.distributed import SingleDeviceGroup
+    from qibo_b200.engine import Engine
+
+    eng = Engine(0)
+    ops, psi, ref, ref2 = _group_reference(case, n, dtype)
+    grp = SingleDeviceGroup(eng, n, world, dtype, ops, global_qubits=layout)
+    grp.configure(pipeline=transport == "pipelined", alltoall_push=transport in ("pipelined", "push"), alltoall=transport != "pairwise")
+    grp.scatter(psi)
+    stats = grp.run()
+    t = 1e-12 if dtype == "complex128" else 1e-5
+    assert np.abs(grp.gather() - ref).max() < t
+    nex = grp.programs[0].plan.nexchanges
+    assert all(s.nexchanges == nex for s in stats)
+    if transport == "pipelined" and case == "qft" and layout == "auto":
+        assert all(s.pipelined == 1 and s.nchunk_sweeps > 0 for s in stats)
+    grp.scatter(ref)
+    grp.run(compiled=False)
+    assert np.abs(grp.gather() - ref2).max() < t

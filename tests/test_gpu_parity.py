@@ -166,6 +166,37 @@ def test_qft_full_size_properties(eng, n, dtype):
         assert float((st2.tensor - (0.3 - 0.4j) * st.tensor).abs().max()) < tol(dtype)
 
 
+@pytest.mark.parametrize("n,dtype", [(30, "complex128"), (32, "complex128"), (31, "complex64")])
+@pytest.mark.parametrize("path", ["apply_program", "compiled"])
+def test_qft_basis_state_closed_form_at_bench_size(eng, n, dtype, path):
+    """BASELINE config 2 (QFT(30)) and the benchmarked QFT(32), phase-sensitive and on EVERY amplitude: QFT of a generic
+    basis state |x> against exp(2 pi i x k / 2^n) / sqrt(2^n), evaluated on the device in int64 / float64 chunks
+    (qibo_b200/checks.py, itself pinned to the oracle on the CPU).  From |0...0> no CU1 ever fires; from |x> every one of
+    the n(n+1)/2 + n/2 gates acts (models/qft.py:47-58).  Both the host-matrix path (qb_apply_program) and the compiled
+    program (qb_program_create / qb_program_run) that bench.py times."""
+    from qibo_b200 import circuits
+    from qibo_b200.checks import generic_basis_state, qft_basis_state_error
+
+    free, _ = eng.mem_info()
+    itemsize = 16 if dtype == "complex128" else 8
+    if free < 2.2 * itemsize * 2**n:
+        pytest.skip("needs the state plus the permutation buffer in device memory")
+    ops = circuits.qft(n)
+    x = generic_basis_state(n)
+    st = eng.basis_state(n, dtype, x)
+    if path == "compiled":
+        prog = eng.compile(n, dtype, ops)
+        eng.run_program(prog, st)
+    else:
+        eng.apply_program(st, n, ops)
+    err = qft_basis_state_error(st.tensor, n, x)
+    # relative to the amplitude size 2^(-n/2): 1e-10 is ~1e-15 absolute at n = 30, far inside the 1e-12 north-star bound
+    assert err < (1e-10 if dtype == "complex128" else 2e-3), err
+    assert abs(eng.norm2(st) - 1.0) < (1e-9 if dtype == "complex128" else 1e-4)
+    del st
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("case,n,dtype", [("variational", 27, "complex64"), ("random", 26, "complex128"), ("variational", 25, "complex128"),
                                           ("random", 27, "complex64")])
 def test_scheduled_sweeps_match_gate_by_gate_at_scale(eng, case, n, dtype):
@@ -457,3 +488,40 @@ def test_pauli_expectation_and_vdot(eng, dtype):
         eng.expval_pauli(st, n, "XQ", [0, 1])
     with pytest.raises(ValueError):
         eng.expval_pauli(st, n, "XX", [1, 1])
+
+
+def test_one_backend_entered_from_two_threads(eng):
+    """parallel.py:53 runs one backend object from joblib THREADS: two threads drive the same engine (one context, one
+    stream, per-context mutex in the library) on their own states at once -- every result must equal the single-threaded
+    one bit for bit."""
+    import threading
+
+    from qibo_b200 import circuits
+
+    n = 18
+    progs = [circuits.qft(n), random_zoo(n, 40, 3), circuits.variational(n, 2, np.random.default_rng(3).random(4 * n))]
+    psis = [rand_state(n, s) for s in range(3)]
+    want = [run_k2(eng, psi, ops, n) for psi, ops in zip(psis, progs)]
+    wantp = [eng.probabilities(eng.upload(w), [0, 3, 5], n).numpy() for w in want]
+    errors = []
+
+    def work(i, reps):
+        try:
+            for _ in range(reps):
+                st = eng.upload(psis[i])
+                eng.apply_program(st, n, progs[i])
+                if not np.array_equal(st.numpy(), want[i]):
+                    errors.append(("state", i))
+                if not np.array_equal(eng.probabilities(st, [0, 3, 5], n).numpy(), wantp[i]):
+                    errors.append(("probs", i))
+                u = np.random.default_rng(i).random(64)
+                eng.sample(eng.probabilities(st, list(range(n)), n), u)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=work, args=(i % 3, 6)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors[:3]
