@@ -164,6 +164,13 @@ int qb_sample(qb_handle h, const void* probs, int rdtype, uint64_t nbins, const 
 int qb_collapse(qb_handle h, void* state, int nqubits, int dtype, const int* qubits, int nmeasured,
                 uint64_t outcome, int normalize);
 
+/* Density matrices (rho: flat 2^n x 2^n row-major array on the device).  qb_probabilities_dm replaces the density-matrix
+ * branch of Backend.calculate_probabilities (backends/abstract.py:2741-2749): |sum of the diagonal over the unmeasured
+ * qubits|, bins in the caller's qubit order, real dtype of the state.  qb_collapse_dm replaces
+ * Backend._collapse_density_matrix (abstract.py:3249-3277): rows and columns projected on `outcome`, divided by the trace. */
+int qb_probabilities_dm(qb_handle h, const void* rho, int nqubits, int dtype, const int* qubits, int nmeasured, void* probs_out);
+int qb_collapse_dm(qb_handle h, void* rho, int nqubits, int dtype, const int* qubits, int nmeasured, uint64_t outcome, int normalize);
+
 /* ---- K9: expectation values without leaving the device (abstract.py:2946-3054 exp_value_observable_symbolic: the
  * einsum contraction of one Pauli term with the state; abstract.py:2180-2190 overlap_statevector) --------------------
  * <psi| P |psi> for the Pauli string `paulis` (characters I, X, Y, Z; paulis[i] acts on qubits[i]): one read pass over

@@ -76,6 +76,8 @@ PROTOTYPES = {
     "qb_sample_cdf": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_void_p]),
     "qb_sample": (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_uint64, c_void_p, c_int, POINTER(c_double)]),
     "qb_collapse": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_uint64, c_int]),
+    "qb_probabilities_dm": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p]),
+    "qb_collapse_dm": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_uint64, c_int]),
     "qb_pack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qb_unpack_half": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qb_swap_half_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -28,6 +28,7 @@ from qibo import __version__ as qibo_version
 from qibo.backends.numpy import NumpyBackend
 from qibo.config import SHOT_BATCH_SIZE, log, raise_error
 from qibo.gates.abstract import Gate
+from qibo.gates.special import FusedGate
 from qibo.result import CircuitResult, MeasurementOutcomes, QuantumState
 
 from qibo_b200 import _lib
@@ -62,6 +63,20 @@ class B200Backend(NumpyBackend):
         self.engine_gpu = self._engine(index)  # raises without a CUDA device: there is no CPU path
         if dtype != self.dtype:
             self.set_dtype(dtype)
+
+    @property
+    def exact_sampling(self):
+        """True: shot sampling keeps NumPy's sequential-cumsum CDF (bit-identical to np.random.choice) for ANY number of
+        bins; default: up to 2^22 bins, the parallel scan above (SURVEY 8a hazard 1: about 1e2 of 1e6 samples may then
+        land in a neighbouring bin at 2^30 bins; the sequential scan costs seconds there)."""
+        return self.engine_gpu.exact_scan_max_bins >= (1 << 62)
+
+    @exact_sampling.setter
+    def exact_sampling(self, on):
+        from qibo_b200.engine import EXACT_SCAN_MAX_BINS
+
+        for eng in self._engines.values():
+            eng.exact_scan_max_bins = (1 << 62) if on else EXACT_SCAN_MAX_BINS
 
     # ------------------------------------------------------------------ configuration -------------
     @staticmethod
@@ -124,9 +139,13 @@ class B200Backend(NumpyBackend):
         """Accept a DeviceArray / ndarray / list state -> complex DeviceArray on this backend's GPU."""
         eng = self.engine_gpu
         if isinstance(state, DeviceArray):
+            if state.tensor.device != eng.device:
+                # a state made on another GPU (set_device since, or another rank's): move it rather than hand a foreign
+                # pointer to this device's kernels
+                state = DeviceArray(state.tensor.to(eng.device))
             if state.dtype.kind == "c":
                 return state
-            return eng.upload(state.numpy().astype(np.complex128 if state.dtype == np.float64 else np.complex64))
+            return DeviceArray(state.tensor.to(torch.complex128 if state.dtype == np.float64 else torch.complex64))
         host = np.asarray(state)
         if host.dtype.kind != "c":
             host = host.astype(np.complex64 if host.dtype == np.float32 else np.complex128)
@@ -159,13 +178,13 @@ class B200Backend(NumpyBackend):
     def minus_state(self, nqubits, density_matrix=False, dtype=None):
         self._validate_nqubits(nqubits, density_matrix=density_matrix)
         # |-> on every qubit = Z on every qubit of |+...+>
-        state = self.plus_state(nqubits, density_matrix=False, dtype=dtype)
+        # (density matrix: |-><-| on every qubit = Z on every row AND column qubit of the all-equal matrix)
+        n = 2 * nqubits if density_matrix else nqubits
+        state = self.plus_state(nqubits, density_matrix=density_matrix, dtype=dtype)
+        flat = state.reshape(-1) if density_matrix else state
         z = np.array([1, -1], dtype=np.complex128)
-        ops = [Op(z, (q,), is_diagonal=True) for q in range(nqubits)]
-        self.engine_gpu.apply_program(state, nqubits, ops)
-        if density_matrix:
-            host = state.numpy()
-            return self.engine_gpu.upload(np.outer(host, host.conj()))
+        ops = [Op(z, (q,), is_diagonal=True) for q in range(n)]
+        self.engine_gpu.apply_program(flat, n, ops)
         return state
 
     # ------------------------------------------------------------------ gate -> Op ---------------------
@@ -174,6 +193,11 @@ class B200Backend(NumpyBackend):
         gate.qubits (the library recovers the control structure exactly); `controlled_by` gates arrive as
         target matrix + controls (abstract.py:3176-3197).  Density matrices are 2n-qubit vectors: U on the
         row qubits, conj(U) on the column qubits (abstract.py:2341-2348)."""
+        if isinstance(gate, FusedGate):
+            # circuit.fuse() blocks (gates/special.py:28-157): the member gates go to the sweep planner one by one -- it
+            # packs them into the same HBM sweep anyway, and neither the host-side scipy product of matrix_fused
+            # (abstract.py:2680-2717, ~0.5 ms per block) nor a dense complex 2^r x 2^r multiply per amplitude is paid
+            return [op for member in gate.gates for op in self._gate_ops(member, nqubits, density_matrix)]
         matrix = np.asarray(gate.matrix(self))
         if gate.is_controlled_by:
             targets, controls = tuple(gate.target_qubits), tuple(gate.control_qubits)
@@ -433,10 +457,9 @@ class B200Backend(NumpyBackend):
     # ------------------------------------------------------------------ P1: probabilities ------------------
     def calculate_probabilities(self, state, qubits, nqubits, density_matrix=False):
         qubits = [int(q) for q in qubits]
-        if density_matrix:
-            # diag(rho) marginal: host path of the reference on the (small) matrix -- X1 is outside the BASELINE configs
-            return super().calculate_probabilities(self.cast(state, dtype=state.dtype), qubits, nqubits, density_matrix=True)
         dev = self._to_device(state)
+        if density_matrix:
+            return self.engine_gpu.probabilities_dm(dev.reshape(-1), qubits, nqubits)
         return self.engine_gpu.probabilities(dev, qubits, nqubits)
 
     # ------------------------------------------------------------------ S1/S2: sampling ----------------------
@@ -463,17 +486,22 @@ class B200Backend(NumpyBackend):
         return samples
 
     def sample_frequencies(self, probabilities, nshots):
-        """abstract.py:2760-2772: renormalise, draw in 2^18 batches from one RNG stream, histogram.
-        The histogram is built from the (host) sample vector -- no 2^m-entry Python loop."""
+        """abstract.py:2760-2772: draws in 2^18 batches from one RNG stream (consecutive batches consume consecutive
+        uniforms, so this equals one draw of nshots), histogram.  The CDF is built ONCE on the device and every batch is a
+        search in it; it is normalised by its last entry inside the scan (the reference divides by the pairwise sum first
+        and by cdf[-1] again inside np.random.choice -- the same bins except for uniforms within an ulp of an edge).  The
+        histogram is built from the (host) sample vector -- no 2^m-entry Python loop."""
         probs = self._probs_to_device(probabilities)
         nshots = int(nshots)
+        eng = self.engine_gpu
+        cdf = eng.cdf(probs)
         freqs = Counter()
         batches = (nshots // SHOT_BATCH_SIZE) * [SHOT_BATCH_SIZE] + [nshots % SHOT_BATCH_SIZE]
         for b in batches:
             if b == 0:
                 continue
-            uniforms = np.random.random_sample(b)
-            freqs.update(frequencies_from_samples(self.engine_gpu.sample(probs, uniforms)))
+            uniforms = eng.upload(np.random.random_sample(b))
+            freqs.update(frequencies_from_samples(eng.sample_cdf(cdf, uniforms).numpy()))
         return Counter({int(k): int(v) for k, v in sorted(freqs.items())})
 
     def calculate_frequencies(self, samples):
@@ -483,11 +511,11 @@ class B200Backend(NumpyBackend):
 
     # ------------------------------------------------------------------ C1: collapse ----------------------------
     def collapse_state(self, state, qubits, shot, nqubits, normalize=True, density_matrix=False):
-        if density_matrix:
-            out = super().collapse_state(self.cast(state, dtype=state.dtype), list(qubits), shot, nqubits, normalize, True)
-            return self.engine_gpu.upload(out)
         dev = self._to_device(state)
         outcome = int(np.asarray(shot).ravel()[0])
+        if density_matrix:
+            self.engine_gpu.collapse_dm(dev.reshape(-1), nqubits, [int(q) for q in qubits], outcome, normalize)
+            return dev
         self.engine_gpu.collapse(dev, nqubits, [int(q) for q in qubits], outcome, normalize)
         return dev
 

@@ -937,6 +937,82 @@ int qb_collapse(qb_handle h, void* state, int nqubits, int dtype, const int* qub
 }
 
 // ---------------------------------------------------------------------------------------------------
+// X1: density-matrix probabilities and collapse
+// ---------------------------------------------------------------------------------------------------
+int qb_probabilities_dm(qb_handle h, const void* rho, int nqubits, int dtype, const int* qubits, int nmeasured, void* probs_out) {
+  if (!h || !rho || !probs_out || nqubits < 1 || 2 * nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128))
+    return fail(QB_ERR_INVALID, "bad density-matrix arguments");
+  if (nmeasured < 0 || nmeasured > nqubits || (nmeasured && !qubits)) return fail(QB_ERR_INVALID, "bad measured qubits");
+  DmProbParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = nqubits;
+  p.m = nmeasured;
+  uint64_t mmask = 0;
+  for (int i = 0; i < nmeasured; ++i) {
+    const int q = qubits[i];
+    if (q < 0 || q >= nqubits) return fail(QB_ERR_INVALID, "measured qubit out of range");
+    const int pos = nqubits - 1 - q;
+    if ((mmask >> pos) & 1) return fail(QB_ERR_INVALID, "repeated measured qubit");
+    mmask |= uint64_t(1) << pos;
+    p.pos[i] = (uint8_t)pos;
+  }
+  p.umask = ((uint64_t(1) << nqubits) - 1) & ~mmask;
+  p.n_u = nqubits - nmeasured;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  const uint64_t nbins = uint64_t(1) << nmeasured;
+  const unsigned grid = (unsigned)((nbins * 32 + 255) / 256);
+  if (dtype == QB_C128) k3_probs_dm<double2, double><<<grid, 256, 0, h->stream>>>((const double2*)rho, (double*)probs_out, p);
+  else k3_probs_dm<float2, float><<<grid, 256, 0, h->stream>>>((const float2*)rho, (float*)probs_out, p);
+  QB_CHECK_LAUNCH("k3_probs_dm");
+  return QB_OK;
+}
+
+int qb_collapse_dm(qb_handle h, void* rho, int nqubits, int dtype, const int* qubits, int nmeasured, uint64_t outcome, int normalize) {
+  if (!h || !rho || nqubits < 1 || 2 * nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128))
+    return fail(QB_ERR_INVALID, "bad density-matrix arguments");
+  if (nmeasured < 1 || nmeasured > nqubits || !qubits) return fail(QB_ERR_INVALID, "bad measured qubits");
+  if (outcome >> nmeasured) return fail(QB_ERR_INVALID, "outcome out of range");
+  uint64_t mask = 0, val = 0;
+  std::vector<int> pos;
+  for (int i = 0; i < nmeasured; ++i) {
+    const int q = qubits[i];
+    if (q < 0 || q >= nqubits) return fail(QB_ERR_INVALID, "measured qubit out of range");
+    const int p = nqubits - 1 - q;
+    if ((mask >> p) & 1) return fail(QB_ERR_INVALID, "repeated measured qubit");
+    mask |= uint64_t(1) << p;
+    if ((outcome >> (nmeasured - 1 - i)) & 1) val |= uint64_t(1) << p;
+    pos.push_back(p);
+  }
+  std::sort(pos.begin(), pos.end());
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  const uint64_t ngroups = uint64_t(1) << (nqubits - nmeasured);
+  const int grid = grid_for(ngroups, RED_THREADS, h->sm_count, 8);
+  int rc = ensure_scratch(h, (size_t)(2 * grid + 8) * sizeof(double));
+  if (rc != QB_OK) return rc;
+  double* partial = (double*)h->scratch + 8;
+  double* trace = (double*)h->scratch;
+  if (normalize) {
+    InsertList ins;
+    ins.n = nmeasured;
+    for (int i = 0; i < nmeasured; ++i) ins.pos[i] = (uint8_t)pos[i];
+    if (dtype == QB_C128) k5_diag_slice_sum<double2><<<grid, RED_THREADS, 0, h->stream>>>((const double2*)rho, nqubits, ngroups, ins, val, partial, partial + grid);
+    else k5_diag_slice_sum<float2><<<grid, RED_THREADS, 0, h->stream>>>((const float2*)rho, nqubits, ngroups, ins, val, partial, partial + grid);
+    QB_CHECK_LAUNCH("k5_diag_slice_sum");
+    k9_sum_partials2<<<1, 32, 0, h->stream>>>(partial, partial + grid, grid, trace);
+    QB_CHECK_LAUNCH("k9_sum_partials2");
+  }
+  const uint64_t count = uint64_t(1) << (2 * nqubits);
+  const uint64_t mask2 = (mask << nqubits) | mask, val2 = (val << nqubits) | val;
+  const int g2 = grid_for(count, 256, h->sm_count);
+  if (dtype == QB_C128) k5_project_dm<double2><<<g2, 256, 0, h->stream>>>((double2*)rho, count, mask2, val2, trace, normalize);
+  else k5_project_dm<float2><<<g2, 256, 0, h->stream>>>((float2*)rho, count, mask2, val2, trace, normalize);
+  QB_CHECK_LAUNCH("k5_project_dm");
+  return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K7 plumbing (exchange kernels live in qb_sweep.cuh)
 // ---------------------------------------------------------------------------------------------------
 int qb_pack_half(qb_handle h, const void* state, int nqubits, int dtype, int local_qubit, int bit, void* staging) {

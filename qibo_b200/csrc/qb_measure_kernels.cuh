@@ -286,6 +286,75 @@ __global__ void __launch_bounds__(256) k5_project(C* __restrict__ state, uint64_
   }
 }
 
+// ---- X1: density matrices (rho as a flat 2^n x 2^n row-major array) --------------------------------------------------
+// calculate_probabilities(density_matrix=True) (abstract.py:2741-2749): abs(sum of the diagonal over the unmeasured
+// qubits), bins in the caller's qubit order.  One warp per bin; density matrices are small (n <= ~15).
+struct DmProbParams {
+  int n, m;
+  uint64_t umask;       // unmeasured bit positions of the row index
+  int n_u;
+  uint8_t pos[48];      // bit position of measured qubit i (caller order: qubit 0 of the list = MSB of the bin)
+};
+template <typename C, typename R>
+__global__ void __launch_bounds__(256) k3_probs_dm(const C* __restrict__ rho, R* __restrict__ out, const __grid_constant__ DmProbParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t bin = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (bin >> p.m) return;
+  uint64_t base = 0;
+  for (int i = 0; i < p.m; ++i) base |= ((bin >> (p.m - 1 - i)) & 1ull) << p.pos[i];
+  const uint64_t diag = (uint64_t(1) << p.n) + 1;
+  double re = 0.0, im = 0.0;
+  for (uint64_t u = lane; u < (uint64_t(1) << p.n_u); u += 32) {
+    const C v = rho[(base | deposit(u, p.umask)) * diag];
+    re += (double)v.x;
+    im += (double)v.y;
+  }
+  re = warp_sum(re);
+  im = warp_sum(im);
+  if (lane == 0) out[bin] = (R)hypot(re, im);
+}
+
+// _collapse_density_matrix (abstract.py:3249-3277): keep the block whose row AND column bits equal the outcome, divide by
+// its (complex) trace, zero everything else.
+template <typename C>
+__global__ void __launch_bounds__(RED_THREADS) k5_diag_slice_sum(const C* __restrict__ rho, int n, uint64_t ngroups, InsertList ins, uint64_t val,
+                                                                 double* __restrict__ partial_re, double* __restrict__ partial_im) {
+  __shared__ double sm[RED_THREADS / 32];
+  double re = 0.0, im = 0.0;
+  const uint64_t diag = (uint64_t(1) << n) + 1;
+  const uint64_t stride = uint64_t(gridDim.x) * RED_THREADS;
+  for (uint64_t g = uint64_t(blockIdx.x) * RED_THREADS + threadIdx.x; g < ngroups; g += stride) {
+    const C v = rho[(expand(g, ins) | val) * diag];
+    re += (double)v.x;
+    im += (double)v.y;
+  }
+  const double r = block_sum<RED_THREADS>(re, sm);
+  const double i = block_sum<RED_THREADS>(im, sm);
+  if (threadIdx.x == 0) {
+    partial_re[blockIdx.x] = r;
+    partial_im[blockIdx.x] = i;
+  }
+}
+template <typename C>
+__global__ void __launch_bounds__(256) k5_project_dm(C* __restrict__ rho, uint64_t count, uint64_t mask, uint64_t val, const double* __restrict__ trace,
+                                                     int normalize) {
+  typedef typename real_of<C>::type R;
+  const double tr = trace[0], ti = trace[1];
+  const double den = tr * tr + ti * ti;
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    if ((i & mask) == val) {
+      if (normalize) {
+        const C v = rho[i];
+        const double x = (double)v.x, y = (double)v.y;
+        rho[i] = cmake<C>((R)((x * tr + y * ti) / den), (R)((y * tr - x * ti) / den));
+      }
+    } else {
+      rho[i] = cmake<C>(0, 0);
+    }
+  }
+}
+
 // ---- K9: <psi| P |psi> for a Pauli string, and <a|b> ------------------------------------------------------------------
 // P|x> = i^{nY} (-1)^{popcount(x & zmask)} |x ^ xmask>  (xmask: bits with X or Y, zmask: bits with Z or Y), so
 // <psi|P|psi> = i^{nY} sum_x (-1)^{popcount(x & zmask)} conj(psi[x ^ xmask]) psi[x]: one read pass over the state (the

@@ -14,12 +14,16 @@ import torch
 
 from qibo_b200 import _lib
 from qibo_b200.array import DeviceArray, torch_dtype
-from qibo_b200.ops import Op, pack_ops
+from qibo_b200.ops import Op, is_wide, pack_ops
 
 _DT = {np.dtype("complex64"): _lib.QB_C64, np.dtype("complex128"): _lib.QB_C128}
 _RT = {np.dtype("float32"): _lib.QB_F32, np.dtype("float64"): _lib.QB_F64}
-# NumPy's exact-scan contract is kept up to this many bins; beyond it the parallel scan is used
-EXACT_SCAN_MAX_BINS = 1 << 22
+import os
+
+# NumPy's exact-scan contract (sequential float64 cumsum, bit-identical to np.random.choice) is kept up to this many
+# bins; beyond it the parallel scan is used unless the caller opts in (Engine.exact_scan_max_bins, env
+# QB_EXACT_SCAN_MAX_BINS, B200Backend.exact_sampling): the sequential scan costs ~4 ns per bin (seconds at 2^30 bins)
+EXACT_SCAN_MAX_BINS = int(os.environ.get("QB_EXACT_SCAN_MAX_BINS", 1 << 22))
 
 
 def _int_array(values):
@@ -47,8 +51,19 @@ class Engine:
         handle = ctypes.c_void_p()
         _lib.check(self.lib.qb_create(self.device_index, ctypes.c_void_p(stream), ctypes.byref(handle)))
         self.handle = handle
+        self._stream = stream
         self.last_stats = None
         self.permute_swap_runs = True
+        self.exact_scan_max_bins = EXACT_SCAN_MAX_BINS
+
+    def bind_current_stream(self):
+        """Follow torch's current stream (``with torch.cuda.stream(s):``): the library's kernels and torch's copies /
+        allocations of the same buffers must be ordered on ONE stream.  Called at the top of every entry point; a no-op
+        unless the current stream changed since the last call."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        if stream != self._stream:
+            _lib.check(self.lib.qb_set_stream(self.handle, ctypes.c_void_p(stream)))
+            self._stream = stream
 
     def close(self):
         if getattr(self, "handle", None):
@@ -114,6 +129,9 @@ class Engine:
 
     # ---- K1: one gate ---------------------------------------------------------------------------
     def apply_op(self, state: DeviceArray, nqubits: int, op: Op) -> DeviceArray:
+        self.bind_current_stream()
+        if is_wide(op):
+            return self.apply_wide(state, nqubits, op)
         if len(op.targets) > 5 and not op.is_diagonal:
             # the one-gate kernels hold 2^k amplitudes per thread (k <= 5); 6-qubit blocks go through the sweep kernel
             self._apply_sweeps(state, nqubits, [op], True, False)
@@ -127,8 +145,39 @@ class Engine:
         )
         return state
 
+    def apply_wide(self, state: DeviceArray, nqubits: int, op: Op) -> DeviceArray:
+        """A block on k > 6 targets (the reference takes a Unitary of any width, gates/gates.py:2774): 2^k complex MACs
+        per amplitude make it GEMM-shaped, so the targets (then the controls) are brought to the leading qubits with one
+        K8 permutation sweep, the matrix multiplies the state viewed as a (2^k, 2^(n-k)) matrix -- a plain library GEMM
+        (cuBLAS through torch.matmul) on the slice where all controls are 1 -- and a second K8 sweep restores the order."""
+        k, c = len(op.targets), len(op.controls)
+        mat = np.diag(op.data) if op.is_diagonal else op.data
+        if c == 0 and np.array_equal(mat, np.eye(1 << k)):
+            return state  # gates.I(*range(7)) and friends
+        lead = list(op.targets) + list(op.controls)
+        if len(set(lead)) != k + c or any(q < 0 or q >= nqubits for q in lead):
+            raise ValueError("bad target / control qubits")
+        rest = [q for q in range(nqubits) if q not in lead]
+        order = lead + rest  # order[p] = the qubit that moves to position p
+        dest = [0] * nqubits
+        for p, q in enumerate(order):
+            dest[q] = p
+        moved = dest != list(range(nqubits))
+        if moved:
+            self.permute_qubits(state, nqubits, dest)
+        u = torch.from_numpy(np.ascontiguousarray(mat)).to(self.device).to(state.tensor.dtype)
+        view = state.tensor.view(1 << k, 1 << c, -1)
+        if c == 0:
+            state.tensor = torch.matmul(u, view[:, 0, :]).reshape(-1)
+        else:
+            view[:, -1, :] = torch.matmul(u, view[:, -1, :])
+        if moved:
+            self.permute_qubits(state, nqubits, order)  # position p goes back to qubit order[p]
+        return state
+
     # ---- K2: a gate queue -------------------------------------------------------------------------
     def _apply_sweeps(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool, timed: bool):
+        self.bind_current_stream()
         stats = _lib.QbProgramStats()
         if len(ops) == 0:
             return stats
@@ -148,6 +197,7 @@ class Engine:
         a second buffer of the same shape to permute into -- the two DeviceArrays then trade buffers (shards that other
         ranks have mapped through CUDA IPC ping-pong between two exported buffers this way); an IPC-exported buffer
         without ``alt`` gets its result copied back in place.  Returns elapsed ms or None."""
+        self.bind_current_stream()
         scratch = torch.empty_like(state.tensor) if alt is None else alt.tensor
         if timed or spans is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -192,8 +242,13 @@ class Engine:
         total = _lib.QbProgramStats()
         total.nops = len(ops)
         total.perm_ms, total.nperm = 0.0, 0  # K8 launches inside this program (reported apart from the sweep kernel)
-        segments = split_swap_runs(ops, nqubits) if fuse and self.permute_swap_runs else [("ops", list(ops))]
+        segments = split_segments(ops, nqubits, fuse and self.permute_swap_runs)
         for kind, payload in segments:
+            if kind == "wide":
+                self.apply_wide(state, nqubits, payload)
+                total.nsweeps += 3
+                total.bytes_moved += 6.0 * state.nbytes
+                continue
             if kind == "perm":
                 try:
                     ms = self.permute_qubits(state, nqubits, payload, timed=timed, alt=alt, spans=spans)
@@ -235,6 +290,7 @@ class Engine:
                     spans: Optional[list] = None):
         """Apply a compiled program to ``state`` (same nqubits / dtype / device as it was compiled for).  ``timed`` /
         ``spans`` as in ``apply_program``."""
+        self.bind_current_stream()
         if np.dtype(state.dtype) != prog.dtype or state.size != (1 << prog.nqubits):
             raise ValueError(f"program compiled for {prog.nqubits} qubits of {prog.dtype}, got a state of {state.size} x {state.dtype}")
         total = _lib.QbProgramStats()
@@ -242,6 +298,11 @@ class Engine:
         total.perm_ms, total.nperm = 0.0, 0
         flags = _lib.QB_PROGRAM_TIME if timed else 0
         for kind, payload in prog.segments:
+            if kind == "wide":
+                self.apply_wide(state, prog.nqubits, payload)
+                total.nsweeps += 3
+                total.bytes_moved += 6.0 * state.nbytes
+                continue
             if kind == "perm":
                 try:
                     ms = self.permute_qubits(state, prog.nqubits, payload, timed=timed, alt=alt, spans=spans)
@@ -274,6 +335,7 @@ class Engine:
 
     # ---- K3: probabilities --------------------------------------------------------------------------
     def probabilities(self, state: DeviceArray, qubits: Sequence[int], nqubits: int) -> DeviceArray:
+        self.bind_current_stream()
         rdtype = np.dtype("float64") if state.dtype == np.dtype("complex128") else np.dtype("float32")
         out = self.empty((1 << len(qubits),), rdtype)
         _lib.check(
@@ -283,12 +345,35 @@ class Engine:
         )
         return out
 
+    def probabilities_dm(self, rho: DeviceArray, qubits: Sequence[int], nqubits: int) -> DeviceArray:
+        """calculate_probabilities(density_matrix=True), abstract.py:2741-2749, on a device-resident rho."""
+        self.bind_current_stream()
+        rdtype = np.dtype("float64") if rho.dtype == np.dtype("complex128") else np.dtype("float32")
+        out = self.empty((1 << len(qubits),), rdtype)
+        _lib.check(
+            self.lib.qb_probabilities_dm(
+                self.handle, rho.data_ptr(), nqubits, _DT[rho.dtype], _int_array(qubits), len(qubits), out.data_ptr()
+            )
+        )
+        return out
+
+    def collapse_dm(self, rho: DeviceArray, nqubits: int, qubits: Sequence[int], outcome: int, normalize: bool = True):
+        """_collapse_density_matrix, abstract.py:3249-3277, in place on a device-resident rho."""
+        self.bind_current_stream()
+        _lib.check(
+            self.lib.qb_collapse_dm(
+                self.handle, rho.data_ptr(), nqubits, _DT[rho.dtype], _int_array(qubits), len(qubits), int(outcome), 1 if normalize else 0
+            )
+        )
+        return rho
+
     # ---- K4: sampling ---------------------------------------------------------------------------------
     def sample(self, probs: DeviceArray, uniforms: np.ndarray, mode: Optional[int] = None, return_total: bool = False):
         """Inverse-CDF sampling: ``searchsorted(cumsum(p) / sum, u, side="right")`` as np.random.choice does."""
+        self.bind_current_stream()
         nbins = probs.size
         if mode is None:
-            mode = _lib.QB_SCAN_EXACT if nbins <= EXACT_SCAN_MAX_BINS else _lib.QB_SCAN_PARALLEL
+            mode = _lib.QB_SCAN_EXACT if nbins <= self.exact_scan_max_bins else _lib.QB_SCAN_PARALLEL
         uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
         out = np.empty(uniforms.shape[0], dtype=np.int64)
         total = ctypes.c_double()
@@ -300,7 +385,10 @@ class Engine:
         )
         return (out, total.value) if return_total else out
 
-    def cdf(self, probs: DeviceArray, mode: int) -> DeviceArray:
+    def cdf(self, probs: DeviceArray, mode: Optional[int] = None) -> DeviceArray:
+        self.bind_current_stream()
+        if mode is None:
+            mode = _lib.QB_SCAN_EXACT if probs.size <= self.exact_scan_max_bins else _lib.QB_SCAN_PARALLEL
         out = self.empty((probs.size,), np.float64)
         _lib.check(self.lib.qb_cdf(self.handle, probs.data_ptr(), _RT[probs.dtype], probs.size, out.data_ptr(), mode))
         return out
@@ -331,6 +419,7 @@ class Engine:
 
     # ---- K5: collapse -----------------------------------------------------------------------------------
     def collapse(self, state: DeviceArray, nqubits: int, qubits: Sequence[int], outcome: int, normalize: bool = True):
+        self.bind_current_stream()
         _lib.check(
             self.lib.qb_collapse(
                 self.handle, state.data_ptr(), nqubits, _DT[state.dtype], _int_array(qubits), len(qubits), int(outcome),
@@ -430,10 +519,14 @@ class CompiledProgram:
         self.engine, self.nqubits, self.dtype, self.nops = engine, nqubits, np.dtype(dtype), len(ops)
         self.segments = []
         self.nsweeps = 0
-        segments = split_swap_runs(ops, nqubits) if fuse and engine.permute_swap_runs else [("ops", list(ops))]
+        segments = split_segments(ops, nqubits, fuse and engine.permute_swap_runs)
         flags = 0 if fuse else _lib.QB_PROGRAM_NO_FUSE
         try:
             for kind, payload in segments:
+                if kind == "wide":
+                    self.segments.append(("wide", payload))
+                    self.nsweeps += 3
+                    continue
                 if kind == "perm":
                     self.segments.append(("perm", list(payload)))
                     self.nsweeps += 1
@@ -512,6 +605,26 @@ def split_swap_runs(ops: Sequence[Op], nqubits: int):
     close_run()
     if cur:
         out.append(("ops", cur))
+    return out
+
+
+def split_segments(ops: Sequence[Op], nqubits: int, swap_runs: bool = True):
+    """-> [("ops", [...]) | ("perm", dest_of_qubit) | ("wide", op)]: the queue cut at blocks too wide for a sweep tile pass
+    (Engine.apply_wide) and, between them, at runs of plain SWAPs (K8)."""
+    out, cur = [], []
+
+    def flush():
+        if cur:
+            out.extend(split_swap_runs(cur, nqubits) if swap_runs else [("ops", list(cur))])
+            cur.clear()
+
+    for op in ops:
+        if is_wide(op):
+            flush()
+            out.append(("wide", op))
+        else:
+            cur.append(op)
+    flush()
     return out
 
 

@@ -14,6 +14,11 @@ import numpy as np
 from qibo_b200 import _lib
 
 
+def is_wide(op) -> bool:
+    """More targets than a sweep tile pass takes (Unitary / FusedGate / I on 7+ qubits, gates/gates.py:2774)."""
+    return len(op.targets) > _lib.QB_MAX_OP_TARGETS
+
+
 @dataclass
 class Op:
     data: np.ndarray  # (2^k, 2^k) matrix or (2^k,) diagonal
@@ -28,8 +33,6 @@ class Op:
         want = (2**k,) if self.is_diagonal else (2**k, 2**k)
         if self.data.shape != want:
             raise ValueError(f"gate data has shape {self.data.shape}, expected {want} for {k} target qubits")
-        if k > _lib.QB_MAX_OP_TARGETS:
-            raise NotImplementedError(f"gates with more than {_lib.QB_MAX_OP_TARGETS} target qubits are not supported")
         if len(self.controls) > _lib.QB_MAX_OP_CONTROLS:
             raise NotImplementedError("too many control qubits")
         self.targets = tuple(int(q) for q in self.targets)
@@ -40,6 +43,8 @@ def pack_ops(ops: Sequence[Op]):
     """-> (ctypes array of qb_op, keep-alive list).  Matrices are passed by host pointer."""
     arr = (_lib.QbOp * max(len(ops), 1))()
     for i, op in enumerate(ops):
+        if len(op.targets) > _lib.QB_MAX_OP_TARGETS:  # (Engine routes wider blocks through permute + GEMM, see apply_wide)
+            raise NotImplementedError(f"a sweep program takes gates on at most {_lib.QB_MAX_OP_TARGETS} target qubits")
         c = arr[i]
         c.ntargets = len(op.targets)
         c.ncontrols = len(op.controls)

@@ -361,7 +361,7 @@ def _verify_worker(rank, world, port, n, layout, break_it, out):
 
 @pytest.mark.parametrize("world,layout,break_it", [(2, "auto", False), (4, "auto", False), (4, None, False), (2, "auto", True)])
 def test_bench_closed_form_check(world, layout, break_it):
-    """bench.py's pre-timing check of a sharded QFT (closed form exp(2 pi i x k / 2^n) / sqrt(2^n) at sample amplitudes of
+    """bench.py's pre-timing check of a sharded QFT (closed form exp(2 pi i x k / 2^n) / sqrt(2^n) on every amplitude of
     every rank) on gloo with the oracle as the shard executor: passes on a correct run, fails on every rank when one rank
     holds a wrong amplitude, and leaves |0...0> behind."""
     ctx = mp.get_context("spawn")
@@ -377,8 +377,8 @@ def test_bench_closed_form_check(world, layout, break_it):
     if break_it:
         assert "failed" in res
     else:
-        assert res["max_rel_err"] < 1e-12 and res["samples_per_rank"] >= 2 and ok_reset
-        assert res["exchange_path"].startswith("alltoall")  # (no peer memory on gloo: the name of the configured path)
+        assert res["max_rel_err"] < 1e-12 and res["amplitudes_checked_per_rank"] == 2 ** 10 // world and ok_reset
+        assert res["exchange_path"] == "pipelined-dma"  # (no peer memory on gloo: the name of the configured path)
 
 
 class _FakeEngine:

@@ -525,3 +525,27 @@ def test_one_backend_entered_from_two_threads(eng):
     for t in threads:
         t.join(300)
     assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_wide_unitaries(eng, dtype):
+    """Unitary on more than 6 targets (the reference takes any width, gates/gates.py:2774; gates.I(*range(7)) too):
+    K8 permutation + library GEMM + K8 back (Engine.apply_wide), alone, controlled, and inside a longer program."""
+    from helpers import rand_unitary
+
+    n = 13
+    rng = np.random.default_rng(8)
+    psi = rand_state(n, 4, dtype)
+    wide7 = Op(rand_unitary(7, rng), (12, 0, 5, 3, 9, 1, 7))
+    wide8c = Op(rand_unitary(8, rng), (2, 4, 6, 8, 10, 11, 0, 1), (5, 12))
+    ident = Op(np.eye(128), tuple(range(7)))
+    t = tol(dtype) * (20 if dtype == "complex64" else 1)  # 2^8-term dot products in float32
+    for op in (wide7, wide8c, ident):
+        assert np.abs(run_k1(eng, psi, [op], n) - oracle_run(psi, [op], n)).max() < t
+    ops = [Op(orc.gate_matrix("H"), (3,)), wide7, Op(orc.gate_matrix("CNOT"), (0, 12)), ident, wide8c, Op(orc.gate_matrix("RY", 0.3), (6,))]
+    ref = oracle_run(psi, ops, n)
+    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < t
+    prog = eng.compile(n, dtype, ops)
+    st = eng.upload(psi)
+    eng.run_program(prog, st)
+    assert np.abs(st.numpy() - ref).max() < t

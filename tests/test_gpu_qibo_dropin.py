@@ -257,3 +257,86 @@ def test_symbolic_hamiltonian_expectation_on_device(backends):
     r1 = ref.execute_circuit(circuit()).state()
     r2 = ref.execute_circuit(Circuit(n)).state()
     assert abs(complex(ours.overlap_statevector(s1, s2)) - complex(ref.overlap_statevector(r1, r2))) < 1e-12
+
+
+def rand_density_matrix(n, seed, dtype="complex128"):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(2**n, 2**n)) + 1j * rng.normal(size=(2**n, 2**n))
+    rho = a @ a.conj().T
+    return (rho / np.trace(rho)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_density_matrix_probabilities_collapse_on_device(backends, dtype):
+    """X1 without a host detour: diag(rho) marginals in the caller's qubit order (abstract.py:2741-2749), collapse of rows
+    and columns with trace renormalisation (:3249-3277), `controlled_by` gates (:3199-3234), minus_state -- device kernels
+    against the NumpyBackend on the same matrices."""
+    from qibo import gates
+    from qibo_b200.array import DeviceArray
+
+    ours, ref = backends
+    ours.set_dtype(dtype)
+    ref.set_dtype(dtype)
+    n = 5
+    rho = rand_density_matrix(n, 3, dtype)
+    t = 1e-12 if dtype == "complex128" else 1e-5
+    for qubits in ([0], [4], [1, 3], [3, 1], [4, 0, 2], list(range(n)), [2, 4, 1, 0, 3]):
+        a = ours.calculate_probabilities(np.copy(rho), qubits, n, density_matrix=True)
+        b = ref.calculate_probabilities(np.copy(rho), qubits, n, density_matrix=True)
+        assert isinstance(a, DeviceArray) and a.dtype == b.dtype and a.shape == b.shape
+        assert np.abs(ours.to_numpy(a) - b).max() < t, qubits
+    for qubits, shot in (([0], 1), ([1, 3], 2), ([0, 2, 4], 5), (list(range(n)), 19)):
+        for normalize in (True, False):
+            a = ours.collapse_state(np.copy(rho), qubits, np.array([shot]), n, normalize=normalize, density_matrix=True)
+            b = ref.collapse_state(np.copy(rho), qubits, np.array([shot]), n, normalize=normalize, density_matrix=True)
+            assert isinstance(a, DeviceArray) and a.shape == b.shape
+            assert np.abs(ours.to_numpy(a) - b).max() < t, (qubits, shot, normalize)
+    for gate in (gates.X(2).controlled_by(0, 4), gates.RY(0, 0.7).controlled_by(3), gates.SWAP(1, 2).controlled_by(0),
+                 gates.Unitary(np.linalg.qr(np.random.default_rng(1).normal(size=(4, 4)))[0], 3, 1).controlled_by(4)):
+        a = ours.apply_gate(gate, np.copy(rho), n)
+        b = ref.apply_gate(gate, np.copy(rho), n)
+        assert np.abs(ours.to_numpy(a) - b).max() < t, gate.name
+    for fn in ("zero_state", "plus_state", "minus_state"):
+        a = getattr(ours, fn)(3, density_matrix=True)
+        b = getattr(ref, fn)(3, density_matrix=True)
+        assert isinstance(a, DeviceArray) and a.shape == b.shape
+        assert np.abs(ours.to_numpy(a) - b).max() < t, fn
+    assert np.abs(ours.to_numpy(ours.minus_state(4)) - ref.minus_state(4)).max() < t
+
+
+def test_density_matrix_collapse_circuit(backends):
+    """A density-matrix circuit with a collapsing measurement, end to end through Circuit() (tests/test_measurements_collapse.py)."""
+    from qibo import Circuit, gates
+
+    ours, ref = backends
+    outs = []
+    for be in (ours, ref):
+        c = Circuit(4, density_matrix=True)
+        c.add(gates.H(q) for q in range(4))
+        c.add(gates.CNOT(0, 2))
+        m = c.add(gates.M(1, 2, collapse=True))
+        c.add(gates.RX(3, 0.4))
+        c.add(gates.M(0, 3))
+        be.set_seed(7)
+        res = be.execute_circuit(c, nshots=50)
+        outs.append((be.to_numpy(res.state()), m.samples()[0], res.frequencies()))
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-12
+    assert list(outs[0][1]) == list(outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_measurement_registers_in_add_order_sharded_path(backends):
+    """The joint measurement keeps the qubits in the order they were added (result.py:444-458): M(3, 1) then M(0)."""
+    from qibo import Circuit, gates
+
+    ours, ref = backends
+    outs = []
+    for be in (ours, ref):
+        c = Circuit(5)
+        c.add(gates.RY(q, theta=0.3 + 0.2 * q) for q in range(5))
+        c.add(gates.CNOT(0, 3))
+        c.add(gates.M(3, 1, register_name="a"))
+        c.add(gates.M(0, register_name="b"))
+        be.set_seed(11)
+        res = be.execute_circuit(c, nshots=300)
+        outs.append((res.frequencies(), res.frequencies(registers=True)))
+    assert outs[0] == outs[1]
