@@ -131,8 +131,13 @@ def test_planner_argument_errors():
         plan_program(4, "complex128", [Op(np.eye(4), (1, 1))])
     with pytest.raises(ValueError):
         Op(np.eye(4), (1,))
+    # blocks on more than 6 targets exist as Ops (Engine.apply_wide: permute + GEMM) but never enter a sweep program
+    wide = Op(np.eye(128), tuple(range(7)))
     with pytest.raises(NotImplementedError):
-        Op(np.eye(128), tuple(range(7)))
+        plan_program(8, "complex128", [wide])
+    from qibo_b200.engine import split_segments
+
+    assert [k for k, _ in split_segments([Op(h, (0,)), wide, Op(h, (1,))], 8)] == ["ops", "wide", "ops"]
 
 
 def test_product_circuits_match_oracle_generators():
