@@ -44,6 +44,16 @@ template <typename C> QB_HD uint32_t swz(uint32_t x, uint32_t on) {
   return sizeof(C) == 16 ? x ^ ((x >> 3) & on) : x ^ (((x >> 4) & on) << 1);
 }
 
+// bit that changes between the k-th and the (k+1)-th Gray code: the number of trailing ones of k
+constexpr QB_HD int gray_flip(int k) {
+  int b = 0;
+  while (k & 1) {
+    k >>= 1;
+    ++b;
+  }
+  return b;
+}
+
 template <typename C> QB_HD C slot_ext(const TileSlot& s) { return *reinterpret_cast<const C*>(s.ext); }
 
 // ---- micro-op bodies on a register tile v[2^R] --------------------------------------------------------------
@@ -198,6 +208,21 @@ template <typename C, int R, int CB> QB_HD void mu_phase(C* v, const C ph, uint3
   }
 }
 
+// lone phase controlled by the two register bits HI > LO: the 2^(R-2) register indices with both bits set
+template <typename C, int R, int HI, int LO> QB_HD void mu_phase2(C* v, const C ph) {
+  constexpr int D = 1 << R;
+  constexpr int M = (1 << HI) | (1 << LO);
+  if (ph.y == 0) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if ((j & M) == M) v[j] = creal_mul(ph.x, v[j]);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+    if ((j & M) == M) cmul_inplace(v[j], ph);
+}
+
 template <typename C, int R> QB_HD void mu_diagk(C* v, const MicroOp& mo, const char* blob, uint32_t aux, uint32_t t0) {
   constexpr int D = 1 << R;
   const C* tab = reinterpret_cast<const C*>(blob + mo.payload);
@@ -292,13 +317,13 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
     t0[u] = t;
     p0[u] = swz<C>(t, swz_on);
     if (valid[u]) {
+      // Gray-code walk over the 2^R register indices: consecutive addresses differ by ONE stride (ncu, round 2: the
+      // address arithmetic of the tile loads / stores was 20 % of a layered sweep's instructions)
+      uint32_t o = p0[u];
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        uint32_t o = p0[u];
-#pragma unroll
-        for (int i = 0; i < R; ++i)
-          if ((j >> i) & 1) o ^= stride[i];
-        v[u][j] = tile[o];
+      for (int k = 0; k < D; ++k) {
+        v[u][k ^ (k >> 1)] = tile[o];
+        if (k + 1 < D) o ^= stride[gray_flip(k)];
       }
     }
   }
@@ -363,6 +388,7 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
       QB_CASE_BIT(MH_PHASE_C, { const C ph = inl[0]; QB_EACH((mu_phase<C, R, I>(v[u], ph, 0u))) })
       case MH_PHASE_NC: { const C ph = inl[0]; QB_EACH((mu_phase<C, R, R>(v[u], ph, 0u))) } break;
       case MH_PHASE_M: { const C ph = inl[0]; QB_EACH((mu_phase<C, R, R + 1>(v[u], ph, hot.creg))) } break;
+      QB_CASE_PAIRS(MH_PHASE_C2, { const C ph = inl[0]; QB_EACH((mu_phase2<C, R, HI, LO>(v[u], ph))) })
       case MH_DIAGK: QB_EACH((mu_diagk<C, R>(v[u], mo, blob, ts[slot].aux, t0[u]))) break;
       case MH_REAL_LAYER: {
         const C* m = reinterpret_cast<const C*>(blob + hot.payload);
@@ -384,13 +410,11 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {
     if (valid[u]) {
+      uint32_t o = p0[u];
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        uint32_t o = p0[u];
-#pragma unroll
-        for (int i = 0; i < R; ++i)
-          if ((j >> i) & 1) o ^= stride[i];
-        tile[o] = v[u][j];
+      for (int k = 0; k < D; ++k) {
+        tile[o] = v[u][k ^ (k >> 1)];
+        if (k + 1 < D) o ^= stride[gray_flip(k)];
       }
     }
   }

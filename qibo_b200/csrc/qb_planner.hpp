@@ -53,6 +53,10 @@ enum MicroHandler {
   MH_STAGE_R = 50,  // +I  real 2x2 on bit I, then that fan
   MH_REAL_LAYER = 54,  //  up to R uncontrolled real 2x2 gates on distinct register bits (an RY layer) in one dispatch:
                        //  `k` = mask of the register bits present, payload = their matrices (4 entries each, .x used)
+  MH_PHASE_C2 = 55,    // +P  lone phase whose two register-bit controls are the pair (hi, lo): CZ / CU1 with both qubits
+                       //  among the register bits -- compile-time masks (ncu, round 2: the run-time mask form MH_PHASE_M
+                       //  tests every register index, ~3 instructions per amplitude instead of 1/4)
+  MH_COUNT = 61,
 };
 
 constexpr int SWEEP_MAX_SLOTS = 48;        // ops per sweep that need per-tile set-up (controls / factors from outside the tile)
@@ -623,6 +627,8 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       *reinterpret_cast<C*>(m.inl) = to_dev<C>(p.fan.begin()->second.second);
       if (m.creg == 0) m.handler = MH_PHASE_NC;
       else if (__builtin_popcount(m.creg) == 1) m.handler = (uint8_t)(MH_PHASE_C + __builtin_ctz(m.creg));
+      else if (__builtin_popcount(m.creg) == 2 && !env_int("QB_NO_PHASE_C2", 0))
+        m.handler = (uint8_t)(MH_PHASE_C2 + pair_index(31 - __builtin_clz(m.creg), __builtin_ctz(m.creg)));
       else m.handler = MH_PHASE_M;
     } else {  // fan
       m.type = MU_FAN;
@@ -919,19 +925,32 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
   sd.blob_bytes = off;
 }
 
-// Runs of consecutive state bits that are all inside / all outside the tile: the dimensions of the tensor map that
-// moves a tile with one TMA copy (qb_sweep.cuh).  A run of tile bits is cut so that a box edge stays <= 256 8-byte
-// elements; with the 128-byte swizzle the innermost run is exactly one 128-byte row.  More than 5 runs: no tensor map.
+// Dimensions of the tensor map that moves a tile with ONE TMA copy (qb_sweep.cuh).  A dimension is (first bit, length):
+// every run of consecutive tile bits is one (cut so that a box edge stays <= 256 8-byte elements; with the 128-byte
+// swizzle the innermost one is exactly one 128-byte row), and ALL the bits outside the tile share a single "fold"
+// dimension: its stride is the lowest non-tile bit and its extent everything above, so the coordinate base >> start
+// addresses any tile (the tile bits of a tile base are zero; a TMA address is just base + sum coord_d * stride_d, the
+// dimensions need not be disjoint).  Scattered tiles (random circuits, the wrap-around CZ of the ansatz) thus cost one
+// dimension per run of TILE bits plus one, instead of one per run of either kind.  More than 5: no tensor map.
 struct TileSeg { int start, len; bool tile; };
 inline std::vector<TileSeg> tile_segments(int nqubits, int dtype, uint64_t tile_mask, bool swizzle) {
   const int row_bits = dtype == QB_C128 ? 3 : 4;  // amplitudes per 128-byte row
   std::vector<TileSeg> segs;
+  bool folded = false;
   for (int b = 0; b < nqubits;) {
     const bool t = (tile_mask >> b) & 1;
+    if (!t) {
+      if (!folded) {
+        segs.push_back({b, nqubits - b, false});
+        folded = true;
+      }
+      while (b < nqubits && !((tile_mask >> b) & 1)) ++b;
+      continue;
+    }
     int e = b;
-    const int cap = !t ? 31 : (segs.empty() ? (swizzle ? row_bits : row_bits + 4) : 8);
-    while (e < nqubits && (((tile_mask >> e) & 1) != 0) == t && e - b < cap) ++e;
-    segs.push_back({b, e - b, t});
+    const int cap = segs.empty() ? (swizzle ? row_bits : row_bits + 4) : 8;
+    while (e < nqubits && ((tile_mask >> e) & 1) && e - b < cap) ++e;
+    segs.push_back({b, e - b, true});
     b = e;
   }
   return segs;

@@ -131,9 +131,19 @@ QB_D bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
 }
 QB_D void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    if (clock64() - t0 > 20000000000LL) __trap();
+  // ncu (round 2, profiles/r2a_*): with the suspend-time hint alone the copy warps still executed 12 % of all the
+  // instructions of a sweep -- NANOSLEEP.SYNCS wakes on every mbarrier event of the CTA, and the wake-up loop (try_wait,
+  // clock64, compare) competed with the compute warps of its scheduler.  A plain timed sleep between polls costs at most
+  // a fraction of a microsecond of latency per tile (a tile period is ~10-20 us and three buffers are in flight).
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    __nanosleep(400);
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+    if ((spins & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000LL) __trap();
+    }
   }
 }
 // state index of tile t = deposit(t, other_mask); stepping t by a constant is a masked add (carries ripple through the
@@ -366,8 +376,8 @@ inline qb_encode_tiled_fn tma_encoder() {
   return fn;
 }
 
-// One tensor dimension per run of state bits (tile_segments, qb_planner.hpp).  Returns false (per-run copies) when the
-// tile needs more than 5 dimensions or the driver entry point is missing.
+// One tensor dimension per run of tile bits plus one for all the other bits (tile_segments, qb_planner.hpp).  Returns
+// false (per-run copies) when the tile needs more than 5 dimensions or the driver entry point is missing.
 inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask, bool swizzle, TmaDesc& d) {
   memset(&d, 0, sizeof(d));
   if (env_int("QB_NO_TMA", 0)) return false;
@@ -378,26 +388,30 @@ inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask
   if (segs.empty() || !segs[0].tile || segs.size() > 5) return false;
   cuuint64_t gdim[5], gstride[4];
   cuuint32_t box[5], estr[5];
+  const cuuint64_t amp_bytes = 8 * (cuuint64_t)epa;
   for (int i = 0; i < 5; ++i) {
     estr[i] = 1;
     if (i < (int)segs.size()) {
+      if (segs[i].len > 32) return false;
       gdim[i] = (cuuint64_t(1) << segs[i].len) * (i == 0 ? epa : 1);
+      if (gdim[i] > (cuuint64_t(1) << 32)) return false;
       box[i] = segs[i].tile ? (cuuint32_t)gdim[i] : 1;
       d.shift[i] = segs[i].start;
-      d.mask[i] = segs[i].tile ? 0u : (uint32_t)((uint64_t(1) << segs[i].len) - 1);
+      d.mask[i] = segs[i].tile ? 0u : (segs[i].len >= 32 ? 0xFFFFFFFFu : (uint32_t)((uint64_t(1) << segs[i].len) - 1));
+      // stride of dimension i = the byte offset of its first bit (dimensions are ordered by ascending first bit)
+      if (i > 0) {
+        const cuuint64_t bytes = amp_bytes << segs[i].start;
+        if (bytes >= (cuuint64_t(1) << 40)) return false;
+        gstride[i - 1] = bytes;
+      }
     } else {
       gdim[i] = 1;
       box[i] = 1;
       d.shift[i] = 0;
       d.mask[i] = 0;
+      // unused trailing dimensions: extent 1, any legal stride (a multiple of the one below)
+      if (i > 0) gstride[i - 1] = i >= 2 ? gstride[i - 2] : amp_bytes * (gdim[0] / epa);
     }
-  }
-  // the runs tile the index bits in order, so every stride is the natural one: the byte size of all lower dimensions
-  cuuint64_t bytes = 8;
-  for (int i = 0; i < 4; ++i) {
-    bytes *= gdim[i];
-    if (bytes >= (cuuint64_t(1) << 40)) return false;
-    gstride[i] = bytes;
   }
   if (enc(&d.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, state, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,

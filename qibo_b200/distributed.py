@@ -507,6 +507,7 @@ class LocalPeerShard(PeerShard):
         self.engine, self.rank = engine, rank_
         self.array = engine.empty((1 << nlocal,), dtype)
         self.alt = engine.empty((1 << nlocal,), dtype)
+        self.array._owner = self.alt._owner = None  # (plain torch allocations: nothing to hand over when the buffers flip)
         self._base = (self.array.data_ptr(), self.alt.data_ptr())
         self._peer_ptrs = {}
 

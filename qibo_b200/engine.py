@@ -78,7 +78,37 @@ class Engine:
 
     # ---- memory / state construction (K6) ---------------------------------------------------------
     def empty(self, shape, dtype) -> DeviceArray:
-        return DeviceArray(torch.empty(shape, dtype=torch_dtype(dtype), device=self.device))
+        return DeviceArray(self._alloc(shape, torch_dtype(dtype)))
+
+    _gc_frozen = False
+
+    def _alloc(self, shape, tdtype) -> torch.Tensor:
+        """torch.empty with one precaution for states that fill a large part of the device: the reference keeps a finished
+        Circuit (and through ``_final_state`` its 2^n amplitudes) alive in a reference cycle (Circuit -> M gate ->
+        MeasurementResult -> Circuit), so the buffer of the PREVIOUS execution is only returned by Python's cyclic
+        collector.  Before a large allocation that would not fit, collect; the first time this happens the long-lived
+        module objects are frozen out of the collector's scans (a full collection drops from ~170 ms to < 1 ms)."""
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=tdtype).element_size()
+        if nbytes >= (1 << 30):
+            free, _ = torch.cuda.mem_get_info(self.device)
+            cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            if free + cached < nbytes + (1 << 28):
+                self._reclaim()
+        try:
+            return torch.empty(shape, dtype=tdtype, device=self.device)
+        except torch.cuda.OutOfMemoryError:
+            self._reclaim()
+            torch.cuda.empty_cache()
+            return torch.empty(shape, dtype=tdtype, device=self.device)
+
+    @classmethod
+    def _reclaim(cls):
+        import gc
+
+        gc.collect()
+        if not cls._gc_frozen:
+            gc.freeze()
+            cls._gc_frozen = True
 
     def basis_state(self, nqubits: int, dtype="complex128", index: int = 0) -> DeviceArray:
         """zero_state (abstract.py:2243-2273) generalised to any basis index."""
@@ -198,7 +228,7 @@ class Engine:
         ranks have mapped through CUDA IPC ping-pong between two exported buffers this way); an IPC-exported buffer
         without ``alt`` gets its result copied back in place.  Returns elapsed ms or None."""
         self.bind_current_stream()
-        scratch = torch.empty_like(state.tensor) if alt is None else alt.tensor
+        scratch = self._alloc(tuple(state.tensor.shape), state.tensor.dtype) if alt is None else alt.tensor
         if timed or spans is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

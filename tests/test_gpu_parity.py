@@ -61,10 +61,11 @@ def test_random_zoo_every_bit_position(eng, dtype, seed):
     ops = random_zoo(n, 60, seed)
     psi = rand_state(n, seed, dtype)
     ref = oracle_run(psi, ops, n)
-    scale = 10 if dtype == "complex64" else 1
-    assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
-    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
-    assert np.abs(run_k2(eng, psi, ops, n, fuse=False) - ref).max() < tol(dtype) * scale
+    # north-star bounds as they are (profiles/r2a_tol_probe.json: the CUDA path and the reference algorithm in complex64 both
+    # sit at ~5e-9 from the complex128 result on these programs)
+    assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype)
+    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype)
+    assert np.abs(run_k2(eng, psi, ops, n, fuse=False) - ref).max() < tol(dtype)
 
 
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
@@ -254,7 +255,7 @@ def test_rank_specialised_segments_at_scale(eng, n, world, rank, dtype):
             for op in local:
                 eng.apply_op(b, nlocal, op)
         nseg += 1
-        assert float((a.tensor - b.tensor).abs().max()) < tol(dtype) * (10 if dtype == "complex64" else 1)
+        assert float((a.tensor - b.tensor).abs().max()) < tol(dtype)
     assert nseg >= 4
 
 
@@ -452,9 +453,8 @@ def test_six_qubit_dense_block(eng, dtype):
     ops = [Op(rand_unitary(6, rng), (13, 2, 7, 0, 9, 4)), Op(orc.gate_matrix("H"), (3,)), Op(rand_unitary(6, rng), (1, 5, 3, 8, 12, 6), (10,))]
     psi = rand_state(n, 3, dtype)
     ref = oracle_run(psi, ops, n)
-    scale = 20 if dtype == "complex64" else 1
-    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype) * scale
-    assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype) * scale  # apply_op routes k = 6 to the sweep kernel
+    assert np.abs(run_k2(eng, psi, ops, n) - ref).max() < tol(dtype)
+    assert np.abs(run_k1(eng, psi, ops, n) - ref).max() < tol(dtype)  # apply_op routes k = 6 to the sweep kernel
 
 
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
@@ -539,7 +539,7 @@ def test_wide_unitaries(eng, dtype):
     wide7 = Op(rand_unitary(7, rng), (12, 0, 5, 3, 9, 1, 7))
     wide8c = Op(rand_unitary(8, rng), (2, 4, 6, 8, 10, 11, 0, 1), (5, 12))
     ident = Op(np.eye(128), tuple(range(7)))
-    t = tol(dtype) * (20 if dtype == "complex64" else 1)  # 2^8-term dot products in float32
+    t = tol(dtype)
     for op in (wide7, wide8c, ident):
         assert np.abs(run_k1(eng, psi, [op], n) - oracle_run(psi, [op], n)).max() < t
     ops = [Op(orc.gate_matrix("H"), (3,)), wide7, Op(orc.gate_matrix("CNOT"), (0, 12)), ident, wide8c, Op(orc.gate_matrix("RY", 0.3), (6,))]
