@@ -128,6 +128,29 @@ typedef struct qb_program_s* qb_program;
 int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program* out,
                       qb_program_stats* stats /* may be NULL */);
 int qb_program_run(qb_handle h, qb_program program, void* state, int flags, qb_program_stats* stats /* may be NULL */);
+/* Parameter slots (Circuit.set_parameters + re-execution, models/circuit.py:788-857; parallel.py:124-192): new matrices
+ * for some ops of a compiled program.  The schedule is kept -- only the sweep programs are emitted again and re-uploaded in
+ * stream order; if the new values change the gate structure (an angle of 0 turns a rotation into an identity) the program
+ * is planned from scratch.  `family` != QB_GATE_MATRIX: the matrix is evaluated here from `theta` as
+ * backends/npmatrices.py does (RX :79, RY :84, RZ :89, U1, CU1 :230, CRX, CRY, CRZ), so a variational loop sends angles. */
+#define QB_GATE_MATRIX 0
+#define QB_GATE_RX 1
+#define QB_GATE_RY 2
+#define QB_GATE_RZ 3
+#define QB_GATE_U1 4
+#define QB_GATE_CRX 5 /* two targets: (control, target), the full 4x4 matrix as the reference applies it */
+#define QB_GATE_CRY 6
+#define QB_GATE_CRZ 7
+#define QB_GATE_CU1 8
+typedef struct {
+  int32_t op_index;     /* index into the ops the program was created from */
+  int32_t family;       /* QB_GATE_* */
+  int32_t conjugate;    /* 1: complex-conjugate the matrix (the column side of a density-matrix gate) */
+  int32_t reserved;
+  double theta[3];
+  const double* matrix; /* QB_GATE_MATRIX: host, interleaved complex128, the shape of the op's original data */
+} qb_param_update;
+int qb_program_set_params(qb_handle h, qb_program p, const qb_param_update* updates, int nupdates);
 int qb_program_destroy(qb_handle h, qb_program program);
 /* host-only: run the sweep planner without touching a device (used by the CPU test-suite) */
 int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program_stats* stats,

@@ -79,6 +79,15 @@ def gate_matrix(name, *params, dtype="complex128"):
         cos = np.cos(theta / 2.0) + 0j
         isin = -1j * np.sin(theta / 2.0)
         m = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, cos, isin], [0, 0, isin, cos]]
+    elif name == "CRY":  # :214-218
+        (theta,) = params
+        cos = np.cos(theta / 2.0) + 0j
+        sin = np.sin(theta / 2.0) + 0j
+        m = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, cos, -sin], [0, 0, sin, cos]]
+    elif name == "CRZ":  # :220-228
+        (theta,) = params
+        phase = np.exp(0.5j * theta)
+        m = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, np.conj(phase), 0], [0, 0, 0, phase]]
     elif name == "SWAP":  # :265-268
         m = [[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]
     elif name == "iSWAP":  # :271

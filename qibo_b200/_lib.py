@@ -43,6 +43,19 @@ class QbProgramStats(ctypes.Structure):
     ]
 
 
+class QbParamUpdate(ctypes.Structure):
+    _fields_ = [
+        ("op_index", c_int32),
+        ("family", c_int32),
+        ("conjugate", c_int32),
+        ("reserved", c_int32),
+        ("theta", c_double * 3),
+        ("matrix", c_void_p),
+    ]
+
+
+QB_GATE_MATRIX, QB_GATE_RX, QB_GATE_RY, QB_GATE_RZ, QB_GATE_U1, QB_GATE_CRX, QB_GATE_CRY, QB_GATE_CRZ, QB_GATE_CU1 = range(9)
+
 # name -> (restype, argtypes); every symbol include/qibo_b200.h declares
 PROTOTYPES = {
     "qb_version": (c_int, []),
@@ -69,6 +82,7 @@ PROTOTYPES = {
     "qb_program_create": (c_int, [c_void_p, c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(c_void_p), POINTER(QbProgramStats)]),
     "qb_program_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(QbProgramStats)]),
     "qb_program_destroy": (c_int, [c_void_p, c_void_p]),
+    "qb_program_set_params": (c_int, [c_void_p, c_void_p, POINTER(QbParamUpdate), c_int]),
     "qb_plan_program": (c_int, [c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(QbProgramStats), POINTER(c_int32)]),
     "qb_permute_qubits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
     "qb_probabilities": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p]),

@@ -37,6 +37,10 @@ from qibo_b200.array import torch_dtype as torch_dtype_of
 from qibo_b200.engine import Engine, frequencies_from_samples
 from qibo_b200.ops import Op
 
+# gates whose matrix the library evaluates from the angle (qb_program_set_params): class name -> QB_GATE_*
+_FAMILIES = {"RX": _lib.QB_GATE_RX, "RY": _lib.QB_GATE_RY, "RZ": _lib.QB_GATE_RZ, "U1": _lib.QB_GATE_U1,
+             "CRX": _lib.QB_GATE_CRX, "CRY": _lib.QB_GATE_CRY, "CRZ": _lib.QB_GATE_CRZ, "CU1": _lib.QB_GATE_CU1}
+
 _COMPLEX = {"complex128": np.dtype("complex128"), "complex64": np.dtype("complex64"),
             "float64": np.dtype("complex128"), "float32": np.dtype("complex64")}
 
@@ -52,6 +56,8 @@ class B200Backend(NumpyBackend):
         self.versions = {"qibo": qibo_version, "numpy": np.__version__, "torch": torch.__version__,
                          "qibo_b200": _lib.load().qb_version()}
         self._engines = {}
+        # Circuit objects keep their compiled program between executions (parameter slots, _compiled_circuit)
+        self.compile_circuits = True
         index = 0
         if device is not None:
             index = self._parse_device(device)
@@ -291,6 +297,92 @@ class B200Backend(NumpyBackend):
                     state = self._to_device(state)
         return flush(state)
 
+    # ------------------------------------------------------------------ f2: compiled circuits with parameter slots
+    def _param_slots(self, gate, first_op, nops, density_matrix):
+        """-> [(op index, family, conjugate)] for a parametrised gate whose ops start at ``first_op``."""
+        if not gate.parameters or isinstance(gate, FusedGate):
+            return []
+        family = _FAMILIES.get(gate.__class__.__name__, _lib.QB_GATE_MATRIX)
+        if gate.is_controlled_by or len(gate.parameters) != 1:
+            family = _lib.QB_GATE_MATRIX  # target matrix + controls, U2 / U3 / fSim ...: the host builds the matrix
+        if density_matrix:  # (conj(U) on the column qubits first, then U on the row qubits: _gate_ops)
+            return [(first_op, family, True), (first_op + 1, family, False)]
+        return [(first_op, family, False)]
+
+    def _compiled_circuit(self, circuit, nqubits, density_matrix, dtype):
+        """The whole queue as ONE compiled program, cached on the circuit object and re-parametrised in place when
+        ``Circuit.set_parameters`` (models/circuit.py:788-857) changed angles since the last execution: a variational loop
+        pays kernel launches plus one small C call per step instead of 2 Python calls per gate and a fresh plan.  None for
+        queues with special gates in the middle (callbacks, collapse) or symbolic parameters -- they take _run_queue."""
+        queue = circuit.queue
+        plain = [g for g in queue if self._is_plain(g)]
+        if len(plain) != len(queue):
+            # measurement gates without collapse at the END of the queue leave the state alone; anything else: general path
+            tail = queue[len(plain):] if all(self._is_plain(g) for g in queue[: len(plain)]) else None
+            if tail is None or any(g.__class__.__name__ != "M" or g.collapse for g in tail):
+                return None
+        if any(g.symbolic_parameters for g in plain):
+            return None
+        key = (tuple(map(id, plain)), nqubits, density_matrix, str(dtype), id(self.engine_gpu))
+        cached = getattr(circuit, "_qb200_program", None)
+        if cached is not None and cached["key"] == key:
+            self._update_parameters(cached)
+            return cached["program"]
+        ops, slots = [], []
+        for gate in plain:
+            members = gate.gates if isinstance(gate, FusedGate) else [gate]  # fused blocks are parametrised member by member
+            for member in members:
+                mops = self._gate_ops(member, nqubits, density_matrix)
+                sl = self._param_slots(member, len(ops), len(mops), density_matrix)
+                if sl:
+                    slots.append((member, sl))
+                ops.extend(mops)
+        flat_n = 2 * nqubits if density_matrix else nqubits
+        program = self.engine_gpu.compile(flat_n, dtype, ops)
+        entry = None
+        # (ops inside SWAP runs / wide blocks have no slot in a sweep program: such circuits are compiled on every call)
+        if all(program.op_segment[i][0] >= 0 for _, sl in slots for i, _, _ in sl):
+            fam = [(g, sl) for g, sl in slots if all(f != _lib.QB_GATE_MATRIX for _, f, _ in sl)]
+            other = [(g, sl) for g, sl in slots if any(f == _lib.QB_GATE_MATRIX for _, f, _ in sl)]
+            rec, seg = program.param_records([i for _, sl in fam for i, _, _ in sl], [f for _, sl in fam for _, f, _ in sl],
+                                             [1 if c else 0 for _, sl in fam for _, _, c in sl])
+            entry = {"key": key, "program": program, "fam_gates": [g for g, _ in fam], "fam_rec": rec, "fam_seg": seg,
+                     "fam_row_gate": np.array([k for k, (_, sl) in enumerate(fam) for _ in sl], dtype=np.int64),
+                     "fam_thetas": np.array([float(np.real(g.parameters[0])) for g, _ in fam], dtype=np.float64),
+                     "other": other, "other_thetas": [tuple(g.parameters) for g, _ in other]}
+        try:
+            circuit._qb200_program = entry
+        except Exception:  # (a circuit object that does not take attributes)
+            pass
+        return program
+
+    def _update_parameters(self, cached):
+        """Angles that changed since the cached program last ran -> qb_program_set_params.  Gates of the families the
+        library evaluates itself (RX, RY, RZ, U1, CU1, CRX, CRY, CRZ) cost one float each here; any other parametrised gate
+        sends its new matrix."""
+        program = cached["program"]
+        gates = cached["fam_gates"]
+        if gates:
+            thetas = np.fromiter((np.real(g.parameters[0]) for g in gates), dtype=np.float64, count=len(gates))
+            changed = thetas != cached["fam_thetas"]
+            if changed.any():
+                rows = changed[cached["fam_row_gate"]]
+                rec = cached["fam_rec"][rows]
+                rec["theta"][:, 0] = thetas[cached["fam_row_gate"][rows]]
+                program.set_param_records(rec, cached["fam_seg"][rows])
+                cached["fam_thetas"] = thetas
+        if cached["other"]:
+            now = [tuple(g.parameters) for g, _ in cached["other"]]
+            updates = []
+            for (gate, sl), new, old in zip(cached["other"], now, cached["other_thetas"]):
+                if len(new) == len(old) and all(np.array_equal(a, b) for a, b in zip(new, old)):
+                    continue
+                matrix = np.asarray(gate.matrix(self)).astype(np.complex128, copy=False)
+                for index, family, conj in sl:
+                    updates.append((index, _lib.QB_GATE_MATRIX, [], matrix, conj))
+            program.set_params(updates)
+            cached["other_thetas"] = now
+
     def _execute_circuit(self, circuit, initial_state=None, nshots=1000):
         nqubits = circuit.nqubits
         density_matrix = circuit.density_matrix
@@ -301,7 +393,19 @@ class B200Backend(NumpyBackend):
             state = self._to_device(initial_state)
             if state is initial_state:
                 state = state.copy()
-        state = self._run_queue(circuit.queue, state, nqubits, density_matrix)
+        program = None
+        if self.compile_circuits and str(state.dtype) in ("complex64", "complex128"):
+            program = self._compiled_circuit(circuit, nqubits, density_matrix, state.dtype)
+        if program is not None:
+            flat = state.reshape(-1) if density_matrix else state
+            self.engine_gpu.run_program(program, flat)
+            if flat is not state and flat.tensor.data_ptr() != state.tensor.data_ptr():
+                state.tensor = flat.tensor.reshape(state.shape)
+            for gate in circuit.queue:
+                if not self._is_plain(gate):
+                    gate.result.backend = self  # what M.apply does for a non-collapsing measurement
+        else:
+            state = self._run_queue(circuit.queue, state, nqubits, density_matrix)
         init_dtype = getattr(initial_state, "dtype", None) if initial_state is not None else None
         if self._real_dtype is not None and (init_dtype is None or np.dtype(init_dtype).kind != "c"):
             # float32/float64 backends (real-matrix circuits, abstract.py:133-179): the kernels hold a complex state of

@@ -11,6 +11,7 @@
 
 #include "../../include/qibo_b200.h"
 #include "qb_canon.hpp"
+#include "qb_families.hpp"
 #include "qb_common.cuh"
 #include "qb_gate_kernels.cuh"
 #include "qb_measure_kernels.cuh"
@@ -545,11 +546,20 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
 }
 
 // ---- compiled programs: plan once, keep the sweep programs resident in device memory, launch many times ----------
+struct OpDesc {  // what qb_program_set_params needs to rebuild one op: its qubits and its current host data
+  int ntargets = 0, ncontrols = 0, is_diagonal = 0;
+  int targets[QB_MAX_OP_TARGETS], controls[QB_MAX_OP_CONTROLS];
+  std::vector<double> data;  // interleaved complex128
+};
 struct qb_program_s {
-  int nqubits = 0, dtype = 0, nops = 0, device = 0;
-  Plan plan;                    // sweep descriptors (the blob itself lives in `dev`)
-  std::vector<CanonOp> canon;   // nqubits < 4: the K1 kernels apply the queue gate by gate
+  int nqubits = 0, dtype = 0, nops = 0, device = 0, flags = 0;
+  Plan plan;                    // sweep descriptors + the schedule (the blob itself lives in `dev`)
+  std::vector<CanonOp> canon;   // canonical ops (re-planned on a parameter update; nqubits < 4: applied gate by gate)
+  std::vector<OpDesc> descs;
   void* dev = nullptr;
+  size_t dev_bytes = 0;
+  void* staging = nullptr;      // pinned host copy of the blob for stream-ordered re-uploads
+  size_t staging_bytes = 0;
   qb_program_stats stats;
 };
 
@@ -563,8 +573,20 @@ int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int
   p->dtype = dtype;
   p->nops = nops;
   p->device = h->device;
+  p->flags = flags;
   int rc = canonicalize_program(nqubits, ops, nops, p->canon);
   if (rc != QB_OK) return rc;
+  p->descs.resize(nops);
+  for (int i = 0; i < nops; ++i) {
+    OpDesc& d = p->descs[i];
+    d.ntargets = ops[i].ntargets;
+    d.ncontrols = ops[i].ncontrols;
+    d.is_diagonal = ops[i].is_diagonal != 0;
+    for (int t = 0; t < d.ntargets; ++t) d.targets[t] = ops[i].targets[t];
+    for (int c = 0; c < d.ncontrols; ++c) d.controls[c] = ops[i].controls[c];
+    const size_t dim = size_t(1) << d.ntargets;
+    d.data.assign(ops[i].data, ops[i].data + 2 * (d.is_diagonal ? dim : dim * dim));
+  }
   memset(&p->stats, 0, sizeof(p->stats));
   p->stats.nops = nops;
   if (nqubits < 4) {
@@ -574,11 +596,11 @@ int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int
     std::string err;
     if (!plan_program(nqubits, dtype, p->canon, (flags & QB_PROGRAM_NO_FUSE) != 0, p->plan, err)) return fail(QB_ERR_UNSUPPORTED, err);
     fill_stats(p->plan, nqubits, dtype, nops, &p->stats);
-    p->canon.clear();
     if (!p->plan.blob.empty()) {
       std::lock_guard<std::mutex> lk(h->mu);
       DeviceGuard guard(h->device);
       QB_CUDA(cudaMalloc(&p->dev, p->plan.blob.size()));
+      p->dev_bytes = p->plan.blob.size();
       cudaError_t e = cudaMemcpyAsync(p->dev, p->plan.blob.data(), p->plan.blob.size(), cudaMemcpyHostToDevice, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // the host blob is released below
       if (e != cudaSuccess) {
@@ -624,8 +646,75 @@ int qb_program_run(qb_handle h, qb_program p, void* state, int flags, qb_program
   return QB_OK;
 }
 
+// ---- parameter slots: new matrices for some ops of a compiled program, schedule kept --------------------------------
+// Gate families follow backends/npmatrices.py (RX :79, RY :84, RZ :89, U1 :96-ish, CU1 :230, CRX/CRY/CRZ): evaluated in
+// double here so that a variational loop sends angles, not matrices.
+int qb_program_set_params(qb_handle h, qb_program p, const qb_param_update* updates, int nupdates) {
+  if (!h || !p || nupdates < 0 || (nupdates && !updates)) return fail(QB_ERR_INVALID, "bad parameter-update arguments");
+  if (p->device != h->device) return fail(QB_ERR_INVALID, "the program was compiled for another device");
+  if (nupdates == 0) return QB_OK;
+  std::string err;
+  for (int u = 0; u < nupdates; ++u) {
+    const qb_param_update& up = updates[u];
+    if (up.op_index < 0 || up.op_index >= p->nops) return fail(QB_ERR_INVALID, "parameter update: op index out of range");
+    OpDesc& d = p->descs[up.op_index];
+    std::vector<double> data;
+    if (up.family == QB_GATE_MATRIX) {
+      if (!up.matrix) return fail(QB_ERR_INVALID, "parameter update: null matrix");
+      data.assign(up.matrix, up.matrix + d.data.size());
+    } else if (!family_matrix(up.family, up.theta, d.ntargets, d.is_diagonal != 0, data) || data.size() != d.data.size()) {
+      return fail(QB_ERR_INVALID, "parameter update: gate family does not match the op it updates");
+    }
+    if (up.conjugate)
+      for (size_t i = 1; i < data.size(); i += 2) data[i] = -data[i];
+    d.data.swap(data);
+    CanonOp c;
+    if (!canonicalize(p->nqubits, d.data.data(), d.is_diagonal != 0, d.ntargets, d.targets, d.ncontrols, d.controls, c, err))
+      return fail(QB_ERR_INVALID, "parameter update, op " + std::to_string(up.op_index) + ": " + err);
+    p->canon[up.op_index] = std::move(c);
+  }
+  if (p->nqubits < 4) return QB_OK;  // applied gate by gate from `canon`
+  const bool no_fuse = (p->flags & QB_PROGRAM_NO_FUSE) != 0;
+  Plan fresh;
+  if (!plan_program(p->nqubits, p->dtype, p->canon, no_fuse, fresh, err, &p->plan)) {
+    // the structure changed (a rotation became an identity, a real matrix complex...): schedule from scratch
+    if (!plan_program(p->nqubits, p->dtype, p->canon, no_fuse, fresh, err)) return fail(QB_ERR_UNSUPPORTED, err);
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard guard(h->device);
+  const size_t need = fresh.blob.size();
+  if (need > p->dev_bytes) {
+    QB_CUDA(cudaStreamSynchronize(h->stream));  // launches may still read the old program
+    if (p->dev) cudaFree(p->dev);
+    p->dev = nullptr;
+    p->dev_bytes = 0;
+    QB_CUDA(cudaMalloc(&p->dev, need));
+    p->dev_bytes = need;
+  }
+  if (need > p->staging_bytes) {
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    if (p->staging) cudaFreeHost(p->staging);
+    p->staging = nullptr;
+    p->staging_bytes = 0;
+    QB_CUDA(cudaMallocHost(&p->staging, need));
+    p->staging_bytes = need;
+  } else {
+    QB_CUDA(cudaStreamSynchronize(h->stream));  // (the previous re-upload may still be reading the staging copy)
+  }
+  if (need) {
+    memcpy(p->staging, fresh.blob.data(), need);
+    // stream-ordered: earlier launches of this program have read the old blob by the time the copy runs
+    QB_CUDA(cudaMemcpyAsync(p->dev, p->staging, need, cudaMemcpyHostToDevice, h->stream));
+  }
+  std::vector<char>().swap(fresh.blob);
+  p->plan = std::move(fresh);
+  fill_stats(p->plan, p->nqubits, p->dtype, p->nops, &p->stats);
+  return QB_OK;
+}
+
 int qb_program_destroy(qb_handle h, qb_program p) {
   if (!p) return QB_OK;
+  if (p->staging) cudaFreeHost(p->staging);
   if (p->dev) {
     if (h) {
       std::lock_guard<std::mutex> lk(h->mu);

@@ -182,6 +182,11 @@ struct Plan {
   std::vector<char> blob;
   std::vector<int> sweep_of_op;
   int npasses = 0, ndiag = 0;
+  // the schedule itself, kept so that the same gate structure with NEW matrices (Circuit.set_parameters,
+  // models/circuit.py:788-857) is re-emitted without scheduling again: the merged ops each sweep took, in order, and
+  // the mixing / diagonal bit sets the schedule's legality rests on
+  std::vector<std::vector<uint32_t>> sweep_ops;
+  std::vector<uint64_t> xsets, dsets;
 };
 
 inline int env_int(const char* name, int dflt) {
@@ -964,7 +969,8 @@ inline bool tile_swizzle_ok(int nqubits, int dtype, uint64_t tile_mask) {
 }
 
 template <typename C>
-inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool no_fuse, Plan& plan, std::string& err) {
+inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool no_fuse, Plan& plan, std::string& err,
+                       const Plan* replay = nullptr) {
   const int Tfull = tile_bits_for(dtype);
   const int T = n < Tfull ? n : Tfull;
   // low bits every tile spans.  complex128 up to 30 qubits: 4 (256-byte rows; the tensor-map copy moves 128-byte
@@ -998,6 +1004,12 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     else
       for (auto& kv : p.fan) dset[q] |= uint64_t(1) << kv.first;
   }
+  if (replay && (replay->xsets != xset || replay->dsets != dset)) {
+    err = "the gate structure changed";
+    return false;
+  }
+  plan.xsets = xset;
+  plan.dsets = dset;
   const bool reorder = !no_fuse && !env_int("QB_NO_REORDER", 0);
   const size_t window = (size_t)env_int("QB_REORDER_WINDOW", 4096);
   std::vector<char> done(N, 0);
@@ -1057,9 +1069,20 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
       out_high = hi;
     };
     int best_dense = 0;
-    scan(~uint64_t(0), chosen, high, best_dense);
+    if (replay) {
+      // the schedule of the program this one re-parametrises: same ops per sweep, no scan
+      const size_t si = plan.sweeps.size();
+      if (si >= replay->sweep_ops.size()) { err = "replay: sweep count mismatch"; return false; }
+      for (uint32_t q : replay->sweep_ops[si]) {
+        if (q >= N || done[q]) { err = "replay: bad op index"; return false; }
+        chosen.push_back(q);
+        high |= xset[q] & ~lowmask;
+      }
+    } else {
+      scan(~uint64_t(0), chosen, high, best_dense);
+    }
     if (fatal) return false;
-    if (reorder && free_high > 0 && n > T) {
+    if (!replay && reorder && free_high > 0 && n > T) {
       // candidate tiles: the low bits plus a window of contiguous higher bits (widest light cone); keep the one that
       // takes the most mixing gates
       const int step = N <= 5000 ? 1 : 3;
@@ -1231,6 +1254,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
     const bool too_many_slots = (int)sb.slots.size() > SWEEP_MAX_SLOTS;
     if (!too_many_slots) finish_blob<C>(sb, hdr, plan.blob, sd);
     if (too_many_slots || hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) {
+      if (replay) { err = "replay: sweep program no longer fits"; return false; }
       if (chosen.size() <= 1) {
         err = too_many_slots ? "internal: too many per-tile slots in one sweep" : "internal: sweep program too large";
         return false;
@@ -1254,17 +1278,22 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
         fprintf(stderr, "\n");
       }
     plan.sweeps.push_back(sd);
+    plan.sweep_ops.emplace_back(chosen.begin(), chosen.end());
   }
   return true;
 }
 
-inline bool plan_program(int n, int dtype, const std::vector<CanonOp>& ops, bool no_fuse, Plan& plan, std::string& err) {
+// `replay`: the plan of a program with the same gate structure (targets, controls, which gates are diagonal): its
+// schedule is reused and only the passes are emitted again with the new numbers; false + err when the structure differs
+// (e.g. a rotation angle became 0 and the gate an identity) -- the caller then plans from scratch.
+inline bool plan_program(int n, int dtype, const std::vector<CanonOp>& ops, bool no_fuse, Plan& plan, std::string& err,
+                         const Plan* replay = nullptr) {
   plan = Plan();
   plan.sweep_of_op.assign(ops.size(), -1);
   std::vector<PlanOp> pops;
   merge_ops(ops, no_fuse, pops);
-  if (dtype == QB_C128) return build_plan<d2>(n, dtype, pops, no_fuse, plan, err);
-  return build_plan<f2>(n, dtype, pops, no_fuse, plan, err);
+  if (dtype == QB_C128) return build_plan<d2>(n, dtype, pops, no_fuse, plan, err, replay);
+  return build_plan<f2>(n, dtype, pops, no_fuse, plan, err, replay);
 }
 
 inline void fill_stats(const Plan& plan, int n, int dtype, int nops, qb_program_stats* st) {

@@ -551,6 +551,10 @@ class CompiledProgram:
         self.nsweeps = 0
         segments = split_segments(ops, nqubits, fuse and engine.permute_swap_runs)
         flags = 0 if fuse else _lib.QB_PROGRAM_NO_FUSE
+        # op index in ``ops`` -> (segment index, index inside that segment's program), or (-1, -1) for ops that became a
+        # permutation / a wide block (set_params addresses ops by their position in the compiled list)
+        self.op_segment = [(-1, -1)] * len(ops)
+        position = {id(op): i for i, op in enumerate(ops)}
         try:
             for kind, payload in segments:
                 if kind == "wide":
@@ -563,6 +567,8 @@ class CompiledProgram:
                     continue
                 if not payload:
                     continue
+                for local, op in enumerate(payload):
+                    self.op_segment[position[id(op)]] = (len(self.segments), local)
                 arr, keep = pack_ops(payload)
                 handle, st = ctypes.c_void_p(), _lib.QbProgramStats()
                 _lib.check(engine.lib.qb_program_create(engine.handle, nqubits, _DT[self.dtype], arr, len(payload), flags,
@@ -573,6 +579,48 @@ class CompiledProgram:
         except Exception:
             self.close()
             raise
+
+    # numpy mirror of qb_param_update (include/qibo_b200.h): records are filled column-wise, no per-gate Python work
+    PARAM_DTYPE = np.dtype([("op_index", "<i4"), ("family", "<i4"), ("conjugate", "<i4"), ("reserved", "<i4"),
+                            ("theta", "<f8", (3,)), ("matrix", "<u8")])
+
+    def param_records(self, indices, families, conjugates):
+        """Records for ``set_param_records``: one per op (index in the list the program was compiled from).  -> (records
+        with op_index already translated to the segment-local index, segment of every record)."""
+        assert self.PARAM_DTYPE.itemsize == ctypes.sizeof(_lib.QbParamUpdate)
+        rec = np.zeros(len(indices), dtype=self.PARAM_DTYPE)
+        seg = np.empty(len(indices), dtype=np.int64)
+        for k, index in enumerate(indices):
+            seg[k], rec["op_index"][k] = self.op_segment[index]
+        if (seg < 0).any():
+            raise NotImplementedError("an op inside a SWAP run / wide block has no parameter slot: compile again")
+        rec["family"], rec["conjugate"] = families, conjugates
+        return rec, seg
+
+    def set_param_records(self, rec, seg):
+        """qb_program_set_params on prepared records (``param_records``; the caller has filled ``theta`` / ``matrix``)."""
+        for s_ in np.unique(seg):
+            part = np.ascontiguousarray(rec[seg == s_])
+            _lib.check(self.engine.lib.qb_program_set_params(
+                self.engine.handle, self.segments[int(s_)][1], part.ctypes.data_as(ctypes.POINTER(_lib.QbParamUpdate)), len(part)))
+
+    def set_params(self, updates):
+        """New matrices for some ops of the program: ``updates`` = [(op index in the list the program was compiled from,
+        family, thetas, matrix or None, conjugate)], family one of _lib.QB_GATE_*.  The schedule is kept; the sweep
+        programs are emitted again and re-uploaded in stream order."""
+        if not updates:
+            return
+        rec, seg = self.param_records([u[0] for u in updates], [u[1] for u in updates], [1 if u[4] else 0 for u in updates])
+        keep = []
+        for k, (_, _, thetas, matrix, _) in enumerate(updates):
+            th = list(thetas)[:3]
+            rec["theta"][k, : len(th)] = th
+            if matrix is not None:
+                m = np.ascontiguousarray(matrix, dtype=np.complex128)
+                keep.append(m)
+                rec["matrix"][k] = m.ctypes.data
+        self.set_param_records(rec, seg)
+        del keep
 
     def close(self):
         for kind, payload in self.segments:

@@ -86,3 +86,40 @@ def permute_qubits(state, nqubits, dest_of_qubit):
     rc = lib.emul_permute_qubits(src.ctypes.data, dst.ctypes.data, nqubits, _lib.QB_C128 if src.dtype == np.complex128 else _lib.QB_C64, arr)
     assert rc == 0
     return dst
+
+
+def apply_program_replay(state, nqubits, ops_old, ops_new, fuse=True):
+    """Plan ``ops_old``, emit ``ops_new`` on that schedule (qb_program_set_params' path) and run it -> (state, replayed)."""
+    from qibo_b200 import _lib
+    from qibo_b200.ops import pack_ops
+
+    lib = load()
+    state = np.ascontiguousarray(state).copy()
+    dtype = _lib.QB_C128 if state.dtype == np.complex128 else _lib.QB_C64
+    a, keep_a = pack_ops(ops_old)
+    b, keep_b = pack_ops(ops_new)
+    replayed = ctypes.c_int()
+    lib.emul_apply_program_replay.restype = ctypes.c_int
+    lib.emul_apply_program_replay.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.QbOp), ctypes.POINTER(_lib.QbOp),
+                                              ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    rc = lib.emul_apply_program_replay(state.ctypes.data, nqubits, dtype, a, b, len(ops_old), 0 if fuse else _lib.QB_PROGRAM_NO_FUSE,
+                                       ctypes.byref(replayed))
+    if rc != 0:
+        raise RuntimeError(lib.emul_last_error().decode())
+    del keep_a, keep_b
+    return state, bool(replayed.value)
+
+
+def family_matrix(family, thetas, ntargets, is_diagonal=False):
+    lib = load()
+    th = (ctypes.c_double * 3)(*(list(thetas) + [0.0, 0.0, 0.0])[:3])
+    out = (ctypes.c_double * 64)()
+    count = ctypes.c_int()
+    lib.emul_family_matrix.restype = ctypes.c_int
+    lib.emul_family_matrix.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_int)]
+    rc = lib.emul_family_matrix(family, th, ntargets, int(is_diagonal), out, ctypes.byref(count))
+    if rc != 0:
+        raise ValueError("family does not match")
+    v = np.array(out[: count.value]).view(np.complex128)
+    return v if is_diagonal else v.reshape(1 << ntargets, 1 << ntargets)

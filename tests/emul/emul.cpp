@@ -10,6 +10,7 @@
 
 #include "../../qibo_b200/csrc/qb_passes.cuh"
 #include "../../qibo_b200/csrc/qb_permute.cuh"
+#include "../../qibo_b200/csrc/qb_families.hpp"
 
 using namespace qb;
 
@@ -112,6 +113,53 @@ extern "C" int emul_apply_program(void* state, int nqubits, int dtype, const qb_
     if (dtype == QB_C128) so ? run_sweep<double2, true>((double2*)state, blob) : run_sweep<double2, false>((double2*)state, blob);
     else so ? run_sweep<float2, true>((float2*)state, blob) : run_sweep<float2, false>((float2*)state, blob);
   }
+  return QB_OK;
+}
+
+static void run_plan(void* state, int dtype, Plan& plan) {
+  for (auto& sd : plan.sweeps) {
+    char* blob = plan.blob.data() + sd.blob_offset;
+    const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);
+    if (dtype == QB_C128) so ? run_sweep<double2, true>((double2*)state, blob) : run_sweep<double2, false>((double2*)state, blob);
+    else so ? run_sweep<float2, true>((float2*)state, blob) : run_sweep<float2, false>((float2*)state, blob);
+  }
+}
+
+// qb_program_set_params in miniature: plan `ops_old`, then emit `ops_new` (same gate structure, new numbers) on the OLD
+// schedule and run it; *replayed = 0 when the structure differed and the new ops were planned from scratch.
+extern "C" int emul_apply_program_replay(void* state, int nqubits, int dtype, const qb_op* ops_old, const qb_op* ops_new, int nops,
+                                         int flags, int* replayed) {
+  std::vector<CanonOp> a, b;
+  for (int i = 0; i < nops; ++i) {
+    CanonOp c, d;
+    if (!canonicalize(nqubits, ops_old[i].data, ops_old[i].is_diagonal != 0, ops_old[i].ntargets, ops_old[i].targets,
+                      ops_old[i].ncontrols, ops_old[i].controls, c, g_err) ||
+        !canonicalize(nqubits, ops_new[i].data, ops_new[i].is_diagonal != 0, ops_new[i].ntargets, ops_new[i].targets,
+                      ops_new[i].ncontrols, ops_new[i].controls, d, g_err))
+      return QB_ERR_INVALID;
+    a.push_back(c);
+    b.push_back(d);
+  }
+  const bool no_fuse = (flags & QB_PROGRAM_NO_FUSE) != 0;
+  Plan old_plan, fresh;
+  if (!plan_program(nqubits, dtype, a, no_fuse, old_plan, g_err)) return QB_ERR_UNSUPPORTED;
+  *replayed = 1;
+  if (!plan_program(nqubits, dtype, b, no_fuse, fresh, g_err, &old_plan)) {
+    *replayed = 0;
+    if (!plan_program(nqubits, dtype, b, no_fuse, fresh, g_err)) return QB_ERR_UNSUPPORTED;
+  } else if (fresh.sweeps.size() != old_plan.sweeps.size()) {
+    g_err = "replay changed the number of sweeps";
+    return QB_ERR_UNSUPPORTED;
+  }
+  run_plan(state, dtype, fresh);
+  return QB_OK;
+}
+
+extern "C" int emul_family_matrix(int family, const double* theta, int ntargets, int is_diagonal, double* out, int* count) {
+  std::vector<double> m;
+  if (!family_matrix(family, theta, ntargets, is_diagonal != 0, m)) return QB_ERR_INVALID;
+  for (size_t i = 0; i < m.size(); ++i) out[i] = m[i];
+  *count = (int)m.size();
   return QB_OK;
 }
 

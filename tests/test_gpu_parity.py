@@ -549,3 +549,67 @@ def test_wide_unitaries(eng, dtype):
     st = eng.upload(psi)
     eng.run_program(prog, st)
     assert np.abs(st.numpy() - ref).max() < t
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_compiled_program_parameter_slots(eng, dtype):
+    """qb_program_set_params through the C ABI: angles for the gate families, host matrices for everything else, on a
+    program that also holds a SWAP run (K8 segment) -- against the oracle on the updated ops."""
+    from qibo_b200 import _lib
+
+    n = 15
+    rng = np.random.default_rng(2)
+
+    def build(th):
+        named = []
+        for q in range(n):
+            named.append(("RY", (q,), (th[q],)))
+        for q in range(0, n - 1, 2):
+            named.append(("CZ", (q, q + 1), ()))
+        for q in range(n):
+            named.append(("RX", (q,), (th[n + q],)))
+        for q in range(1, n - 1, 2):
+            named.append(("CU1", (q, q + 1), (th[2 * n + q],)))
+        named.append(("CRZ", (0, n - 1), (th[3 * n],)))
+        ops = ops_from_named(named)
+        ops += ops_from_named([("SWAP", (q, n - 1 - q), ()) for q in range(3)])
+        ops += ops_from_named([("RZ", (q,), (th[3 * n + 1 + q],)) for q in range(n)])
+        return named, ops
+
+    th0 = rng.uniform(0.1, 6, 4 * n + 2)
+    named, ops = build(th0)
+    prog = eng.compile(n, dtype, ops)
+    psi = rand_state(n, 1, dtype)
+    fam = {"RY": _lib.QB_GATE_RY, "RX": _lib.QB_GATE_RX, "CU1": _lib.QB_GATE_CU1, "CRZ": _lib.QB_GATE_CRZ, "RZ": _lib.QB_GATE_RZ}
+    for step in range(3):
+        th = rng.uniform(0.1, 6, 4 * n + 2)
+        _, new_ops = build(th)
+        updates = []
+        for i, (old, new) in enumerate(zip(ops, new_ops)):
+            if old.name in fam:
+                if step == 1 and i % 2:  # every other one as a host matrix
+                    updates.append((i, _lib.QB_GATE_MATRIX, [], new.data, False))
+                else:
+                    theta = {"RY": None}.get("x")
+                    updates.append((i, fam[old.name], [_theta_of(new)], None, False))
+        prog.set_params(updates)
+        st = eng.upload(psi)
+        eng.run_program(prog, st)
+        assert np.abs(st.numpy() - oracle_run(psi, new_ops, n)).max() < tol(dtype), step
+    prog.close()
+
+
+def _theta_of(op):
+    """Angle of an RX / RY / RZ / CU1 / CRZ op from its matrix (test helper)."""
+    m = op.data
+    if op.name == "RY":
+        return 2 * np.arctan2(m[1, 0].real, m[0, 0].real)
+    if op.name == "RX":
+        return 2 * np.arctan2(-m[0, 1].imag, m[0, 0].real)
+    if op.name == "RZ":
+        return 2 * np.angle(m[1, 1])
+    if op.name == "CU1":
+        return np.angle(m[3, 3])
+    if op.name == "CRZ":
+        return 2 * np.angle(m[3, 3])
+    raise KeyError(op.name)

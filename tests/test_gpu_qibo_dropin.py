@@ -340,3 +340,69 @@ def test_measurement_registers_in_add_order_sharded_path(backends):
         res = be.execute_circuit(c, nshots=300)
         outs.append((res.frequencies(), res.frequencies(registers=True)))
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_set_parameters_reexecution_uses_parameter_slots(backends, dtype):
+    """Circuit.set_parameters + re-execution (models/circuit.py:788-857; the loop of models/variational.py:45-120): the
+    backend keeps ONE compiled program per Circuit object and patches the angles in place (qb_program_set_params).  Every
+    execution must equal the NumpyBackend's on the same angles -- plain, fused, density-matrix, gates outside the
+    angle families (U3, controlled_by), and an angle of 0 that changes the gate structure."""
+    from qibo import Circuit, gates
+
+    ours, ref = backends
+    ours.set_dtype(dtype)
+    ref.set_dtype(dtype)
+    n = 10
+    rng = np.random.default_rng(5)
+
+    def ansatz(density_matrix=False):
+        c = Circuit(n, density_matrix=density_matrix)
+        for layer in range(2):
+            c.add(gates.RY(q, theta=0.1) for q in range(n))
+            c.add(gates.CZ(q, q + 1) for q in range(0, n - 1, 2))
+            c.add(gates.RX(q, theta=0.1) for q in range(n))
+            c.add(gates.CU1(q, q + 1, theta=0.1) for q in range(1, n - 1, 2))
+            c.add(gates.RZ(q, theta=0.1) for q in range(0, n, 3))
+            c.add(gates.CRY(0, n - 1, theta=0.1))
+        c.add(gates.U3(2, 0.1, 0.2, 0.3))
+        c.add(gates.RY(4, theta=0.1).controlled_by(1, 7))
+        c.add(gates.M(0, 3))
+        return c
+
+    for density_matrix, nq in ((False, n), (True, 5)):
+        if density_matrix:
+            n_saved, n = n, nq  # noqa: F841 - a smaller register for the density matrix
+        c = ansatz(density_matrix) if not density_matrix else None
+        if density_matrix:
+            c = Circuit(nq, density_matrix=True)
+            c.add(gates.RY(q, theta=0.1) for q in range(nq))
+            c.add(gates.CRZ(0, 1, theta=0.2))
+            c.add(gates.U3(2, 0.1, 0.2, 0.3))
+            c.add(gates.CZ(1, 2))
+            c.add(gates.RX(3, theta=0.3))
+        nparams = len(c.get_parameters(format="flatlist"))
+        program_ids = set()
+        for step in range(4):
+            theta = rng.uniform(0.05, 6.2, nparams)
+            if step == 3:
+                theta[0] = 0.0  # RY(0): the gate becomes an identity -> the library plans afresh
+            c.set_parameters(theta)
+            a = ours.execute_circuit(c).state()
+            cached = getattr(c, "_qb200_program", None)
+            assert cached is not None
+            program_ids.add(id(cached["program"]))
+            c2 = c.copy(deep=True)
+            b = ref.execute_circuit(c2).state()
+            assert np.abs(ours.to_numpy(a) - b).max() < tol(dtype), (density_matrix, step)
+        assert len(program_ids) == 1  # compiled once, patched afterwards
+    # through circuit.fuse(): the members of the fused blocks keep their slots
+    c = ansatz()
+    fc = c.fuse(max_qubits=2)
+    for step in range(3):
+        theta = rng.uniform(0.05, 6.2, len(c.get_parameters(format="flatlist")))
+        fc.set_parameters(theta)
+        a = ours.execute_circuit(fc).state()
+        c.set_parameters(theta)
+        b = ref.execute_circuit(c.copy(deep=True)).state()
+        assert np.abs(ours.to_numpy(a) - b).max() < tol(dtype), step

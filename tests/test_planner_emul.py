@@ -95,9 +95,9 @@ def test_random_zoo(dtype, seed, low_bits):
     psi = rand_state(n, seed, dtype)
     ref = oracle_run(psi, ops, n)
     out, stats = emul.apply_program(psi, n, ops)
-    assert np.abs(out - ref).max() < tol(dtype) * (10 if dtype == "complex64" else 1)
+    assert np.abs(out - ref).max() < tol(dtype)
     out, stats = emul.apply_program(psi, n, ops, fuse=False)
-    assert np.abs(out - ref).max() < tol(dtype) * (10 if dtype == "complex64" else 1)
+    assert np.abs(out - ref).max() < tol(dtype)
 
 
 def test_fused_reference_queue(golden):
@@ -143,7 +143,7 @@ def test_six_qubit_dense_block(dtype):
     psi = rand_state(n, 3, dtype)
     ref = oracle_run(psi, ops, n)
     out, _ = emul.apply_program(psi, n, ops)
-    assert np.abs(out - ref).max() < tol(dtype) * (20 if dtype == "complex64" else 1)
+    assert np.abs(out - ref).max() < tol(dtype)
 
 
 def _phase_heavy_program(rng, n, ngates):
@@ -212,3 +212,64 @@ def test_planner_regressions():
         psi = rand_state(n, seed, "complex64")
         out, _ = emul.apply_program(psi, n, ops)
         assert np.abs(out - oracle_run(psi.astype(np.complex128), ops, n)).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ parameter slots (f2)
+def test_gate_families_match_reference_matrices():
+    """qb_program_set_params evaluates RX/RY/RZ/U1/CU1/CRX/CRY/CRZ from angles (csrc/qb_families.hpp): same matrices as
+    the oracle's restatement of backends/npmatrices.py."""
+    from qibo_b200 import _lib
+
+    fam = {"RX": _lib.QB_GATE_RX, "RY": _lib.QB_GATE_RY, "RZ": _lib.QB_GATE_RZ, "U1": _lib.QB_GATE_U1,
+           "CU1": _lib.QB_GATE_CU1, "CRX": _lib.QB_GATE_CRX, "CRY": _lib.QB_GATE_CRY, "CRZ": _lib.QB_GATE_CRZ}
+    for name, code in fam.items():
+        for theta in (0.0, 0.3, -1.7, np.pi, 5.9):
+            nt = 2 if name.startswith("C") else 1
+            got = emul.family_matrix(code, [theta], nt)
+            want = orc.gate_matrix(name, theta)
+            assert np.abs(got - want).max() < 1e-15, (name, theta)
+    assert np.abs(emul.family_matrix(fam["CU1"], [0.4], 2, is_diagonal=True) - np.diag(orc.gate_matrix("CU1", 0.4))).max() < 1e-15
+    with pytest.raises(ValueError):
+        emul.family_matrix(fam["RX"], [0.4], 1, is_diagonal=True)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("case", ["variational", "qft_angles", "random"])
+def test_schedule_replay_with_new_parameters(case, dtype):
+    """Circuit.set_parameters + re-execution (models/circuit.py:788-857): the ops of a planned program get new matrices,
+    the schedule is reused, only the passes are emitted again -- result equal to the oracle on the NEW ops.  A parameter
+    that changes the gate structure (angle 0 -> identity) falls back to a fresh plan."""
+    n = 14
+    rng = np.random.default_rng(3)
+
+    def build(thetas):
+        th = iter(thetas)
+        if case == "variational":
+            return ops_from_named(orc.variational_ops(n, 3, list(thetas)))
+        if case == "qft_angles":
+            named = []
+            for i in range(n):
+                named.append(("H", (i,), ()))
+                for j in range(i + 1, n):
+                    named.append(("CU1", (j, i), (float(next(th)),)))
+            return ops_from_named(named)
+        named = []
+        for k in range(60):
+            q = k % n
+            named.append((["RX", "RY", "RZ"][k % 3], (q,), (float(next(th)),)))
+            named.append((["CNOT", "CZ"][k % 2], (q, (q + 1 + k % 5) % n), ()))
+        return ops_from_named(named)
+
+    nparams = {"variational": 2 * 3 * n, "qft_angles": n * (n - 1) // 2, "random": 60}[case]
+    old = build(rng.uniform(0.1, 6.0, nparams))
+    new_thetas = rng.uniform(0.1, 6.0, nparams)
+    new = build(new_thetas)
+    psi = rand_state(n, 5, dtype)
+    out, replayed = emul.apply_program_replay(psi, n, old, new)
+    assert replayed
+    assert np.abs(out - oracle_run(psi, new, n)).max() < tol(dtype)
+    # structure change: one angle becomes 0 (RY(0) = identity, CU1(0) = identity)
+    new_thetas[3] = 0.0
+    new0 = build(new_thetas)
+    out, replayed = emul.apply_program_replay(psi, n, old, new0)
+    assert np.abs(out - oracle_run(psi, new0, n)).max() < tol(dtype)
