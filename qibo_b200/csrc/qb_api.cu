@@ -745,7 +745,10 @@ int qb_permute_qubits(qb_handle h, const void* src, void* dst, int nqubits, int 
   }
   PermParams p;
   memset(&p, 0, sizeof(p));
-  const int lowbits = dtype == QB_C128 ? 6 : 6;  // 2^6 amplitudes: 1 KiB (complex128) / 512 B (complex64) contiguous on both sides
+  // 2^6 amplitudes: 1 KiB (complex128) / 512 B (complex64) contiguous on both sides (QB_PERM_LOW_BITS: tuning knob)
+  int lowbits = env_int("QB_PERM_LOW_BITS", 6);
+  if (lowbits < 3) lowbits = 3;
+  if (lowbits > 6) lowbits = 6;
   perm_setup(nqubits, lowbits, lowbits, pi, p);
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);

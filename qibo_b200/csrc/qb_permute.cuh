@@ -141,7 +141,12 @@ __global__ void __launch_bounds__(PERM_THREADS) k8_permute(const C* __restrict__
 inline int launch_permute(cudaStream_t stream, int sm_count, const void* src, void* dst, int dtype, const PermParams& p) {
   const size_t esize = dtype == QB_C128 ? 16 : 8;
   const size_t smem = esize * (size_t)perm_pad(1u << p.tbits);
-  uint64_t cap = (uint64_t)sm_count * 3;
+  // CTAs per SM: as many tiles as fit the shared memory (3 x 65 KiB complex128 tiles; more when the tile is smaller)
+  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  per_sm = env_int("QB_PERM_CTAS_PER_SM", per_sm);
+  uint64_t cap = (uint64_t)sm_count * per_sm;
   unsigned grid = (unsigned)(p.ntiles < cap ? p.ntiles : cap);
   if (dtype == QB_C128) {
     cudaFuncSetAttribute(k8_permute<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
       C* tile = tiles + (size_t)b * tile_elems;
       const TileSlot* ts = tslots + b * SWEEP_MAX_SLOTS;
       mbar_wait(&full[i % SW_NFULL], (uint32_t)((i / SW_NFULL) & 1));  // tile data (async proxy) + slot states (loader warp) are visible
-      for (int pi = 0; pi < npasses; ++pi) {
+      // (tma.pad[0]: profiling knob QB_SWEEP_SKIP_COMPUTE -- the tile passes through untouched, which times the data
+      // movement of a sweep's tile shape alone)
+      for (int pi = 0; pi < (tma.pad[0] ? 0 : npasses); ++pi) {
         const PassHeader& ph = passes[pi];
         if (pi) {
           if (warp_private) __syncwarp();  // the pass only re-reads what this warp wrote
@@ -427,6 +429,7 @@ inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqub
   TmaDesc tma;
   if (!tma_describe(state, nqubits, dtype, sd.tile_mask, sd.swizzle != 0, tma) && sd.swizzle) return QB_ERR_UNSUPPORTED;  // planned for a swizzled tile
   const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);
+  tma.pad[0] = env_int("QB_SWEEP_SKIP_COMPUTE", 0);
   if (dtype == QB_C128) {
     if (so) sweep_kernel<double2, true><<<(unsigned)grid, sw_threads<double2, true>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
     else sweep_kernel<double2, false><<<(unsigned)grid, sw_threads<double2, false>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);

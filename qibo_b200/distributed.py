@@ -666,10 +666,12 @@ class ShardedProgram:
             self.run_segment(index, state, out, timed=timed, compiled=compiled)
         return out
 
-    def run_segment(self, index: int, state, out: "RunStats", timed: bool = False, compiled: bool = True):
+    def run_segment(self, index: int, state, out: "RunStats", timed: bool = False, compiled: bool = True, phase: Optional[int] = None):
         """One segment of the plan on this rank's shard.  Every rank runs segment ``index`` before any rank runs
         ``index + 1`` (the fences inside the exchanges enforce it across processes; SingleDeviceGroup does it by taking
-        turns)."""
+        turns).  ``phase``: an exchange segment whose transport cannot pipeline first applies the deferred ops to the whole
+        shard (phase 0) and then exchanges (phase 1); None = both.  (Ranks that take turns must all finish phase 0 before
+        the first one pulls a sibling's data in phase 1.)"""
         peer = state if isinstance(state, PeerShard) else None
         if peer is not None:
             state = peer.array
@@ -677,21 +679,29 @@ class ShardedProgram:
         spans = out.spans if timed else None
         tensor = state.tensor if hasattr(state, "tensor") else state  # (a permutation re-points the DeviceArray)
         if seg[0] == "local":
-            if seg[1]:
+            if seg[1] and phase in (None, 0):
                 self._run_local(seg, seg[1], state, peer, out, spans, compiled)
             return
         pairs = seg[1]
         piped = seg[4] if len(seg) > 4 else None
+        can_pipeline = piped is not None and self._can_pipeline(peer, pairs)
+        if phase in (None, 0) and piped is not None and not can_pipeline and piped.nlocal_ops:
+            # transport without chunk pipelining (NCCL staging, in-place kernels, CPU test hook): the deferred ops run on
+            # the whole shard
+            self._run_local(piped.full_key, piped.nlocal_ops, state, peer, out, None, compiled)
+        if phase == 0:
+            return
         ev = _span_begin(spans, tensor)
-        if piped is not None and not self._pipelined_exchange(state, peer, pairs, piped, out, compiled):
-            # transport without chunk pipelining (NCCL staging, CPU test hook): the deferred ops run on the whole shard
-            if piped.nlocal_ops:
-                self._run_local(piped.full_key, piped.nlocal_ops, state, peer, out, None, compiled)
-            piped = None
-        if piped is None:
+        if can_pipeline:
+            self._pipelined_exchange(state, peer, pairs, piped, out, compiled)
+        else:
             self._exchange_run(state, peer, tensor, pairs, out, sub_dest=seg[2], timed=timed, compiled=compiled)
         out.nexchanges += len(pairs)
         _span_end(spans, ev, "exchange", 1)
+
+    def _can_pipeline(self, peer, pairs) -> bool:
+        return (peer is not None and self._apply is None and self.alltoall and self.alltoall_push and self.pipeline
+                and alltoall_push_entries(self.rank, self.nlocal, pairs) is not None)
 
     def _run_local(self, key, ops, state, peer, out, spans, compiled):
         tensor = state.tensor if hasattr(state, "tensor") else state
@@ -725,11 +735,7 @@ class ShardedProgram:
         copy stream -- a DMA copy over NVLink peer memory that occupies no SM -- while the next chunk is being swept.
         Remote chunks go first, in order of rank XOR distance (every rank then receives from one sender at a time), the
         chunk that stays on this rank last.  Returns False when this transport is not available (no peer-mapped shard)."""
-        if peer is None or self._apply is not None or not (self.alltoall and self.alltoall_push and self.pipeline):
-            return False
         entries = alltoall_push_entries(self.rank, self.nlocal, pairs)
-        if entries is None:
-            return False
         k = len(pairs)
         sub_n = self.nlocal - k
         elem = state.tensor.element_size()
@@ -976,8 +982,9 @@ class SingleDeviceGroup:
         nseg = len(self.programs[0].segments)
         assert all(len(p.segments) == nseg for p in self.programs)
         for index in range(nseg):
-            for p, s, st in zip(self.programs, self.shards, stats):
-                p.run_segment(index, s, st, compiled=compiled)
+            for phase in (0, 1):
+                for p, s, st in zip(self.programs, self.shards, stats):
+                    p.run_segment(index, s, st, compiled=compiled, phase=phase)
         return stats
 
     def gather(self) -> np.ndarray:

@@ -322,3 +322,20 @@ def test_all_shards_on_one_gpu(case, n, dtype, world, layout, transport):
     grp.scatter(ref)
     grp.run(compiled=False)
     assert np.abs(grp.gather() - ref2).max() < t
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_reference_distributed_cases_under_torchrun():
+    """tests/dist_reference_cases.py: the reference's own distributed tests (entropy callbacks, measurements, collapse)
+    plus Norm / Overlap reductions and the sharded state handle, one process per GPU."""
+    import subprocess
+
+    from conftest import have_qibo
+
+    if not have_qibo():
+        pytest.skip("reference package not importable (baseline/_ref)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(HERE, "dist_reference_cases.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert '"passed"' in out.stdout
