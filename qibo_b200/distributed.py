@@ -693,11 +693,35 @@ class ShardedProgram:
             return
         ev = _span_begin(spans, tensor)
         if can_pipeline:
+            if phase not in (None, 1):
+                return
             self._pipelined_exchange(state, peer, pairs, piped, out, compiled)
-        else:
+        elif phase is not None and self._is_pairwise(peer, pairs, seg[2]):
+            # ranks taking turns: one pairwise exchange per phase (both partners must finish pair k before pair k + 1)
+            if phase - 1 < len(pairs):
+                self._exchange_run(state, peer, tensor, [pairs[phase - 1]], out, timed=timed, compiled=compiled)
+            if phase != len(pairs):
+                return
+        elif phase in (None, 1):
             self._exchange_run(state, peer, tensor, pairs, out, sub_dest=seg[2], timed=timed, compiled=compiled)
+        else:
+            return
         out.nexchanges += len(pairs)
         _span_end(spans, ev, "exchange", 1)
+
+    def _is_pairwise(self, peer, pairs, sub_dest) -> bool:
+        """True when ``_exchange_run`` would carry the run out as one half-shard swap per pair."""
+        if sub_dest is not None:
+            return False
+        use_a2a = peer is not None and self.alltoall and len(pairs) >= self.alltoall_min
+        if use_a2a and self.alltoall_push and len(pairs) <= 3 and alltoall_push_entries(self.rank, self.nlocal, pairs) is not None:
+            return False
+        return not (use_a2a and alltoall_entries(self.rank, self.nlocal, pairs) is not None)
+
+    def segment_phases(self, index: int) -> int:
+        """Phases a group of ranks that take turns must step through for segment ``index`` (run_segment's ``phase``)."""
+        seg = self.segments[index]
+        return 1 if seg[0] == "local" else 1 + max(1, len(seg[1]))
 
     def _can_pipeline(self, peer, pairs) -> bool:
         return (peer is not None and self._apply is None and self.alltoall and self.alltoall_push and self.pipeline
@@ -982,7 +1006,7 @@ class SingleDeviceGroup:
         nseg = len(self.programs[0].segments)
         assert all(len(p.segments) == nseg for p in self.programs)
         for index in range(nseg):
-            for phase in (0, 1):
+            for phase in range(max(p.segment_phases(index) for p in self.programs)):
                 for p, s, st in zip(self.programs, self.shards, stats):
                     p.run_segment(index, s, st, compiled=compiled, phase=phase)
         return stats

@@ -1,8 +1,5 @@
-"""Where the host time of the plugin-level e2e step goes: cProfile of `QFT(n) + M -> c(nshots).frequencies()`."""
-import cProfile
-import io
+"""Where the time of the plugin-level e2e step goes: phases separated by device synchronisation + allocator statistics."""
 import os
-import pstats
 import sys
 import time
 
@@ -14,18 +11,43 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 import torch  # noqa: E402
 
 qibo, be = bench.plugin_backend("complex128")
-for _ in range(2):
-    bench.plugin_qft_step(n, 10, 1000)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-bench.plugin_qft_step(n, 10, 1000)
-torch.cuda.synchronize()
-print("step wall ms", 1e3 * (time.perf_counter() - t0))
-pr = cProfile.Profile()
-pr.enable()
-bench.plugin_qft_step(n, 10, 1000)
-torch.cuda.synchronize()
-pr.disable()
-s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(35)
-print(s.getvalue())
+from qibo import gates  # noqa: E402
+from qibo.models import QFT  # noqa: E402
+
+
+def stats():
+    s = torch.cuda.memory_stats()
+    return {k: s[k] for k in ("num_device_alloc", "num_device_free", "num_alloc_retries", "num_ooms")} | {
+        "reserved_GiB": round(torch.cuda.memory_reserved() / 2**30, 1), "allocated_GiB": round(torch.cuda.memory_allocated() / 2**30, 1)}
+
+
+def sync():
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
+for step in range(4):
+    t0 = sync()
+    c = QFT(n)
+    c.add(gates.M(*range(10)))
+    t1 = sync()
+    res = c(nshots=1000)
+    t2 = sync()
+    f = res.frequencies(binary=False)
+    t3 = sync()
+    print(f"step {step}: build {1e3 * (t1 - t0):.1f} ms, execute {1e3 * (t2 - t1):.1f} ms, frequencies {1e3 * (t3 - t2):.1f} ms", stats(), flush=True)
+    del c, res, f
+# the pieces of execute
+eng = be.engine_gpu
+from qibo_b200 import circuits  # noqa: E402
+
+for step in range(3):
+    t0 = sync()
+    st = eng.basis_state(n, "complex128")
+    t1 = sync()
+    eng.apply_program(st, n, circuits.qft(n))
+    t2 = sync()
+    p = eng.probabilities(st, list(range(10)), n)
+    t3 = sync()
+    print(f"engine {step}: zero state {1e3 * (t1 - t0):.1f} ms, program {1e3 * (t2 - t1):.1f} ms, marginal {1e3 * (t3 - t2):.1f} ms", stats(), flush=True)
+    del st, p
