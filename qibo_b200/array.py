@@ -25,6 +25,46 @@ def torch_dtype(dtype):
     return _NP2TORCH[np.dtype(dtype)]
 
 
+import os as _os
+
+STREAM_D2H_MIN_BYTES = int(_os.environ.get("QB_STREAM_D2H_MIN_BYTES", 1 << 28))  # below: one plain copy
+STREAM_D2H_CHUNK_BYTES = int(_os.environ.get("QB_STREAM_D2H_CHUNK_BYTES", 1 << 27))
+_staging = {}
+
+
+def _stream_to_host(t: torch.Tensor) -> torch.Tensor:
+    """Chunked, double-buffered device->host copy of a contiguous CUDA tensor into a new (pageable) CPU tensor."""
+    flat = t.reshape(-1).view(torch.uint8)
+    out = torch.empty(flat.numel(), dtype=torch.uint8)
+    key = (t.device.index, STREAM_D2H_CHUNK_BYTES)
+    if key not in _staging:
+        _staging[key] = ([torch.empty(STREAM_D2H_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+                         torch.cuda.Stream(device=t.device))
+    bufs, side = _staging[key]
+    side.wait_stream(torch.cuda.current_stream(t.device))  # the state must be complete before it is read
+    total = flat.numel()
+    starts = list(range(0, total, STREAM_D2H_CHUNK_BYTES))
+    events = [None, None]
+
+    def issue(i):
+        a = starts[i]
+        b = min(total, a + STREAM_D2H_CHUNK_BYTES)
+        with torch.cuda.stream(side):
+            bufs[i % 2][: b - a].copy_(flat[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        events[i % 2] = ev
+
+    issue(0)
+    for i, a in enumerate(starts):
+        b = min(total, a + STREAM_D2H_CHUNK_BYTES)
+        events[i % 2].synchronize()
+        if i + 1 < len(starts):
+            issue(i + 1)  # (the other staging buffer: its previous contents were consumed one iteration ago)
+        out[a:b].copy_(bufs[i % 2][: b - a])
+    return out.view(t.dtype).reshape(t.shape)
+
+
 class DeviceArray(NDArrayOperatorsMixin):
     __array_priority__ = 1000
 
@@ -62,7 +102,13 @@ class DeviceArray(NDArrayOperatorsMixin):
 
     # ---- host interop ---------------------------------------------------------------------
     def numpy(self):
-        return self.tensor.detach().cpu().numpy()
+        """Host copy (QuantumState.state(numpy=True) / dump, result.py:69-88, 116-163).  Large states stream through two
+        pinned staging buffers: the device->host DMA of chunk i + 1 overlaps the (multi-threaded) host copy of chunk i
+        into the result, instead of one pageable cudaMemcpy of the whole state."""
+        t = self.tensor.detach()
+        if t.numel() * t.element_size() < STREAM_D2H_MIN_BYTES or not t.is_contiguous():
+            return t.cpu().numpy()
+        return _stream_to_host(t).numpy()
 
     def __array__(self, dtype=None, copy=None):
         out = self.numpy()

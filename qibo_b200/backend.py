@@ -549,6 +549,26 @@ class B200Backend(NumpyBackend):
             expval += float(np.real(coefficient * value))
         return expval
 
+    def expectation_value(self, hamiltonian, state, normalize):
+        """<state| H |state> for a dense Hamiltonian matrix (abstract.py:2807-2825; Hamiltonian.expectation_from_state)
+        with the state left on the device: H is uploaded, H|psi> is one library GEMV (cuBLAS through torch.matmul -- a
+        plain dense product, the one place a library kernel is the right tool), the inner product is K9.  Density
+        matrices: Re tr(H rho).  Sparse Hamiltonians and host states keep the reference's path."""
+        if not isinstance(state, DeviceArray) or state.dtype.kind != "c" or self.is_sparse(hamiltonian):
+            return super().expectation_value(hamiltonian, state, normalize)
+        h = torch.as_tensor(np.asarray(hamiltonian)).to(state.tensor.device).to(state.tensor.dtype)
+        if state.ndim == 2:
+            ev = float(torch.einsum("ij,ji->", h, state.tensor).real.item())
+            if normalize:
+                ev /= float(torch.diagonal(state.tensor).sum().real.item())
+            return ev
+        n = int(np.log2(state.shape[0]))
+        hpsi = DeviceArray(torch.matmul(h, state.tensor))
+        ev = float(np.real(self.engine_gpu.vdot(state, hpsi, n)))
+        if normalize:
+            ev /= self.engine_gpu.norm2(state)
+        return ev
+
     def overlap_statevector(self, state_1, state_2, dtype=None):
         """<state_1|state_2> (abstract.py:2180-2190) with K9 when both states already live on the device."""
         if (isinstance(state_1, DeviceArray) and isinstance(state_2, DeviceArray) and state_1.dtype == state_2.dtype

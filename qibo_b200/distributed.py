@@ -757,8 +757,10 @@ class ShardedProgram:
         k leading local qubits (``piped.ops``, already re-indexed to the chunk's nlocal - k qubits) run on one chunk at a
         time on the compute stream; as soon as a chunk is done it leaves for the destination rank's second buffer on the
         copy stream -- a DMA copy over NVLink peer memory that occupies no SM -- while the next chunk is being swept.
-        Remote chunks go first, in order of rank XOR distance (every rank then receives from one sender at a time), the
-        chunk that stays on this rank last.  Returns False when this transport is not available (no peer-mapped shard)."""
+        Remote chunks are swept and sent in order of rank XOR distance (every rank then receives from one sender at a
+        time); the chunk that stays on this rank is copied first, unswept, while the copy engine is still idle, and swept
+        in the second buffer at the end (measured on 2 GPUs, QFT(33): 212.9 ms without the pipeline, 177.5 ms with it and
+        the local chunk copied last).  The ranks then continue in their second buffers."""
         entries = alltoall_push_entries(self.rank, self.nlocal, pairs)
         k = len(pairs)
         sub_n = self.nlocal - k
@@ -777,21 +779,37 @@ class ShardedProgram:
         order = sorted(entries, key=lambda e: ((e[0] ^ self.rank) == 0, e[0] ^ self.rank))
         from qibo_b200.array import DeviceArray
 
+        def sweep_chunk(view):
+            if not piped.ops:
+                return
+            st = eng.run_program(prog, view) if prog is not None else eng.apply_program(view, sub_n, piped.ops)
+            out.nsweeps += st.nsweeps
+            out.nchunk_sweeps += st.nsweeps
+
+        # the chunk that stays on this rank moves FIRST, unswept, while the copy engine has nothing else to do (the remote
+        # chunks are still being swept); its gates then run on the copy, in the second buffer, at the end
+        start = torch.cuda.Event()
+        start.record(main)
+        copy.wait_event(start)
+        stays = None
         for r2, a, b, lo, hi in order:
-            if piped.ops:
-                view = DeviceArray(state.tensor[a : a + (1 << sub_n)])
-                if prog is not None:
-                    st = eng.run_program(prog, view)
-                else:
-                    st = eng.apply_program(view, sub_n, piped.ops)
-                out.nsweeps += st.nsweeps
-                out.nchunk_sweeps += st.nsweeps
+            if r2 == self.rank:
+                eng.memcpy_async(dst[r2] + b * elem, src0 + a * elem, (hi - lo) * elem, copy.cuda_stream)
+                stays = torch.cuda.Event()
+                stays.record(copy)
+                stays_view = DeviceArray(peer.alt.tensor[b : b + (1 << sub_n)])
+        for r2, a, b, lo, hi in order:
+            if r2 == self.rank:
+                continue
+            sweep_chunk(DeviceArray(state.tensor[a : a + (1 << sub_n)]))
             done = torch.cuda.Event()
             done.record(main)
             copy.wait_event(done)
             eng.memcpy_async(dst[r2] + b * elem, src0 + a * elem, (hi - lo) * elem, copy.cuda_stream)
-            if r2 != self.rank:
-                out.exchange_bytes += 2 * elem * (hi - lo)
+            out.exchange_bytes += 2 * elem * (hi - lo)
+        if stays is not None:
+            main.wait_event(stays)
+            sweep_chunk(stays_view)
         landed = torch.cuda.Event()
         landed.record(copy)
         main.wait_event(landed)
@@ -1109,7 +1127,7 @@ def _apply_special(backend, gate, shard, n, measure, gather_max):
             target = backend.to_numpy(cb.state) if isinstance(cb.state, DeviceArray) else np.asarray(cb.state)
             nl = measure.nlocal
             mine = backend.engine_gpu.upload(np.ascontiguousarray(target[measure.rank << nl : (measure.rank + 1) << nl]).astype(shard.dtype))
-            cb.append(abs(measure.global_vdot(mine, shard)))
+            cb.append(measure.global_vdot(mine, shard))  # <target|state>, complex, as overlap_statevector returns it (abstract.py:2180-2190)
             return
         if n > gather_max:
             raise_error(NotImplementedError, f"callback {kind} needs the full state, which is not gathered above {gather_max} qubits")

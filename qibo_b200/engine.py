@@ -52,6 +52,7 @@ class Engine:
         _lib.check(self.lib.qb_create(self.device_index, ctypes.c_void_p(stream), ctypes.byref(handle)))
         self.handle = handle
         self._stream = stream
+        self._freeze_imports()
         self.last_stats = None
         self.permute_swap_runs = True
         self.exact_scan_max_bins = EXACT_SCAN_MAX_BINS
@@ -82,12 +83,25 @@ class Engine:
 
     _gc_frozen = False
 
+    @classmethod
+    def _freeze_imports(cls):
+        """Once per process, when the first engine is created (i.e. right after the imports, before any circuit of this
+        backend exists): move the long-lived module objects (qibo, sympy, torch: ~3e5 tracked objects) out of the cyclic
+        collector's scans, so that the collections ``_alloc`` triggers under memory pressure cost < 1 ms instead of
+        ~170 ms.  Objects created later are collected as usual.  QB_NO_GC_FREEZE=1 leaves the collector alone."""
+        if cls._gc_frozen or os.environ.get("QB_NO_GC_FREEZE", "") not in ("", "0"):
+            return
+        import gc
+
+        gc.collect()
+        gc.freeze()
+        cls._gc_frozen = True
+
     def _alloc(self, shape, tdtype) -> torch.Tensor:
         """torch.empty with one precaution for states that fill a large part of the device: the reference keeps a finished
         Circuit (and through ``_final_state`` its 2^n amplitudes) alive in a reference cycle (Circuit -> M gate ->
         MeasurementResult -> Circuit), so the buffer of the PREVIOUS execution is only returned by Python's cyclic
-        collector.  Before a large allocation that would not fit, collect; the first time this happens the long-lived
-        module objects are frozen out of the collector's scans (a full collection drops from ~170 ms to < 1 ms)."""
+        collector.  Before a large allocation that would not fit, collect."""
         nbytes = int(np.prod(shape)) * torch.empty((), dtype=tdtype).element_size()
         if nbytes >= (1 << 30):
             free, _ = torch.cuda.mem_get_info(self.device)
@@ -101,14 +115,11 @@ class Engine:
             torch.cuda.empty_cache()
             return torch.empty(shape, dtype=tdtype, device=self.device)
 
-    @classmethod
-    def _reclaim(cls):
+    @staticmethod
+    def _reclaim():
         import gc
 
         gc.collect()
-        if not cls._gc_frozen:
-            gc.freeze()
-            cls._gc_frozen = True
 
     def basis_state(self, nqubits: int, dtype="complex128", index: int = 0) -> DeviceArray:
         """zero_state (abstract.py:2243-2273) generalised to any basis index."""

@@ -98,7 +98,7 @@ def main():
         c.add(gates.H(n - 1))
         c.add(gates.CallbackGate(ov))
         st = be.execute_circuit(c).state()
-        results.append((be.to_numpy(st), [float(np.real(be.to_numpy(x))) for x in norm[:]], [float(np.real(be.to_numpy(x))) for x in ov[:]]))
+        results.append((be.to_numpy(st), [float(np.real(be.to_numpy(x))) for x in norm[:]], [complex(be.to_numpy(x)) for x in ov[:]]))
     close(results[0][0], results[1][0])
     np.testing.assert_allclose(results[0][1], results[1][1], atol=1e-12)
     np.testing.assert_allclose(results[0][2], results[1][2], atol=1e-12)

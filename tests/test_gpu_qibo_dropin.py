@@ -406,3 +406,53 @@ def test_set_parameters_reexecution_uses_parameter_slots(backends, dtype):
         c.set_parameters(theta)
         b = ref.execute_circuit(c.copy(deep=True)).state()
         assert np.abs(ours.to_numpy(a) - b).max() < tol(dtype), step
+
+
+def test_dense_hamiltonian_expectation_on_device(backends):
+    """Backend.expectation_value (abstract.py:2807-2825) through Hamiltonian.expectation on a device-resident final state
+    and on a density matrix, against the NumpyBackend."""
+    from qibo import Circuit, gates, hamiltonians
+
+    ours, ref = backends
+    n = 6
+    vals = []
+    for be in (ours, ref):
+        h = hamiltonians.XXZ(n, delta=0.7, dense=True, backend=be)
+        c = Circuit(n)
+        c.add(gates.RY(q, theta=0.4 + 0.3 * q) for q in range(n))
+        c.add(gates.CNOT(q, q + 1) for q in range(n - 1))
+        st = be.execute_circuit(c).state()
+        cd = Circuit(n, density_matrix=True)
+        cd.add(gates.RX(q, theta=0.2 + 0.1 * q) for q in range(n))
+        cd.add(gates.CZ(0, 3))
+        rho = be.execute_circuit(cd).state()
+        vals.append((float(h.expectation_from_state(st)), float(h.expectation_from_state(rho)), float(h.expectation_from_state(st, normalize=True))))
+    assert np.abs(np.array(vals[0]) - np.array(vals[1])).max() < 1e-12
+
+
+def test_state_host_io_streaming_and_dump_load(backends, tmp_path, monkeypatch):
+    """f3: `state(numpy=True)`, `QuantumState.dump` / `load` (result.py:69-88, 116-163) on device-resident states; the
+    chunked pinned device->host path (qibo_b200/array.py) gives the same bytes as a plain copy."""
+    from qibo import Circuit, gates
+    from qibo.result import QuantumState, load_result
+
+    import qibo_b200.array as qarr
+
+    ours, ref = backends
+    n = 18
+    c = Circuit(n)
+    c.add(gates.RY(q, theta=0.1 + 0.05 * q) for q in range(n))
+    c.add(gates.CNOT(q, q + 1) for q in range(n - 1))
+    res = ours.execute_circuit(c)
+    plain = res.state(numpy=True)
+    monkeypatch.setattr(qarr, "STREAM_D2H_MIN_BYTES", 1 << 16)
+    monkeypatch.setattr(qarr, "STREAM_D2H_CHUNK_BYTES", (1 << 18) + 4096)  # ragged last chunk
+    qarr._staging.clear()
+    streamed = res.state().numpy()
+    np.testing.assert_array_equal(streamed, plain)
+    assert np.abs(plain - ref.execute_circuit(c.copy(deep=True)).state()).max() < 1e-12
+    path = tmp_path / "state.npy"
+    res.dump(str(path))
+    loaded = load_result(str(path))
+    assert isinstance(loaded, QuantumState)
+    np.testing.assert_array_equal(np.asarray(ours.to_numpy(loaded.state())), plain)
