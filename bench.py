@@ -394,7 +394,7 @@ def config3_leg(qibo, be, torch, small=False):
     # VQE-style loop on the same Circuit object: new angles every step (Circuit.set_parameters, models/circuit.py:788-857),
     # the backend patches its compiled program in place (qb_program_set_params) instead of planning again
     rng = np.random.default_rng(3)
-    nparams = len(c.get_parameters(format="flatlist"))
+    nparams = len(c.get_parameters("flatlist"))
     set_ms, patch_ms, exec_s = [], [], []
     for _ in range(4):
         theta = 2 * np.pi * rng.random(nparams)

@@ -480,9 +480,21 @@ class B200Backend(NumpyBackend):
             state_copy = self._to_device(initial_state)
 
         program_cache = {}  # the plain-gate runs of the queue, compiled once for all shots
+        sharded = False
+        if not density_matrix and circuit.accelerators:
+            from qibo_b200 import distributed
+
+            sharded = distributed.world_size() > 1
         for _ in range(nshots):
-            state = state_copy.copy()
-            state = self._run_queue(circuit.queue, state, nqubits, density_matrix, substitute_symbols=True, program_cache=program_cache)
+            if sharded:
+                # abstract.py:2579-2582: every shot is one distributed execution (collapses act on the sharded state)
+                for gate in circuit.queue:
+                    if gate.symbolic_parameters:
+                        gate.substitute_symbols()
+                state = distributed.execute_circuit(self, circuit, state_copy, return_state=True)
+            else:
+                state = state_copy.copy()
+                state = self._run_queue(circuit.queue, state, nqubits, density_matrix, substitute_symbols=True, program_cache=program_cache)
             if density_matrix:
                 final_states.append(state)
             if circuit.measurements:

@@ -1137,10 +1137,11 @@ def _apply_special(backend, gate, shard, n, measure, gather_max):
     raise_error(NotImplementedError, f"{name} is not supported inside distributed circuits")
 
 
-def execute_circuit(backend, circuit, initial_state=None, nshots=None):
+def execute_circuit(backend, circuit, initial_state=None, nshots=None, return_state: bool = False):
     """``Backend.execute_distributed_circuit`` under torchrun: every rank calls it with the same circuit (and the same
     RNG seed).  The queue is cut at the special gates (distcircuit.py:278-284: callbacks and collapsing measurements see
-    the full state); each run of plain gates is one ShardedProgram."""
+    the full state); each run of plain gates is one ShardedProgram.  ``return_state``: the gathered final state itself
+    (what the per-shot loop of execute_circuit_repeated asks for, abstract.py:2579-2582)."""
     from qibo.config import raise_error
     from qibo.result import CircuitResult, MeasurementOutcomes, QuantumState
 
@@ -1189,6 +1190,10 @@ def execute_circuit(backend, circuit, initial_state=None, nshots=None):
                     shard = prog.scatter(host)
             _apply_special(backend, payload, shard, n, measure, gather_max)
         first = False
+    if return_state:
+        if n > gather_max:
+            raise_error(NotImplementedError, f"per-shot re-execution gathers the state: not above {gather_max} qubits")
+        return eng.upload(prog.gather(shard))
     if n > gather_max:
         # too large to replicate: measurement outcomes come from the sharded state (dist_measure.py) -- marginal over the
         # measured qubits (all-reduce), then inverse-CDF sampling with the global legacy RNG as sample_shots does

@@ -141,22 +141,38 @@ def main():
     os.environ.pop("QB_GATHER_MAX_QUBITS")
     done.append("registers_in_add_order (gathered and sharded)")
 
-    # ---- collapsing measurement inside a distributed circuit (distcircuit.py:278-284; tests/test_measurements_collapse.py)
-    outs = []
-    for be, kw in ((ours, acc), (ref, None)):
+    # ---- collapsing measurement inside a distributed circuit (distcircuit.py:278-284): ONE distributed execution against
+    # the same gates applied one by one on the NumpyBackend with the same seed (same outcome, same collapsed state) ...
+    def collapse_circuit(kw):
         c = Circuit(6, kw) if kw else Circuit(6)
         c.add(gates.H(q) for q in range(6))
         c.add(gates.CNOT(0, 4))
         m = c.add(gates.M(0, 3, collapse=True))
         c.add(gates.RY(2, theta=0.4))
         c.add(gates.CNOT(5, 1))
+        return c, m
+
+    c, m = collapse_circuit(acc)
+    ours.set_seed(123)
+    got = ours.execute_distributed_circuit(c).state()
+    t, mt = collapse_circuit(None)
+    ref.set_seed(123)
+    st = ref.zero_state(6)
+    for gate in t.queue:
+        st = gate.apply(ref, st, 6)
+    close(got, st)
+    assert [int(x) for x in m.result.samples()[0]] == [int(x) for x in mt.result.samples()[0]]
+    # ... and through Circuit execution, which re-executes per shot (abstract.py:2532-2636, :2579-2582): same seed, same
+    # frequencies of the final measurement
+    outs = []
+    for be, kw in ((ours, acc), (ref, None)):
+        c, m = collapse_circuit(kw)
         c.add(gates.M(1, 5))
-        be.set_seed(123)
-        res = be.execute_circuit(c, nshots=64)
-        outs.append((be.to_numpy(res.state()), [int(x) for x in m.samples()[0]], dict(res.frequencies())))
-    close(outs[0][0], outs[1][0])
-    assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
-    done.append("collapsing_measurement_in_distributed_circuit")
+        be.set_seed(321)
+        res = be.execute_circuit(c, nshots=12)
+        outs.append(dict(res.frequencies()))
+    assert outs[0] == outs[1], outs
+    done.append("collapsing_measurement_in_distributed_circuit (one execution + per-shot re-execution)")
 
     # ---- a register too large to gather without measurements: a sharded state handle instead of an error
     os.environ["QB_GATHER_MAX_QUBITS"] = "0"

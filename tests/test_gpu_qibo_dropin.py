@@ -381,7 +381,7 @@ def test_set_parameters_reexecution_uses_parameter_slots(backends, dtype):
             c.add(gates.U3(2, 0.1, 0.2, 0.3))
             c.add(gates.CZ(1, 2))
             c.add(gates.RX(3, theta=0.3))
-        nparams = len(c.get_parameters(format="flatlist"))
+        nparams = len(c.get_parameters("flatlist"))
         program_ids = set()
         for step in range(4):
             theta = rng.uniform(0.05, 6.2, nparams)
@@ -400,7 +400,7 @@ def test_set_parameters_reexecution_uses_parameter_slots(backends, dtype):
     c = ansatz()
     fc = c.fuse(max_qubits=2)
     for step in range(3):
-        theta = rng.uniform(0.05, 6.2, len(c.get_parameters(format="flatlist")))
+        theta = rng.uniform(0.05, 6.2, len(c.get_parameters("flatlist")))
         fc.set_parameters(theta)
         a = ours.execute_circuit(fc).state()
         c.set_parameters(theta)
