@@ -371,8 +371,6 @@ def test_set_parameters_reexecution_uses_parameter_slots(backends, dtype):
         return c
 
     for density_matrix, nq in ((False, n), (True, 5)):
-        if density_matrix:
-            n_saved, n = n, nq  # noqa: F841 - a smaller register for the density matrix
         c = ansatz(density_matrix) if not density_matrix else None
         if density_matrix:
             c = Circuit(nq, density_matrix=True)
@@ -400,7 +398,8 @@ def test_set_parameters_reexecution_uses_parameter_slots(backends, dtype):
     c = ansatz()
     fc = c.fuse(max_qubits=2)
     for step in range(3):
-        theta = rng.uniform(0.05, 6.2, len(c.get_parameters("flatlist")))
+        # (one entry per gate: the shallow copy behind fuse() loses the flat-list bookkeeping, models/circuit.py:410-411)
+        theta = [tuple(rng.uniform(0.05, 6.2, g.nparams)) if g.nparams > 1 else float(rng.uniform(0.05, 6.2)) for g in c.trainable_gates]
         fc.set_parameters(theta)
         a = ours.execute_circuit(fc).state()
         c.set_parameters(theta)
