@@ -161,7 +161,7 @@ def main():
     for gate in t.queue:
         st = gate.apply(ref, st, 6)
     close(got, st)
-    assert [int(x) for x in m.result.samples()[0]] == [int(x) for x in mt.result.samples()[0]]
+    assert [int(x) for x in m.samples()[0]] == [int(x) for x in mt.samples()[0]]  # (Circuit.add returns the M gate's result)
     # ... and through Circuit execution, which re-executes per shot (abstract.py:2532-2636, :2579-2582): same seed, same
     # frequencies of the final measurement
     outs = []
