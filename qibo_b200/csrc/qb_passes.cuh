@@ -294,6 +294,41 @@ QB_HD void stage_chain(C (&v)[GPT][1 << R], const uint32_t* g, const bool* valid
   }
 }
 
+// PASS_FULL_STAGE: R add/sub stages with their fans on register bits R-1 .. 0 as one basic block (qb_planner.hpp)
+struct alignas(16) MicroTab { uint16_t la, R; uint32_t tb_off, n_ext, gt_off; };  // second 16 bytes of MicroOp
+template <typename C, int R, int GPT, int I, uint32_t SMASK, uint32_t RMASK>
+QB_HD void stage_full(C (&v)[GPT][1 << R], const uint32_t* g, const MicroOp* mops, const char* blob, const TileSlot* ts) {
+  if constexpr (I >= 0) {
+    if constexpr ((SMASK >> I) & 1u) {
+      constexpr int INDEX = __builtin_popcount(SMASK >> (I + 1));  // ops are stored by descending register bit
+      const MicroOp& mo = mops[INDEX];
+      const MicroHot hot = *reinterpret_cast<const MicroHot*>(&mo);
+      const MicroTab tab = *reinterpret_cast<const MicroTab*>(reinterpret_cast<const char*>(&mo) + 16);
+      const C ext = slot_ext<C>(ts[hot.w0 >> 16]);
+      const C* ta = reinterpret_cast<const C*>(blob + hot.payload);
+      const C* tb = reinterpret_cast<const C*>(blob + tab.tb_off);
+      const C* gt = reinterpret_cast<const C*>(blob + tab.gt_off);
+      const uint32_t la = tab.la, ma = (1u << la) - 1u;
+      if constexpr ((RMASK >> I) & 1u) {
+        const C* inl = reinterpret_cast<const C*>(mo.inl);
+        const C m[4] = {inl[0], inl[1], inl[2], inl[3]};
+#pragma unroll
+        for (int u = 0; u < GPT; ++u) mu_real1<C, R, I, 0>(v[u], m, 0u);
+      } else {
+#pragma unroll
+        for (int u = 0; u < GPT; ++u) mu_addsub<C, R, I, 0>(v[u], 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < GPT; ++u) {
+        C ph0 = cmul(ext, ta[g[u] & ma]);
+        ph0 = cmul(ph0, tb[g[u] >> la]);
+        mu_fan<C, R, I>(v[u], ph0, gt, 0u);
+      }
+    }
+    stage_full<C, R, GPT, I - 1, SMASK, RMASK>(v, g, mops, blob, ts);
+  }
+}
+
 // One REGTILE pass over the tile.  Each thread keeps GPT groups in registers at once, so that the decode of a
 // micro-op is paid once per GPT * 2^R amplitudes.  `ts` = this team's per-tile slot states.
 template <typename C, int R, int GPT, bool SO = false>
@@ -329,7 +364,14 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
   }
   const MicroOp* mops = reinterpret_cast<const MicroOp*>(blob + ph.offset);
   const int nmicro = (int)ph.nmicro;
-  if (ph.stage_mask) {
+  if ((ph.flags & PASS_FULL_STAGE) && R == 4) {
+    switch (ph.stage_mask | (ph.flags & 0xF0u)) {
+      case 0x0F: stage_full<C, R, GPT, R - 1, 0xFu, 0x0u>(v, g, mops, blob, ts); break;
+      case 0x1F: stage_full<C, R, GPT, R - 1, 0xFu, 0x1u>(v, g, mops, blob, ts); break;
+      case 0x07: stage_full<C, R, GPT, R - 1, 0x7u, 0x0u>(v, g, mops, blob, ts); break;
+      default: stage_full<C, R, GPT, R - 1, 0x7u, 0x1u>(v, g, mops, blob, ts); break;
+    }
+  } else if (ph.stage_mask) {
     // a pass made of fused stage ops on descending register bits (every QFT pass): straight-line code, no per-op
     // jump sequence (ncu: the compare tree nvcc makes of the handler switch costs ~5 dependent branches per op)
     int mi = 0;

@@ -91,9 +91,9 @@ struct alignas(16) MicroOp {
   // ---- second 16 bytes ---------------------------------------------------------------------------------
   uint16_t la;           // FAN: TA is indexed by the low `la` bits of the group index, TB by the rest
   uint16_t R;            // register bits of the pass this op belongs to (table layout)
-  uint32_t k;            // DIAGK: number of target bits
+  uint32_t k;            // DIAGK: number of target bits | FAN: byte offset of TB in the blob (filled with the payload offset)
   uint32_t n_ext;        // FAN: number of ext tables
-  uint32_t pad0;
+  uint32_t gt_off;       // FAN: byte offset of G in the blob
   // ---- inline data -------------------------------------------------------------------------------------
   double inl[8];         // DENSE1: the 2x2 matrix in the state's precision (4 x C); PHASE: the phase (a C)
   // ---- cold part (per-tile set-up, DIAGK) ------------------------------------------------------------------
@@ -126,7 +126,8 @@ struct PassHeader {
   uint16_t nmicro;
   uint16_t R;            // REGTILE: number of register bits of this pass
   uint32_t offset;       // byte offset of MicroOp[0] (REGTILE) or of the DevOp (BIG)
-  uint16_t off[16];      // REGTILE: tile-local offset of register index j (deposit of j into rmask), precomputed
+  uint16_t off[14];      // REGTILE: tile-local offset of register index j (deposit of j into rmask), j < 14 (host-side debugging aid)
+  uint32_t flags;        // PASS_FULL_STAGE: see below
   uint8_t pos[8];        // REGTILE: tile-local positions of the register bits, ascending
   uint32_t gtab;         // REGTILE: byte offset of uint16[SWEEP_TEAM_THREADS * groups-per-thread]: the group (index over the
                          // non-register tile bits, ascending) that thread `ctid` handles as its u-th, or 0xFFFF for none
@@ -135,6 +136,15 @@ struct PassHeader {
                          // then runs them as straight-line code, without the per-op jump sequence
 };
 static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligned");
+// PASS_FULL_STAGE: the pass is exactly R fused stages of the add/sub kind (MH_STAGE_A) on register bits R-1 .. 0, none with
+// a control outside the tile, on a full tile (every thread owns valid groups): the kernel runs them as ONE basic block --
+// no handler decode, no activity test, no validity test per stage -- so that the next stage's table loads can be
+// scheduled under the current stage's arithmetic (round 2: the QFT sweeps are issue-bound at ~13 instructions per
+// amplitude and stage, 5.2 of them FP64).  Every pass of a QFT but the one holding its last Hadamard qualifies.
+constexpr uint32_t PASS_FULL_STAGE = 1u;  // flags bits 4-7: which of the stages use the real-matrix form (MH_STAGE_R)
+// (stage mask | real mask << 4) combinations the kernel instantiates: four stages, or the three lowest (the second pass of a
+// 7-stage sweep), each with or without a real-matrix stage on bit 0
+inline bool pass_full_stage_supported(uint32_t key) { return key == 0x0F || key == 0x1F || key == 0x07 || key == 0x17; }
 
 struct SweepHeader {
   uint32_t npasses;
@@ -508,7 +518,7 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
   ph.kind = PASS_REGTILE;
   ph.rmask = rmask;
   ph.R = (uint16_t)R;
-  for (int j = 0; j < (1 << R) && j < 16; ++j) {
+  for (int j = 0; j < (1 << R) && j < 14; ++j) {
     uint32_t o = 0;
     int kbit = 0;
     for (int lb = 0; lb < T; ++lb)
@@ -813,6 +823,24 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       mask |= 1u << I;
     }
     ph.stage_mask = ok && any_stage ? mask : 0u;
+    const int Rfull = regtile_bits_for(sizeof(C) == 16 ? QB_C128 : QB_C64);
+    if (ph.stage_mask && R == Rfull && Rfull == 4 && T == tile_bits_for(sizeof(C) == 16 ? QB_C128 : QB_C64) && !env_int("QB_NO_FULL_STAGE", 0)) {
+      // which stages multiply by a real 2x2 matrix (MH_STAGE_R: the Hadamard that carries the sweep's scalars) instead of
+      // the add/sub form; every op must be a fused stage with a slot and without controls outside the tile
+      uint32_t real_mask = 0;
+      bool full = true;
+      for (auto& m : mops) {
+        if (m.handler >= MH_STAGE_A && m.handler < MH_STAGE_A + 4) {
+        } else if (m.handler >= MH_STAGE_R && m.handler < MH_STAGE_R + 4) {
+          real_mask |= 1u << (m.handler - MH_STAGE_R);
+        } else {
+          full = false;
+        }
+        if (m.ext_cmask != 0 || m.slot == MU_NO_SLOT) full = false;
+      }
+      const uint32_t key = ph.stage_mask | (real_mask << 4);
+      if (full && pass_full_stage_supported(key)) ph.flags |= PASS_FULL_STAGE | (real_mask << 4);
+    }
   }
   {
     auto it = sb.gtab_of_rmask.find(rmask);
@@ -888,6 +916,13 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
     else sb.micro[own.first][own.second].payload = (uint32_t)off;
     off += align16(sb.payloads[s].size() * sizeof(C));
   }
+  for (size_t p = 0; p < sb.passes.size(); ++p)
+    for (auto& m : sb.micro[p])
+      if (m.type == MU_FAN) {  // TA | TB | G follow each other in the fan's payload
+        const int gb = sb.T - (int)m.R;
+        m.k = m.payload + (uint32_t)((size_t(1) << m.la) * sizeof(C));
+        m.gt_off = m.k + (uint32_t)((size_t(1) << (gb - (int)m.la)) * sizeof(C));
+      }
   std::vector<uint32_t> gtab_off(sb.gtabs.size(), 0);
   for (size_t g = 0; g < sb.gtabs.size(); ++g) {
     gtab_off[g] = (uint32_t)off;
@@ -1273,7 +1308,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
               sops.size(), sd.npasses, (unsigned long long)tile_mask, L, hdr.swizzle, hdr.warp_private, sb.split_mask, hdr.blob_bytes, sb.slots.size(), sd.stage_only);
     if (env_int("QB_PLAN_DEBUG", 0) > 1)
       for (size_t p_ = 0; p_ < sb.passes.size(); ++p_) {
-        fprintf(stderr, "[qb plan]   pass %zu kind %u rmask %#x stage_mask %#x handlers:", p_, sb.passes[p_].kind, sb.passes[p_].rmask, sb.passes[p_].stage_mask);
+        fprintf(stderr, "[qb plan]   pass %zu kind %u rmask %#x stage_mask %#x flags %u handlers:", p_, sb.passes[p_].kind, sb.passes[p_].rmask, sb.passes[p_].stage_mask, sb.passes[p_].flags);
         for (auto& m_ : sb.micro[p_]) fprintf(stderr, " %d", (int)m_.handler);
         fprintf(stderr, "\n");
       }
