@@ -113,10 +113,13 @@ typedef struct {
   double bytes_moved;      /* algorithmic bytes: sum over sweeps of 2*B*2^n      */
   float elapsed_ms;        /* CUDA-event time of the whole program (flags & QB_PROGRAM_TIME) */
   int32_t nstage_sweeps;   /* of nsweeps: sweeps made of straight-line stage passes only (the lean two-team kernel) */
+  int32_t perm_fused;      /* *_permuted calls: 1 = the trailing qubit permutation rode on the last sweep (no K8 launch) */
+  int32_t reserved;
 } qb_program_stats;
 
 #define QB_PROGRAM_TIME 1      /* bracket with CUDA events, synchronise, fill elapsed_ms */
 #define QB_PROGRAM_NO_FUSE 2   /* one sweep per gate (gate-by-gate accounting)           */
+#define QB_PROGRAM_PERM_FUSED_ONLY 4 /* *_permuted calls: QB_ERR_UNSUPPORTED (nothing launched) when the permutation cannot ride on a sweep */
 int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
                      qb_program_stats* stats /* may be NULL */);
 /* Compiled programs: the same gate queue planned ONCE, its sweep programs kept resident in device memory, and launched
@@ -152,9 +155,24 @@ typedef struct {
 } qb_param_update;
 int qb_program_set_params(qb_handle h, qb_program p, const qb_param_update* updates, int nupdates);
 int qb_program_destroy(qb_handle h, qb_program program);
+/* A gate queue FOLLOWED BY A QUBIT PERMUTATION (the run of SWAP gates ending models/qft.py:55-57; the closing local
+ * permutation of a distributed run), out of place: the ops are applied to `state` and the result, with qubit q moved to
+ * qubit dest_of_qubit[q], is written to `dst` (another buffer of the same size; `state` is left holding an intermediate
+ * state).  When the permutation's tile can be a sweep's tile, the LAST sweep writes its tiles permuted through a second
+ * tensor map -- no separate K8 pass over the state (stats->perm_fused = 1, nsweeps counts only sweep launches); otherwise
+ * the ops run in place and K8 follows (perm_fused = 0, nsweeps includes the K8 launch). */
+int qb_apply_program_permuted(qb_handle h, void* state, void* dst, int nqubits, int dtype, const qb_op* ops, int nops,
+                              const int* dest_of_qubit, int flags, qb_program_stats* stats /* may be NULL */);
+int qb_program_create_permuted(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, const int* dest_of_qubit,
+                               int flags, qb_program* out, qb_program_stats* stats /* may be NULL */);
+/* runs a program made by qb_program_create_permuted (qb_program_run refuses those: they need `dst`) */
+int qb_program_run_permuted(qb_handle h, qb_program program, void* state, void* dst, int flags,
+                            qb_program_stats* stats /* may be NULL */);
 /* host-only: run the sweep planner without touching a device (used by the CPU test-suite) */
 int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program_stats* stats,
                     int32_t* sweep_of_op /* nops entries, may be NULL */);
+int qb_plan_program_permuted(int nqubits, int dtype, const qb_op* ops, int nops, const int* dest_of_qubit, int flags,
+                             qb_program_stats* stats, int32_t* sweep_of_op /* nops entries, may be NULL */);
 
 /* ---- K8: qubit permutation, out of place, one sweep (a run of SWAP gates such as the bit reversal ending
  * models/qft.py:55-57; gates/gates.py:1669 SWAP).  dst[.. qubit dest_of_qubit[q] ..] = src[.. qubit q ..];

@@ -15,7 +15,7 @@ QB_C64, QB_C128 = 0, 1
 QB_F32, QB_F64 = 0, 1
 QB_OK, QB_ERR_INVALID, QB_ERR_OOM, QB_ERR_CUDA, QB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 QB_MAX_OP_TARGETS, QB_MAX_OP_CONTROLS = 6, 32
-QB_PROGRAM_TIME, QB_PROGRAM_NO_FUSE = 1, 2
+QB_PROGRAM_TIME, QB_PROGRAM_NO_FUSE, QB_PROGRAM_PERM_FUSED_ONLY = 1, 2, 4
 QB_SCAN_EXACT, QB_SCAN_PARALLEL = 0, 1
 
 
@@ -40,6 +40,8 @@ class QbProgramStats(ctypes.Structure):
         ("bytes_moved", c_double),
         ("elapsed_ms", c_float),
         ("nstage_sweeps", c_int32),
+        ("perm_fused", c_int32),
+        ("reserved", c_int32),
     ]
 
 
@@ -84,6 +86,10 @@ PROTOTYPES = {
     "qb_program_destroy": (c_int, [c_void_p, c_void_p]),
     "qb_program_set_params": (c_int, [c_void_p, c_void_p, POINTER(QbParamUpdate), c_int]),
     "qb_plan_program": (c_int, [c_int, c_int, POINTER(QbOp), c_int, c_int, POINTER(QbProgramStats), POINTER(c_int32)]),
+    "qb_apply_program_permuted": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(QbOp), c_int, POINTER(c_int), c_int, POINTER(QbProgramStats)]),
+    "qb_program_create_permuted": (c_int, [c_void_p, c_int, c_int, POINTER(QbOp), c_int, POINTER(c_int), c_int, POINTER(c_void_p), POINTER(QbProgramStats)]),
+    "qb_program_run_permuted": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(QbProgramStats)]),
+    "qb_plan_program_permuted": (c_int, [c_int, c_int, POINTER(QbOp), c_int, POINTER(c_int), c_int, POINTER(QbProgramStats), POINTER(c_int32)]),
     "qb_permute_qubits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
     "qb_probabilities": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_int, c_void_p]),
     "qb_cdf": (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_int]),

@@ -386,6 +386,7 @@ class B200Backend(NumpyBackend):
     def _execute_circuit(self, circuit, initial_state=None, nshots=1000):
         nqubits = circuit.nqubits
         density_matrix = circuit.density_matrix
+        self.engine_gpu.reclaim_before((16 if self.dtype != "complex64" else 8) << (2 * nqubits if density_matrix else nqubits))
         if initial_state is None:
             state = self.zero_state(nqubits, density_matrix=density_matrix)
         else:

@@ -476,13 +476,101 @@ int qb_plan_program(int nqubits, int dtype, const qb_op* ops, int nops, int flag
   return QB_OK;
 }
 
+// dest_of_qubit (Qibo qubit ids) -> PermSpec (bit positions); false when it is not a permutation
+static bool perm_from_qubits(int nqubits, const int* dest_of_qubit, PermSpec& perm) {
+  uint64_t seen = 0;
+  for (int q = 0; q < nqubits; ++q) {
+    const int d = dest_of_qubit[q];
+    if (d < 0 || d >= nqubits || ((seen >> d) & 1)) return false;
+    seen |= uint64_t(1) << d;
+    perm.pi[nqubits - 1 - q] = nqubits - 1 - d;
+  }
+  return true;
+}
+
+// K8 launch (the caller holds the context's mutex)
+static int permute_locked(qb_context* h, const void* src, void* dst, int nqubits, int dtype, const int* pi) {
+  PermParams p;
+  memset(&p, 0, sizeof(p));
+  // 2^6 amplitudes: 1 KiB (complex128) / 512 B (complex64) contiguous on both sides (QB_PERM_LOW_BITS: tuning knob)
+  int lowbits = env_int("QB_PERM_LOW_BITS", 6);
+  if (lowbits < 3) lowbits = 3;
+  if (lowbits > 6) lowbits = 6;
+  perm_setup(nqubits, lowbits, lowbits, pi, p);
+  if (launch_permute(h->stream, h->sm_count, src, dst, dtype, p) != QB_OK) return cuda_fail(cudaGetLastError(), "k8_permute");
+  return QB_OK;
+}
+
+// a permutation that rides on a sweep needs the tensor-map encoder at launch time
+static const PermSpec* fusable(const PermSpec* perm) { return perm && tma_encoder() != nullptr ? perm : nullptr; }
+
+// the sweeps of a plan, then -- when a permutation was asked for and does not ride on the last sweep -- K8 into `dst`
+static int launch_plan(qb_context* h, void* state, void* dst, int nqubits, int dtype, const Plan& plan, const char* prog_dev,
+                       const PermSpec* perm) {
+  for (size_t s = 0; s < plan.sweeps.size(); ++s) {
+    const int rc = launch_sweep(h->stream, h->sm_count, state, nqubits, dtype, plan.sweeps[s], prog_dev, dst);
+    if (rc != QB_OK) {
+      const std::string what = cudaGetErrorString(cudaGetLastError());
+      return fail(rc, "sweep launch failed: " + what + " [" + sweep_resources(dtype) + "]");
+    }
+  }
+  if (perm && !plan.perm_fused) return permute_locked(h, state, dst, nqubits, dtype, perm->pi);
+  return QB_OK;
+}
+
+static void count_k8(const Plan& plan, const PermSpec* perm, int nqubits, int dtype, qb_program_stats* st) {
+  if (!perm || plan.perm_fused) return;
+  st->nsweeps += 1;
+  st->ndense_passes += 1;
+  st->bytes_moved += 2.0 * (dtype == QB_C128 ? 16.0 : 8.0) * (double)(uint64_t(1) << nqubits);
+}
+
+int qb_plan_program_permuted(int nqubits, int dtype, const qb_op* ops, int nops, const int* dest_of_qubit, int flags,
+                             qb_program_stats* stats, int32_t* sweep_of_op) {
+  if (nqubits < 1 || nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128) || nops < 0 || (nops && !ops) || !dest_of_qubit)
+    return fail(QB_ERR_INVALID, "bad program arguments");
+  PermSpec perm;
+  if (!perm_from_qubits(nqubits, dest_of_qubit, perm)) return fail(QB_ERR_INVALID, "dest_of_qubit is not a permutation");
+  std::vector<CanonOp> canon;
+  int rc = canonicalize_program(nqubits, ops, nops, canon);
+  if (rc != QB_OK) return rc;
+  Plan plan;
+  std::string err;
+  if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, err, nullptr, &perm)) return fail(QB_ERR_UNSUPPORTED, err);
+  if (stats) {
+    fill_stats(plan, nqubits, dtype, nops, stats);
+    count_k8(plan, &perm, nqubits, dtype, stats);
+  }
+  if (sweep_of_op)
+    for (int i = 0; i < nops; ++i) sweep_of_op[i] = plan.sweep_of_op[i];
+  return QB_OK;
+}
+
+static int apply_program_impl(qb_handle h, void* state, void* dst, int nqubits, int dtype, const qb_op* ops, int nops,
+                              const PermSpec* perm, int flags, qb_program_stats* stats);
+
 int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
                      qb_program_stats* stats) {
   if (!h || !valid_state_args(state, nqubits, dtype) || nops < 0 || (nops && !ops))
     return fail(QB_ERR_INVALID, "bad program arguments");
+  return apply_program_impl(h, state, nullptr, nqubits, dtype, ops, nops, nullptr, flags, stats);
+}
+
+int qb_apply_program_permuted(qb_handle h, void* state, void* dst, int nqubits, int dtype, const qb_op* ops, int nops,
+                              const int* dest_of_qubit, int flags, qb_program_stats* stats) {
+  if (!h || !valid_state_args(state, nqubits, dtype) || !dst || dst == state || nops < 0 || (nops && !ops) || !dest_of_qubit)
+    return fail(QB_ERR_INVALID, "bad program arguments");
+  PermSpec perm;
+  if (!perm_from_qubits(nqubits, dest_of_qubit, perm)) return fail(QB_ERR_INVALID, "dest_of_qubit is not a permutation");
+  return apply_program_impl(h, state, dst, nqubits, dtype, ops, nops, &perm, flags, stats);
+}
+
+static int apply_program_impl(qb_handle h, void* state, void* dst, int nqubits, int dtype, const qb_op* ops, int nops,
+                              const PermSpec* perm, int flags, qb_program_stats* stats) {
   std::vector<CanonOp> canon;
   int rc = canonicalize_program(nqubits, ops, nops, canon);
   if (rc != QB_OK) return rc;
+  if (nqubits < 4 && perm && (flags & QB_PROGRAM_PERM_FUSED_ONLY)) return fail(QB_ERR_UNSUPPORTED, "no sweeps below 4 qubits");
   if (nqubits < 4) {
     // up to 8 amplitudes: nothing to tile (a register group of the sweep kernel is 2^4 amplitudes); the K1 kernels
     // apply the queue gate by gate
@@ -498,12 +586,20 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
       rc = dtype == QB_C128 ? apply_canon_k1<double2>(h, state, nqubits, c) : apply_canon_k1<float2>(h, state, nqubits, c);
       if (rc != QB_OK) return rc;
     }
+    if (perm) {
+      if (stats) stats->nsweeps += 1;
+      return permute_locked(h, state, dst, nqubits, dtype, perm->pi);
+    }
     return QB_OK;
   }
   Plan plan;
   std::string err;
-  if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, err)) return fail(QB_ERR_UNSUPPORTED, err);
-  if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
+  if (!plan_program(nqubits, dtype, canon, (flags & QB_PROGRAM_NO_FUSE) != 0, plan, err, nullptr, fusable(perm))) return fail(QB_ERR_UNSUPPORTED, err);
+  if (perm && !plan.perm_fused && (flags & QB_PROGRAM_PERM_FUSED_ONLY)) return fail(QB_ERR_UNSUPPORTED, "the permutation cannot ride on a sweep of this program");
+  if (stats) {
+    fill_stats(plan, nqubits, dtype, nops, stats);
+    count_k8(plan, perm, nqubits, dtype, stats);
+  }
 
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
@@ -527,13 +623,8 @@ int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_
     QB_CUDA(cudaMemcpyAsync(h->prog_dev, h->prog_host, need, cudaMemcpyHostToDevice, h->stream));
   }
   if (flags & QB_PROGRAM_TIME) QB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  for (size_t s = 0; s < plan.sweeps.size(); ++s) {
-    rc = launch_sweep(h->stream, h->sm_count, state, nqubits, dtype, plan.sweeps[s], (const char*)h->prog_dev);
-    if (rc != QB_OK) {
-      const std::string what = cudaGetErrorString(cudaGetLastError());
-      return fail(rc, "sweep launch failed: " + what + " [" + sweep_resources(dtype) + "]");
-    }
-  }
+  rc = launch_plan(h, state, dst, nqubits, dtype, plan, (const char*)h->prog_dev, perm);
+  if (rc != QB_OK) return rc;
   QB_CUDA(cudaEventRecord(h->prog_done, h->stream));
   if (flags & QB_PROGRAM_TIME) {
     QB_CUDA(cudaEventRecord(h->ev1, h->stream));
@@ -561,14 +652,38 @@ struct qb_program_s {
   void* staging = nullptr;      // pinned host copy of the blob for stream-ordered re-uploads
   size_t staging_bytes = 0;
   qb_program_stats stats;
+  bool has_perm = false;        // qb_program_create_permuted: the ops are followed by `perm`, the result goes to another buffer
+  PermSpec perm;
 };
+
+static int program_create_impl(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, const PermSpec* perm, int flags,
+                               qb_program* out, qb_program_stats* stats);
 
 int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, int flags, qb_program* out,
                       qb_program_stats* stats) {
   if (!h || !out || nqubits < 1 || nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128) || nops < 0 || (nops && !ops))
     return fail(QB_ERR_INVALID, "bad program arguments");
+  return program_create_impl(h, nqubits, dtype, ops, nops, nullptr, flags, out, stats);
+}
+
+int qb_program_create_permuted(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, const int* dest_of_qubit, int flags,
+                               qb_program* out, qb_program_stats* stats) {
+  if (!h || !out || nqubits < 1 || nqubits > QB_MAX_QUBITS || (dtype != QB_C64 && dtype != QB_C128) || nops < 0 || (nops && !ops) ||
+      !dest_of_qubit)
+    return fail(QB_ERR_INVALID, "bad program arguments");
+  PermSpec perm;
+  if (!perm_from_qubits(nqubits, dest_of_qubit, perm)) return fail(QB_ERR_INVALID, "dest_of_qubit is not a permutation");
+  return program_create_impl(h, nqubits, dtype, ops, nops, &perm, flags, out, stats);
+}
+
+static int program_create_impl(qb_handle h, int nqubits, int dtype, const qb_op* ops, int nops, const PermSpec* perm, int flags,
+                               qb_program* out, qb_program_stats* stats) {
   *out = nullptr;
   std::unique_ptr<qb_program_s> p(new qb_program_s());
+  if (perm) {
+    p->has_perm = true;
+    p->perm = *perm;
+  }
   p->nqubits = nqubits;
   p->dtype = dtype;
   p->nops = nops;
@@ -589,13 +704,18 @@ int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int
   }
   memset(&p->stats, 0, sizeof(p->stats));
   p->stats.nops = nops;
+  if (nqubits < 4 && perm && (flags & QB_PROGRAM_PERM_FUSED_ONLY)) return fail(QB_ERR_UNSUPPORTED, "no sweeps below 4 qubits");
   if (nqubits < 4) {
-    p->stats.nsweeps = nops;
+    p->stats.nsweeps = nops + (perm ? 1 : 0);
     p->stats.bytes_moved = (double)nops * 2.0 * (dtype == QB_C128 ? 16.0 : 8.0) * (double)(uint64_t(1) << nqubits);
   } else {
     std::string err;
-    if (!plan_program(nqubits, dtype, p->canon, (flags & QB_PROGRAM_NO_FUSE) != 0, p->plan, err)) return fail(QB_ERR_UNSUPPORTED, err);
+    if (!plan_program(nqubits, dtype, p->canon, (flags & QB_PROGRAM_NO_FUSE) != 0, p->plan, err, nullptr, fusable(perm)))
+      return fail(QB_ERR_UNSUPPORTED, err);
+    if (perm && !p->plan.perm_fused && (flags & QB_PROGRAM_PERM_FUSED_ONLY))
+      return fail(QB_ERR_UNSUPPORTED, "the permutation cannot ride on a sweep of this program");
     fill_stats(p->plan, nqubits, dtype, nops, &p->stats);
+    count_k8(p->plan, perm, nqubits, dtype, &p->stats);
     if (!p->plan.blob.empty()) {
       std::lock_guard<std::mutex> lk(h->mu);
       DeviceGuard guard(h->device);
@@ -615,8 +735,21 @@ int qb_program_create(qb_handle h, int nqubits, int dtype, const qb_op* ops, int
   return QB_OK;
 }
 
+static int program_run_impl(qb_handle h, qb_program p, void* state, void* dst, int flags, qb_program_stats* stats);
+
 int qb_program_run(qb_handle h, qb_program p, void* state, int flags, qb_program_stats* stats) {
   if (!h || !p || !valid_state_args(state, p->nqubits, p->dtype)) return fail(QB_ERR_INVALID, "bad program arguments");
+  if (p->has_perm) return fail(QB_ERR_INVALID, "the program ends with a permutation: run it with qb_program_run_permuted");
+  return program_run_impl(h, p, state, nullptr, flags, stats);
+}
+
+int qb_program_run_permuted(qb_handle h, qb_program p, void* state, void* dst, int flags, qb_program_stats* stats) {
+  if (!h || !p || !valid_state_args(state, p->nqubits, p->dtype) || !dst || dst == state) return fail(QB_ERR_INVALID, "bad program arguments");
+  if (!p->has_perm) return fail(QB_ERR_INVALID, "the program was not created with qb_program_create_permuted");
+  return program_run_impl(h, p, state, dst, flags, stats);
+}
+
+static int program_run_impl(qb_handle h, qb_program p, void* state, void* dst, int flags, qb_program_stats* stats) {
   if (p->device != h->device) return fail(QB_ERR_INVALID, "the program was compiled for another device");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
@@ -627,14 +760,13 @@ int qb_program_run(qb_handle h, qb_program p, void* state, int flags, qb_program
       int rc = p->dtype == QB_C128 ? apply_canon_k1<double2>(h, state, p->nqubits, c) : apply_canon_k1<float2>(h, state, p->nqubits, c);
       if (rc != QB_OK) return rc;
     }
-  } else {
-    for (size_t s = 0; s < p->plan.sweeps.size(); ++s) {
-      int rc = launch_sweep(h->stream, h->sm_count, state, p->nqubits, p->dtype, p->plan.sweeps[s], (const char*)p->dev);
-      if (rc != QB_OK) {
-        const std::string what = cudaGetErrorString(cudaGetLastError());
-        return fail(rc, "sweep launch failed: " + what + " [" + sweep_resources(p->dtype) + "]");
-      }
+    if (p->has_perm) {
+      int rc = permute_locked(h, state, dst, p->nqubits, p->dtype, p->perm.pi);
+      if (rc != QB_OK) return rc;
     }
+  } else {
+    int rc = launch_plan(h, state, dst, p->nqubits, p->dtype, p->plan, (const char*)p->dev, p->has_perm ? &p->perm : nullptr);
+    if (rc != QB_OK) return rc;
   }
   if (flags & QB_PROGRAM_TIME) {
     QB_CUDA(cudaEventRecord(h->ev1, h->stream));
@@ -676,9 +808,10 @@ int qb_program_set_params(qb_handle h, qb_program p, const qb_param_update* upda
   if (p->nqubits < 4) return QB_OK;  // applied gate by gate from `canon`
   const bool no_fuse = (p->flags & QB_PROGRAM_NO_FUSE) != 0;
   Plan fresh;
-  if (!plan_program(p->nqubits, p->dtype, p->canon, no_fuse, fresh, err, &p->plan)) {
+  const PermSpec* perm = p->has_perm ? fusable(&p->perm) : nullptr;
+  if (!plan_program(p->nqubits, p->dtype, p->canon, no_fuse, fresh, err, &p->plan, perm)) {
     // the structure changed (a rotation became an identity, a real matrix complex...): schedule from scratch
-    if (!plan_program(p->nqubits, p->dtype, p->canon, no_fuse, fresh, err)) return fail(QB_ERR_UNSUPPORTED, err);
+    if (!plan_program(p->nqubits, p->dtype, p->canon, no_fuse, fresh, err, nullptr, perm)) return fail(QB_ERR_UNSUPPORTED, err);
   }
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
@@ -709,6 +842,7 @@ int qb_program_set_params(qb_handle h, qb_program p, const qb_param_update* upda
   std::vector<char>().swap(fresh.blob);
   p->plan = std::move(fresh);
   fill_stats(p->plan, p->nqubits, p->dtype, p->nops, &p->stats);
+  count_k8(p->plan, p->has_perm ? &p->perm : nullptr, p->nqubits, p->dtype, &p->stats);
   return QB_OK;
 }
 
@@ -743,17 +877,9 @@ int qb_permute_qubits(qb_handle h, const void* src, void* dst, int nqubits, int 
     seen |= uint64_t(1) << d;
     pi[nqubits - 1 - q] = nqubits - 1 - d;
   }
-  PermParams p;
-  memset(&p, 0, sizeof(p));
-  // 2^6 amplitudes: 1 KiB (complex128) / 512 B (complex64) contiguous on both sides (QB_PERM_LOW_BITS: tuning knob)
-  int lowbits = env_int("QB_PERM_LOW_BITS", 6);
-  if (lowbits < 3) lowbits = 3;
-  if (lowbits > 6) lowbits = 6;
-  perm_setup(nqubits, lowbits, lowbits, pi, p);
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
-  if (launch_permute(h->stream, h->sm_count, src, dst, dtype, p) != QB_OK) return cuda_fail(cudaGetLastError(), "k8_permute");
-  return QB_OK;
+  return permute_locked(h, src, dst, nqubits, dtype, pi);
 }
 
 // ---------------------------------------------------------------------------------------------------

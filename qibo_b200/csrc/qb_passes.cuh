@@ -331,8 +331,14 @@ QB_HD void stage_full(C (&v)[GPT][1 << R], const uint32_t* g, const MicroOp* mop
 
 // One REGTILE pass over the tile.  Each thread keeps GPT groups in registers at once, so that the decode of a
 // micro-op is paid once per GPT * 2^R amplitudes.  `ts` = this team's per-tile slot states.
-template <typename C, int R, int GPT, bool SO = false>
-QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t swz_on, uint32_t ctid, uint32_t nct) {
+// A PASS_PERMUTED_STORE pass (the last pass of a permuting sweep) writes its groups to `out` (the kernel: the same buffer,
+// after `barrier()` -- every thread of the team has loaded its groups by then; the CPU emulation: a second buffer) at the
+// DESTINATION-layout addresses: dtab gives the destination-local index of each group base, dpos the destination
+// positions of the register bits.
+struct NoBarrier { QB_HD void operator()() const {} };
+template <typename C, int R, int GPT, bool SO = false, typename Barrier = NoBarrier>
+QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHeader& ph, int T, uint32_t swz_on, uint32_t ctid, uint32_t nct,
+                    C* out = nullptr, Barrier barrier = Barrier()) {
   constexpr int D = 1 << R;
   const int gbits = T - R;
   uint32_t stride[R > 0 ? R : 1];  // physical (swizzled) offset of register bit i (swz is linear over XOR)
@@ -448,6 +454,16 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
 #undef QB_CASE_BIT
 #undef QB_EACH
   }
+  }
+  if (ph.flags & PASS_PERMUTED_STORE) {
+    const uint32_t dswz_on = (ph.flags & PASS_PERMUTED_DSWZ) ? 7u : 0u;
+    const uint16_t* dtab = reinterpret_cast<const uint16_t*>(blob + ph.dtab);
+#pragma unroll
+    for (int i = 0; i < R; ++i) stride[i] = swz<C>(1u << ph.dpos[i], dswz_on);
+#pragma unroll
+    for (int u = 0; u < GPT; ++u) p0[u] = swz<C>(dtab[ctid + (uint32_t)u * nct], dswz_on);
+    barrier();
+    if (out) tile = out;
   }
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -134,6 +135,10 @@ struct PassHeader {
   uint32_t stage_mask;   // REGTILE: non-zero when the pass is nothing but fused stage ops (MH_STAGE_*) on strictly descending
                          // register bits -- the shape of every QFT pass; bit I set = a stage on register bit I.  The kernel
                          // then runs them as straight-line code, without the per-op jump sequence
+  // PASS_PERMUTED_STORE (the last pass of a permuting sweep): the groups go back to shared memory in the destination layout
+  uint8_t dpos[8];       // tile-local DESTINATION positions of the register bits (same order as pos[])
+  uint32_t dtab;         // byte offset of uint16[thread slots]: destination-local index of the slot's group base
+  uint32_t pad1;
 };
 static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligned");
 // PASS_FULL_STAGE: the pass is exactly R fused stages of the add/sub kind (MH_STAGE_A) on register bits R-1 .. 0, none with
@@ -141,6 +146,8 @@ static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligne
 // no handler decode, no activity test, no validity test per stage -- so that the next stage's table loads can be
 // scheduled under the current stage's arithmetic (round 2: the QFT sweeps are issue-bound at ~13 instructions per
 // amplitude and stage, 5.2 of them FP64).  Every pass of a QFT but the one holding its last Hadamard qualifies.
+constexpr uint32_t PASS_PERMUTED_STORE = 2u;  // the pass writes its groups in the destination layout of a permuting sweep
+constexpr uint32_t PASS_PERMUTED_DSWZ = 4u;   // ... which is swizzled
 constexpr uint32_t PASS_FULL_STAGE = 1u;  // flags bits 4-7: which of the stages use the real-matrix form (MH_STAGE_R)
 // (stage mask | real mask << 4) combinations the kernel instantiates: four stages, or the three lowest (the second pass of a
 // 7-stage sweep), each with or without a real-matrix stage on bit 0
@@ -162,6 +169,12 @@ struct SweepHeader {
   uint32_t warp_private;   // 1: every warp owns the same 1/8 of the tile in every pass (no REGTILE pass mixes across three fixed
                            // tile bits): passes are separated by __syncwarp instead of a team barrier, so warps drift apart and
                            // one warp's shared-memory bursts overlap another's FP math
+  // ---- permuting sweep (a trailing qubit permutation -- the QFT's bit reversal -- rides on the last sweep) -----------
+  uint32_t permuted;       // 1: the last pass leaves the tile in the DESTINATION layout and the storer writes it through
+                           // the destination tensor map at the permuted tile base (out of place)
+  uint32_t dswizzle;       // the destination layout is swizzled
+  uint64_t dtile_mask;     // destination state bits spanned by the (permuted) tile
+  uint8_t dst_bit[64];     // destination bit of every source state bit (bits outside the tile: the storer's tile base)
 };
 static_assert(sizeof(SweepHeader) % 16 == 0, "SweepHeader must stay 16-byte aligned");
 
@@ -178,6 +191,9 @@ struct PlanOp {
 };
 
 struct SweepDesc {
+  int permuted = 0;          // the sweep writes its tiles, permuted, into ANOTHER buffer (launch_sweep needs `dst`)
+  int dswizzle = 0;
+  uint64_t dmask = 0;        // destination tile mask
   int swizzle = 0;
   int stage_only = 0;  // every pass is a straight-line stage pass: the lean two-team kernel instantiation may run it
   int T = 0, L = 0;
@@ -185,6 +201,19 @@ struct SweepDesc {
   size_t blob_offset = 0, blob_bytes = 0;
   int npasses = 0, ndiag = 0;
   uint64_t ntiles = 0;
+};
+
+// A qubit permutation to apply after the ops: pi[b] = destination bit of source state bit b.
+struct PermSpec {
+  int pi[64];
+};
+// its tile geometry when the permutation rides on a sweep: the `ls` lowest source bits (contiguous reads), the source bits
+// that land on the `ld` lowest destination bits (contiguous writes) and, when those leave room in the tile, the bits the
+// last gates of the program mix
+struct PermGeom {
+  uint64_t S = 0, D = 0;    // source / destination tile masks
+  int sigma[16];            // tile-local source bit -> tile-local destination bit
+  int dswizzle = 0;
 };
 
 struct Plan {
@@ -197,6 +226,8 @@ struct Plan {
   // the mixing / diagonal bit sets the schedule's legality rests on
   std::vector<std::vector<uint32_t>> sweep_ops;
   std::vector<uint64_t> xsets, dsets;
+  int perm_fused = 0;  // the trailing permutation the caller asked for rides on the last sweep (its tile: pgeom)
+  PermGeom pgeom;
 };
 
 inline int env_int(const char* name, int dflt) {
@@ -370,6 +401,7 @@ template <typename C> struct SweepBuilder {
   std::vector<std::vector<uint16_t>> gtabs;  // distinct group tables
   std::map<uint32_t, int> gtab_of_rmask;
   std::vector<int> gtab_of_pass;             // per pass: index into gtabs, -1 for BIG
+  std::vector<int> dtab_of_pass;             // per pass: index into gtabs of the destination-index table (permuted store), or -1
   uint32_t split_mask = 0;                   // warp-private sweeps: the three tile bits that select the warp
 };
 
@@ -499,9 +531,146 @@ inline uint32_t choose_split(int T, int R, int csize, bool swizzle, const std::v
   return best_mask;
 }
 
+// ---- permuting sweep: geometry and the thread -> group tables of its last pass ---------------------------------------
+// 16-byte chunk (bank group) of a tile-local index inside its 128-byte row: what must differ between the eight lanes of a
+// quarter-warp for a conflict-free LDS.128 / STS.128 (complex64: LDS.64, sixteen lanes, two amplitudes per chunk)
+inline uint32_t chunk_of(uint32_t x, int csize, bool swizzle) {
+  const uint32_t p = swz_host(x, csize, swizzle);
+  return csize == 16 ? (p & 7u) : ((p >> 1) & 7u);
+}
+inline int rank3(uint32_t a, uint32_t b, uint32_t c) {  // rank over GF(2) of three 3-bit vectors
+  uint32_t v[3] = {a & 7u, b & 7u, c & 7u};
+  int r = 0;
+  for (int bit = 2; bit >= 0; --bit) {
+    int piv = -1;
+    for (int i = r; i < 3; ++i)
+      if ((v[i] >> bit) & 1u) { piv = i; break; }
+    if (piv < 0) continue;
+    std::swap(v[r], v[piv]);
+    for (int i = 0; i < 3; ++i)
+      if (i != r && ((v[i] >> bit) & 1u)) v[i] ^= v[r];
+    ++r;
+  }
+  return r;
+}
+
+// Thread slot -> group of the last pass of a permuting sweep.  Lane bits 0..2 (the eight lanes of a quarter-warp) must
+// reach eight different 16-byte chunks BOTH when the pass loads its groups (source layout) and when it stores them
+// (destination layout): lane bit k flips a set V_k of one or two free tile bits, chosen so that the chunk images of
+// V_0, V_1, V_2 are linearly independent on both sides (a bit reversal maps the low source bits to high destination
+// bits: the lanes then walk a diagonal).  Returns the number of conflict ways left (1 = none).
+inline int make_permuted_tables_uncached(int T, int R, int csize, uint32_t rmask, const int* sigma, bool sswz, bool dswz, uint32_t nthreads,
+                                         std::vector<uint16_t>& gtab, std::vector<uint16_t>& dtab);
+// (the search below walks ~40 k lane assignments: a program planned again -- every step of a loop that sends host matrices
+// -- finds its tables here)
+inline int make_permuted_tables(int T, int R, int csize, uint32_t rmask, const int* sigma, bool sswz, bool dswz, uint32_t nthreads,
+                                std::vector<uint16_t>& gtab, std::vector<uint16_t>& dtab) {
+  struct Entry { std::vector<uint16_t> g, d; int ways; };
+  static std::mutex mu;
+  static std::map<std::vector<int>, Entry> cache;
+  std::vector<int> key = {T, R, csize, (int)rmask, (int)sswz, (int)dswz, (int)nthreads};
+  for (int b = 0; b < T; ++b) key.push_back(sigma[b]);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      gtab = it->second.g;
+      dtab = it->second.d;
+      return it->second.ways;
+    }
+  }
+  const int ways = make_permuted_tables_uncached(T, R, csize, rmask, sigma, sswz, dswz, nthreads, gtab, dtab);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 256) cache.clear();
+  cache[key] = Entry{gtab, dtab, ways};
+  return ways;
+}
+inline int make_permuted_tables_uncached(int T, int R, int csize, uint32_t rmask, const int* sigma, bool sswz, bool dswz, uint32_t nthreads,
+                                         std::vector<uint16_t>& gtab, std::vector<uint16_t>& dtab) {
+  std::vector<int> F;  // free (non-register) tile-local source positions, ascending
+  for (int b = 0; b < T; ++b)
+    if (!((rmask >> b) & 1u)) F.push_back(b);
+  const int nf = (int)F.size();
+  std::vector<uint32_t> cs(T), cd(T);
+  for (int b = 0; b < T; ++b) {
+    cs[b] = chunk_of(1u << b, csize, sswz);
+    cd[b] = chunk_of(1u << sigma[b], csize, dswz);
+  }
+  // candidate sets: single free positions and pairs
+  struct Cand { int a, b; uint32_t A, B; };
+  std::vector<Cand> cands;
+  for (int i = 0; i < nf; ++i) cands.push_back({F[i], -1, cs[F[i]], cd[F[i]]});
+  for (int i = 0; i < nf; ++i)
+    for (int j = 0; j < nf; ++j)
+      if (i != j) cands.push_back({F[i], F[j], cs[F[i]] ^ cs[F[j]], cd[F[i]] ^ cd[F[j]]});
+  int best[3] = {-1, -1, -1}, best_rank = -1;
+  long best_cost = 0;
+  for (size_t x = 0; x < cands.size(); ++x)
+    for (size_t y = x + 1; y < cands.size(); ++y) {
+      const Cand &cx = cands[x], &cy = cands[y];
+      if (cx.a == cy.a || cx.a == cy.b || (cx.b >= 0 && (cx.b == cy.a || cx.b == cy.b))) continue;
+      for (size_t z = y + 1; z < cands.size(); ++z) {
+        const Cand& cz = cands[z];
+        const int used[4] = {cx.a, cx.b, cy.a, cy.b};
+        bool clash = false;
+        for (int u : used)
+          if (u >= 0 && (u == cz.a || u == cz.b)) clash = true;
+        if (clash) continue;
+        const int rk = rank3(cx.A, cy.A, cz.A) + rank3(cx.B, cy.B, cz.B);
+        const long cost = (cx.b >= 0) + (cy.b >= 0) + (cz.b >= 0);  // prefer plain lanes when they are enough
+        if (rk > best_rank || (rk == best_rank && cost < best_cost)) {
+          best_rank = rk;
+          best_cost = cost;
+          best[0] = (int)x;
+          best[1] = (int)y;
+          best[2] = (int)z;
+        }
+        if (best_rank == 6 && best_cost == 0) break;
+      }
+    }
+  if (best[0] < 0) return 8;
+  // slot bit -> set of free positions it flips
+  const int gbits = nf;
+  std::vector<uint32_t> flips(gbits, 0);
+  uint32_t taken = 0;
+  std::vector<int> second;  // second members: each gets an independent slot bit of its own
+  for (int k = 0; k < 3; ++k) {
+    const Cand& c = cands[best[k]];
+    flips[k] = 1u << c.a;
+    taken |= 1u << c.a;
+    if (c.b >= 0) {
+      flips[k] |= 1u << c.b;
+      taken |= 1u << c.b;
+      second.push_back(c.b);
+    }
+  }
+  int sb = 3;
+  for (int b : F)
+    if (!((taken >> b) & 1u)) flips[sb++] = 1u << b;
+  for (int b : second) flips[sb++] = 1u << b;
+  const uint32_t nslots = 1u << gbits;
+  const uint32_t full_groups = 1u << (SWEEP_TILE_BYTES_LOG2 - (csize == 16 ? 4 : 3) - regtile_bits_for(csize == 16 ? QB_C128 : QB_C64));
+  const uint32_t gpt = std::max<uint32_t>((nslots + nthreads - 1) / nthreads, (full_groups + nthreads - 1) / nthreads);
+  gtab.assign((size_t)gpt * nthreads, 0xFFFF);
+  dtab.assign((size_t)gpt * nthreads, 0);
+  const uint32_t all = (1u << T) - 1;
+  for (uint32_t slot = 0; slot < nslots; ++slot) {
+    uint32_t t = 0;
+    for (int k = 0; k < gbits; ++k)
+      if ((slot >> k) & 1u) t ^= flips[k];
+    uint32_t y = 0;
+    for (int b = 0; b < T; ++b)
+      if ((t >> b) & 1u) y |= 1u << sigma[b];
+    gtab[slot] = (uint16_t)extract_u32(t, all & ~rmask);
+    dtab[slot] = (uint16_t)y;
+  }
+  return best_rank == 6 ? 1 : 2;
+}
+
 // Emits the micro-ops of one REGTILE pass given its final register-bit mask.
 template <typename C>
-inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanOp*>& ops, uint32_t rmask, std::string& err) {
+inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanOp*>& ops, uint32_t rmask, std::string& err,
+                              const PermGeom* pg = nullptr, bool sswz = false) {
   const int T = sb.T, R = __builtin_popcount(rmask);
   std::vector<int> rbit_of_local(32, -1), gbit_of_local(32, -1);
   {
@@ -842,7 +1011,19 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
       if (full && pass_full_stage_supported(key)) ph.flags |= PASS_FULL_STAGE | (real_mask << 4);
     }
   }
-  {
+  if (pg) {
+    // the last pass of a permuting sweep: its own thread -> group table (conflict-free on both layouts) and the
+    // destination index of every slot's group
+    std::vector<uint16_t> gt, dt;
+    make_permuted_tables(T, R, (int)sizeof(C), rmask, pg->sigma, sswz, pg->dswizzle != 0, SWEEP_TEAM_THREADS, gt, dt);
+    ph.flags |= PASS_PERMUTED_STORE | (pg->dswizzle ? PASS_PERMUTED_DSWZ : 0u);
+    for (int i = 0; i < R; ++i) ph.dpos[i] = (uint8_t)pg->sigma[ph.pos[i]];
+    sb.gtab_of_pass.push_back((int)sb.gtabs.size());
+    sb.gtabs.push_back(std::move(gt));
+    sb.dtab_of_pass.resize(sb.passes.size() + 1, -1);
+    sb.dtab_of_pass[sb.passes.size()] = (int)sb.gtabs.size();
+    sb.gtabs.push_back(std::move(dt));
+  } else {
     auto it = sb.gtab_of_rmask.find(rmask);
     if (it == sb.gtab_of_rmask.end()) {
       it = sb.gtab_of_rmask.emplace(rmask, (int)sb.gtabs.size()).first;
@@ -928,8 +1109,10 @@ template <typename C> inline void finish_blob(SweepBuilder<C>& sb, SweepHeader& 
     gtab_off[g] = (uint32_t)off;
     off += align16(sb.gtabs[g].size() * sizeof(uint16_t));
   }
-  for (size_t p = 0; p < sb.passes.size(); ++p)
+  for (size_t p = 0; p < sb.passes.size(); ++p) {
     if (sb.gtab_of_pass[p] >= 0) sb.passes[p].gtab = gtab_off[sb.gtab_of_pass[p]];
+    if (p < sb.dtab_of_pass.size() && sb.dtab_of_pass[p] >= 0) sb.passes[p].dtab = gtab_off[sb.dtab_of_pass[p]];
+  }
   hdr.npasses = (uint32_t)sb.passes.size();
   hdr.nslots = (uint32_t)sb.slots.size();
   hdr.blob_bytes = (uint32_t)off;  // the part the kernel copies to shared memory
@@ -1003,9 +1186,44 @@ inline bool tile_swizzle_ok(int nqubits, int dtype, uint64_t tile_mask) {
   return tile_segments(nqubits, dtype, tile_mask, true).size() <= 5;
 }
 
+// Tile of a permuting sweep for permutation `perm` on n bits: the `ls` lowest source bits (contiguous reads), the source
+// bits that land on the `ld` lowest destination bits (contiguous writes), then the bits of `extra` in order (what the last
+// gates of the program mix) while there is room, then more low bits of either side.  False when a side cannot get a
+// swizzled tensor map.
+inline bool perm_geometry(int n, int dtype, int T, const PermSpec& perm, int ls, int ld, const std::vector<int>& extra, PermGeom& g) {
+  if (n <= T || ls + ld > T) return false;
+  int inv[64];
+  uint64_t seen = 0;
+  for (int b = 0; b < n; ++b) {
+    if (perm.pi[b] < 0 || perm.pi[b] >= n || ((seen >> perm.pi[b]) & 1)) return false;
+    seen |= uint64_t(1) << perm.pi[b];
+    inv[perm.pi[b]] = b;
+  }
+  uint64_t S = (uint64_t(1) << ls) - 1;
+  for (int d = 0; d < ld; ++d) S |= uint64_t(1) << inv[d];
+  for (int b : extra)
+    if ((int)__builtin_popcountll(S) < T) S |= uint64_t(1) << b;
+  for (int k = 0; (int)__builtin_popcountll(S) < T && k < n; ++k) {  // fill: next source bit, next destination bit, ...
+    S |= uint64_t(1) << k;
+    if ((int)__builtin_popcountll(S) < T) S |= uint64_t(1) << inv[k];
+  }
+  if ((int)__builtin_popcountll(S) != T) return false;
+  uint64_t D = 0;
+  for (int b = 0; b < n; ++b)
+    if ((S >> b) & 1) D |= uint64_t(1) << perm.pi[b];
+  if (!tile_swizzle_ok(n, dtype, S) || !tile_swizzle_ok(n, dtype, D)) return false;
+  g.S = S;
+  g.D = D;
+  g.dswizzle = 1;
+  int i = 0;
+  for (int b = 0; b < n; ++b)
+    if ((S >> b) & 1) g.sigma[i++] = (int)__builtin_popcountll(D & ((uint64_t(1) << perm.pi[b]) - 1));
+  return true;
+}
+
 template <typename C>
 inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool no_fuse, Plan& plan, std::string& err,
-                       const Plan* replay = nullptr) {
+                       const Plan* replay = nullptr, const PermSpec* perm = nullptr) {
   const int Tfull = tile_bits_for(dtype);
   const int T = n < Tfull ? n : Tfull;
   // low bits every tile spans.  complex128 up to 30 qubits: 4 (256-byte rows; the tensor-map copy moves 128-byte
@@ -1049,9 +1267,289 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
   const size_t window = (size_t)env_int("QB_REORDER_WINDOW", 4096);
   std::vector<char> done(N, 0);
   size_t ndone = 0, first = 0;
+  // ---- a trailing permutation rides on the LAST sweep: the maximal suffix of ops that mix only bits of that sweep's tile
+  // is held back for it (possibly no op at all: the sweep is then the permutation alone).  Candidate tiles trade row
+  // length for room: f free tile bits next to 2^ls-amplitude source rows and 2^ld-amplitude destination rows take the f
+  // bits the last gates mix; the candidate that leaves the fewest sweeps in front wins, longer rows first.
+  PermGeom pgeom;
+  bool fuse_perm = false;
+  std::vector<size_t> held;
+  if (perm != nullptr && replay) {
+    if (replay->perm_fused && !replay->sweep_ops.empty()) {
+      fuse_perm = true;
+      pgeom = replay->pgeom;
+      for (uint32_t q : replay->sweep_ops.back()) {
+        if (q >= N) { err = "replay: bad op index"; return false; }
+        held.push_back(q);
+      }
+    }
+  } else if (perm != nullptr && !no_fuse && !env_int("QB_NO_FUSE_PERM", 0)) {
+    auto hold = [&](const PermGeom& pg, std::vector<size_t>& out) {
+      out.clear();
+      size_t est = sizeof(SweepHeader) + 2 * sizeof(PassHeader) + 4096;
+      int slot_est = 0;
+      for (size_t q = N; q > 0; --q) {
+        const PlanOp& p = pops[q - 1];
+        if (xset[q - 1] & ~pg.S) break;
+        est += blob_estimate(p, csize, T, R) + sizeof(PassHeader);
+        slot_est += (p.kind == CK_PHASE || p.kind == CK_DIAG || !p.cpos.empty()) ? 1 : 0;
+        if ((int)out.size() >= max_ops / 2 || est > (size_t)SWEEP_BLOB_MAX || slot_est > SWEEP_MAX_SLOTS) break;
+        out.push_back(q - 1);
+      }
+      std::reverse(out.begin(), out.end());
+      // leading diagonal ops belong to the gate in front of them (the fan of a QFT stage whose Hadamard stays behind)
+      size_t lead = 0;
+      while (lead < out.size() && xset[out[lead]] == 0) ++lead;
+      out.erase(out.begin(), out.begin() + (long)lead);
+    };
+    int best_est = 1 << 30;
+    const int fmax = env_int("QB_PERM_MAX_FREE", 4);
+    for (int f = 0; f <= fmax && f <= T - 8; ++f) {
+      const int ld = (T - f) / 2, ls = T - f - ld;
+      // the f bits the last mixing gates need beyond the rows
+      PermGeom base;
+      if (!perm_geometry(n, dtype, T, *perm, ls, ld, {}, base)) continue;
+      std::vector<int> extra;
+      if (f > 0) {
+        uint64_t have = (uint64_t(1) << ls) - 1;
+        for (int b = 0; b < n; ++b)
+          if (perm->pi[b] < ld) have |= uint64_t(1) << b;
+        for (size_t q = N; q > 0 && (int)extra.size() < f; --q) {
+          uint64_t miss = xset[q - 1] & ~have;
+          if ((int)__builtin_popcountll(miss) + (int)extra.size() > f) break;
+          for (int b = 0; miss; ++b)
+            if ((miss >> b) & 1) {
+              extra.push_back(b);
+              have |= uint64_t(1) << b;
+              miss &= ~(uint64_t(1) << b);
+            }
+        }
+      }
+      PermGeom cand;
+      if (!perm_geometry(n, dtype, T, *perm, ls, ld, extra, cand)) continue;
+      std::vector<size_t> h;
+      hold(cand, h);
+      // sweeps left in front: the high bits the other gates mix, free_high per sweep
+      std::vector<char> is_held(N, 0);
+      for (size_t q : h) is_held[q] = 1;
+      uint64_t mixed = 0;
+      for (size_t q = 0; q < N; ++q)
+        if (!is_held[q]) mixed |= xset[q];
+      const int hb = (int)__builtin_popcountll(mixed & ~lowmask);
+      const int est = mixed == 0 ? 0 : std::max(1, (hb + std::max(free_high, 1) - 1) / std::max(free_high, 1));
+      if (est < best_est) {
+        best_est = est;
+        pgeom = cand;
+        held = h;
+        fuse_perm = true;
+      }
+    }
+  }
+  if (fuse_perm) {
+    for (size_t h : held) done[h] = 2;  // not available to the sweeps before
+    ndone += held.size();
+  }
   // ops a sweep may take: the blob estimate of the scan below cannot know the passes (one group table per distinct
   // register set, 1 KiB each for complex64), so a sweep whose program does not fit after all is planned again with
   // half as many ops
+  enum { SW_OK = 0, SW_RETRY = 1, SW_FAIL = 2 };
+  // one sweep from the ops `chosen` (program order) on the tile lowmask | high; `pg`: the permuting sweep
+  auto emit_sweep = [&](const std::vector<size_t>& chosen, uint64_t high, const PermGeom* pg) -> int {
+    // ---- complete the tile with the lowest unused bits (longest contiguous runs)
+    uint64_t tile_mask = pg ? pg->S : (lowmask | high);
+    for (int b = 0; b < n && __builtin_popcountll(tile_mask) < T; ++b) tile_mask |= uint64_t(1) << b;
+    if (pg && tile_mask != pg->S) { err = "internal: permuting sweep tile mismatch"; return SW_FAIL; }
+    SweepBuilder<C> sb;
+    sb.T = T;
+    sb.R = R;
+    sb.tile_mask = tile_mask;
+    sb.local_of_pos.assign(64, -1);
+    {
+      int lb = 0;
+      for (int b = 0; b < n; ++b)
+        if ((tile_mask >> b) & 1) sb.local_of_pos[b] = lb++;
+    }
+    int L = 0;
+    while (L < n && ((tile_mask >> L) & 1)) ++L;
+    SweepHeader hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.T = T;
+    hdr.L = L;
+    hdr.R = R;
+    hdr.tile_mask = tile_mask;
+    hdr.other_mask = all & ~tile_mask;
+    hdr.ntiles = uint64_t(1) << (n - T);
+    hdr.swizzle = tile_swizzle_ok(n, dtype, tile_mask) ? 1u : 0u;
+    SweepDesc sd;
+    sd.swizzle = (int)hdr.swizzle;
+    sd.T = T;
+    sd.L = L;
+    sd.tile_mask = tile_mask;
+    sd.ntiles = hdr.ntiles;
+    if (pg) {
+      hdr.permuted = 1;
+      hdr.dswizzle = pg->dswizzle ? 1u : 0u;
+      hdr.dtile_mask = pg->D;
+      for (int b = 0; b < n; ++b) hdr.dst_bit[b] = (uint8_t)perm->pi[b];
+      sd.permuted = 1;
+      sd.dswizzle = pg->dswizzle;
+      sd.dmask = pg->D;
+    }
+
+    // ---- H-like gates: all but the last one of the sweep run as (a+b, a-b); the last one carries the product of
+    // their scalars (a scalar commutes with everything).  Halves the FP work of those gates.
+    std::vector<PlanOp> sops;
+    sops.reserve(chosen.size());
+    for (size_t q : chosen) sops.push_back(pops[q]);
+    if (!no_fuse && !env_int("QB_NO_ADDSUB", 0)) {
+      std::vector<size_t> cand;
+      for (size_t q = 0; q < sops.size(); ++q)
+        if (is_hadamard_like(sops[q])) cand.push_back(q);
+      if (cand.size() >= 2) {
+        cd prod(1.0, 0.0);
+        for (size_t q : cand) prod *= sops[q].data[0];
+        for (size_t c = 0; c + 1 < cand.size(); ++c) sops[cand[c]].special = 1;
+        PlanOp& last = sops[cand.back()];
+        last.data = {prod, prod, prod, -prod};
+      }
+    }
+
+    // ---- split the sweep's ops into passes: a REGTILE pass holds ops whose dense targets fit R register bits
+    std::vector<const PlanOp*> cur;
+    uint32_t cur_r = 0;  // tile-local mask of the register bits demanded so far
+    struct PassPlan { std::vector<const PlanOp*> ops; uint32_t need; const PlanOp* big; };
+    std::vector<PassPlan> pplans;
+    auto close_pass = [&]() -> bool {
+      if (cur.empty()) return true;
+      pplans.push_back({cur, cur_r, nullptr});
+      cur.clear();
+      cur_r = 0;
+      return true;
+    };
+    // list scheduling again, one level down: a gate joins the open pass when it commutes with every gate of the sweep
+    // that stays behind and the pass still has a register bit for it (a pass follows the light cone of its <= R qubits)
+    {
+      const size_t M = sops.size();
+      std::vector<uint64_t> sx(M, 0), sd_(M, 0);
+      for (size_t q = 0; q < M; ++q) {
+        const PlanOp& p = sops[q];
+        for (int s : p.src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
+        for (int c : p.cpos) sd_[q] |= uint64_t(1) << c;
+        if (p.kind == CK_DENSE || p.kind == CK_SWAP)
+          for (int t : p.tpos) sx[q] |= uint64_t(1) << t;
+        else if (p.kind == CK_DIAG)
+          for (int t : p.tpos) sd_[q] |= uint64_t(1) << t;
+        else
+          for (auto& kv : p.fan) sd_[q] |= uint64_t(1) << kv.first;
+        if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
+      }
+      std::vector<char> placed(M, 0);
+      size_t nplaced = 0, head = 0;
+      while (nplaced < M) {
+        while (head < M && placed[head]) ++head;
+        uint64_t bx = 0, bd = 0;
+        bool took_big = false;
+        for (size_t q = head; q < M; ++q) {
+          if (placed[q]) continue;
+          const PlanOp& p = sops[q];
+          bool ok = !((sx[q] & (bx | bd)) || (sd_[q] & bx));
+          if (ok && p.kind == CK_DENSE && p.tpos.size() > 2) {
+            if (cur.empty()) {  // a dense block on 3..6 targets is a pass of its own
+              pplans.push_back({{}, 0u, &p});
+              ++sd.npasses;
+              placed[q] = 1;
+              ++nplaced;
+              took_big = true;
+              break;
+            }
+            ok = false;
+          } else if (ok) {
+            uint32_t need = 0;
+            if (p.kind == CK_DENSE || p.kind == CK_SWAP)
+              for (int t : p.tpos) need |= 1u << sb.local_of_pos[t];
+            if (__builtin_popcount(need) > R) { err = "internal: gate needs more register bits than a pass has"; return SW_FAIL; }
+            if (__builtin_popcount(cur_r | need) > R) {
+              ok = false;
+            } else {
+              cur_r |= need;
+              cur.push_back(&p);
+              placed[q] = 1;
+              ++nplaced;
+            }
+          }
+          if (!ok) {
+            if (!reorder) break;
+            bx |= sx[q];
+            bd |= sd_[q];
+          }
+        }
+        if (took_big) continue;
+        if (cur.empty()) { err = "internal: the pass scheduler made no progress"; return SW_FAIL; }
+        ++sd.npasses;
+        if (!close_pass()) return SW_FAIL;
+      }
+    }
+    if (!close_pass()) return SW_FAIL;
+    // ---- warp-private sub-tiles when three tile bits stay out of every pass's register set, then emit the passes
+    {
+      std::vector<uint32_t> needs;
+      bool has_big = false;
+      for (auto& pp : pplans) {
+        if (pp.big) has_big = true;
+        else needs.push_back(pp.need);
+      }
+      // (a permuting sweep's last pass stores across warps: team barriers)
+      sb.split_mask = (no_fuse || pg) ? 0u : choose_split(T, R, csize, hdr.swizzle != 0, needs, has_big);
+      hdr.warp_private = sb.split_mask ? 1u : 0u;
+      // the LAST pass of a permuting sweep writes its groups in the destination layout: it must be a REGTILE pass (an
+      // empty one when the sweep ends with a dense block, or has no gate at all)
+      if (pg && (pplans.empty() || pplans.back().big)) {
+        pplans.push_back({{}, 0u, nullptr});
+        ++sd.npasses;
+      }
+      for (size_t pi_ = 0; pi_ < pplans.size(); ++pi_) {
+        auto& pp = pplans[pi_];
+        if (pp.big) {
+          if (!emit_big_pass<C>(sb, *pp.big, err)) return SW_FAIL;
+        } else {
+          // pad the register set to R bits, preferring high tile-local bits (keeps lanes on the low bits)
+          const bool last_permuted = pg && pi_ + 1 == pplans.size();
+          if (!emit_regtile_pass<C>(sb, pp.ops, pad_register_bits(T, R, pp.need, sb.split_mask), err, last_permuted ? pg : nullptr, hdr.swizzle != 0))
+            return SW_FAIL;
+        }
+      }
+    }
+    // (an empty pass -- the permuted store alone -- runs on either kernel instantiation)
+    sd.stage_only = sb.passes.empty() ? 0 : 1;
+    for (auto& ph_ : sb.passes)
+      if (ph_.kind != PASS_REGTILE || (ph_.stage_mask == 0 && ph_.nmicro != 0)) sd.stage_only = 0;
+    const size_t blob_before = plan.blob.size();
+    const bool too_many_slots = (int)sb.slots.size() > SWEEP_MAX_SLOTS;
+    if (!too_many_slots) finish_blob<C>(sb, hdr, plan.blob, sd);
+    if (too_many_slots || hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) {
+      if (replay) { err = "replay: sweep program no longer fits"; return SW_FAIL; }
+      if (chosen.size() <= 1) {
+        err = too_many_slots ? "internal: too many per-tile slots in one sweep" : "internal: sweep program too large";
+        return SW_FAIL;
+      }
+      plan.blob.resize(blob_before);  // plan this sweep again with fewer ops
+      return SW_RETRY;
+    }
+    plan.npasses += sd.npasses;
+    plan.ndiag += sd.ndiag;
+    if (env_int("QB_PLAN_DEBUG", 0))
+      fprintf(stderr, "[qb plan] sweep %zu: ops %zu passes %d tile %#llx L %d swizzle %u warp_private %u split %#x blob %u B slots %zu stage_only %d\n", plan.sweeps.size(),
+              sops.size(), sd.npasses, (unsigned long long)tile_mask, L, hdr.swizzle, hdr.warp_private, sb.split_mask, hdr.blob_bytes, sb.slots.size(), sd.stage_only);
+    if (env_int("QB_PLAN_DEBUG", 0) > 1)
+      for (size_t p_ = 0; p_ < sb.passes.size(); ++p_) {
+        fprintf(stderr, "[qb plan]   pass %zu kind %u rmask %#x stage_mask %#x flags %u handlers:", p_, sb.passes[p_].kind, sb.passes[p_].rmask, sb.passes[p_].stage_mask, sb.passes[p_].flags);
+        for (auto& m_ : sb.micro[p_]) fprintf(stderr, " %d", (int)m_.handler);
+        fprintf(stderr, "\n");
+      }
+    plan.sweeps.push_back(sd);
+    plan.sweep_ops.emplace_back(chosen.begin(), chosen.end());
+    return SW_OK;
+  };
   int cur_max_ops = max_ops;
   while (ndone < N) {
     while (first < N && done[first]) ++first;
@@ -1136,184 +1634,24 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
       }
     }
     if (chosen.empty()) { err = "internal: the sweep scheduler made no progress"; return false; }
-    for (size_t q : chosen) done[q] = 1;
-    ndone += chosen.size();
-    // ---- complete the tile with the lowest unused bits (longest contiguous runs)
-    uint64_t tile_mask = lowmask | high;
-    for (int b = 0; b < n && __builtin_popcountll(tile_mask) < T; ++b) tile_mask |= uint64_t(1) << b;
-    SweepBuilder<C> sb;
-    sb.T = T;
-    sb.R = R;
-    sb.tile_mask = tile_mask;
-    sb.local_of_pos.assign(64, -1);
-    {
-      int lb = 0;
-      for (int b = 0; b < n; ++b)
-        if ((tile_mask >> b) & 1) sb.local_of_pos[b] = lb++;
-    }
-    int L = 0;
-    while (L < n && ((tile_mask >> L) & 1)) ++L;
-    SweepHeader hdr;
-    memset(&hdr, 0, sizeof(hdr));
-    hdr.T = T;
-    hdr.L = L;
-    hdr.R = R;
-    hdr.tile_mask = tile_mask;
-    hdr.other_mask = all & ~tile_mask;
-    hdr.ntiles = uint64_t(1) << (n - T);
-    hdr.swizzle = tile_swizzle_ok(n, dtype, tile_mask) ? 1u : 0u;
-    SweepDesc sd;
-    sd.swizzle = (int)hdr.swizzle;
-    sd.T = T;
-    sd.L = L;
-    sd.tile_mask = tile_mask;
-    sd.ntiles = hdr.ntiles;
-
-    // ---- H-like gates: all but the last one of the sweep run as (a+b, a-b); the last one carries the product of
-    // their scalars (a scalar commutes with everything).  Halves the FP work of those gates.
-    std::vector<PlanOp> sops;
-    sops.reserve(chosen.size());
-    for (size_t q : chosen) sops.push_back(pops[q]);
-    if (!no_fuse && !env_int("QB_NO_ADDSUB", 0)) {
-      std::vector<size_t> cand;
-      for (size_t q = 0; q < sops.size(); ++q)
-        if (is_hadamard_like(sops[q])) cand.push_back(q);
-      if (cand.size() >= 2) {
-        cd prod(1.0, 0.0);
-        for (size_t q : cand) prod *= sops[q].data[0];
-        for (size_t c = 0; c + 1 < cand.size(); ++c) sops[cand[c]].special = 1;
-        PlanOp& last = sops[cand.back()];
-        last.data = {prod, prod, prod, -prod};
-      }
-    }
-
-    // ---- split the sweep's ops into passes: a REGTILE pass holds ops whose dense targets fit R register bits
-    std::vector<const PlanOp*> cur;
-    uint32_t cur_r = 0;  // tile-local mask of the register bits demanded so far
-    struct PassPlan { std::vector<const PlanOp*> ops; uint32_t need; const PlanOp* big; };
-    std::vector<PassPlan> pplans;
-    auto close_pass = [&]() -> bool {
-      if (cur.empty()) return true;
-      pplans.push_back({cur, cur_r, nullptr});
-      cur.clear();
-      cur_r = 0;
-      return true;
-    };
-    // list scheduling again, one level down: a gate joins the open pass when it commutes with every gate of the sweep
-    // that stays behind and the pass still has a register bit for it (a pass follows the light cone of its <= R qubits)
-    {
-      const size_t M = sops.size();
-      std::vector<uint64_t> sx(M, 0), sd_(M, 0);
-      for (size_t q = 0; q < M; ++q) {
-        const PlanOp& p = sops[q];
-        for (int s : p.src) plan.sweep_of_op[s] = (int)plan.sweeps.size();
-        for (int c : p.cpos) sd_[q] |= uint64_t(1) << c;
-        if (p.kind == CK_DENSE || p.kind == CK_SWAP)
-          for (int t : p.tpos) sx[q] |= uint64_t(1) << t;
-        else if (p.kind == CK_DIAG)
-          for (int t : p.tpos) sd_[q] |= uint64_t(1) << t;
-        else
-          for (auto& kv : p.fan) sd_[q] |= uint64_t(1) << kv.first;
-        if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
-      }
-      std::vector<char> placed(M, 0);
-      size_t nplaced = 0, head = 0;
-      while (nplaced < M) {
-        while (head < M && placed[head]) ++head;
-        uint64_t bx = 0, bd = 0;
-        bool took_big = false;
-        for (size_t q = head; q < M; ++q) {
-          if (placed[q]) continue;
-          const PlanOp& p = sops[q];
-          bool ok = !((sx[q] & (bx | bd)) || (sd_[q] & bx));
-          if (ok && p.kind == CK_DENSE && p.tpos.size() > 2) {
-            if (cur.empty()) {  // a dense block on 3..6 targets is a pass of its own
-              pplans.push_back({{}, 0u, &p});
-              ++sd.npasses;
-              placed[q] = 1;
-              ++nplaced;
-              took_big = true;
-              break;
-            }
-            ok = false;
-          } else if (ok) {
-            uint32_t need = 0;
-            if (p.kind == CK_DENSE || p.kind == CK_SWAP)
-              for (int t : p.tpos) need |= 1u << sb.local_of_pos[t];
-            if (__builtin_popcount(need) > R) { err = "internal: gate needs more register bits than a pass has"; return false; }
-            if (__builtin_popcount(cur_r | need) > R) {
-              ok = false;
-            } else {
-              cur_r |= need;
-              cur.push_back(&p);
-              placed[q] = 1;
-              ++nplaced;
-            }
-          }
-          if (!ok) {
-            if (!reorder) break;
-            bx |= sx[q];
-            bd |= sd_[q];
-          }
-        }
-        if (took_big) continue;
-        if (cur.empty()) { err = "internal: the pass scheduler made no progress"; return false; }
-        ++sd.npasses;
-        if (!close_pass()) return false;
-      }
-    }
-    if (!close_pass()) return false;
-    // ---- warp-private sub-tiles when three tile bits stay out of every pass's register set, then emit the passes
-    {
-      std::vector<uint32_t> needs;
-      bool has_big = false;
-      for (auto& pp : pplans) {
-        if (pp.big) has_big = true;
-        else needs.push_back(pp.need);
-      }
-      sb.split_mask = no_fuse ? 0u : choose_split(T, R, csize, hdr.swizzle != 0, needs, has_big);
-      hdr.warp_private = sb.split_mask ? 1u : 0u;
-      for (auto& pp : pplans) {
-        if (pp.big) {
-          if (!emit_big_pass<C>(sb, *pp.big, err)) return false;
-        } else {
-          // pad the register set to R bits, preferring high tile-local bits (keeps lanes on the low bits)
-          if (!emit_regtile_pass<C>(sb, pp.ops, pad_register_bits(T, R, pp.need, sb.split_mask), err)) return false;
-        }
-      }
-    }
-    sd.stage_only = sb.passes.empty() ? 0 : 1;
-    for (auto& ph_ : sb.passes)
-      if (ph_.kind != PASS_REGTILE || ph_.stage_mask == 0) sd.stage_only = 0;
-    const size_t blob_before = plan.blob.size();
-    const bool too_many_slots = (int)sb.slots.size() > SWEEP_MAX_SLOTS;
-    if (!too_many_slots) finish_blob<C>(sb, hdr, plan.blob, sd);
-    if (too_many_slots || hdr.blob_bytes > (size_t)SWEEP_BLOB_MAX + 1024) {
-      if (replay) { err = "replay: sweep program no longer fits"; return false; }
-      if (chosen.size() <= 1) {
-        err = too_many_slots ? "internal: too many per-tile slots in one sweep" : "internal: sweep program too large";
-        return false;
-      }
-      plan.blob.resize(blob_before);  // plan this sweep again with fewer ops
-      for (size_t q : chosen) done[q] = 0;
-      ndone -= chosen.size();
+    const int rc = emit_sweep(chosen, high, nullptr);
+    if (rc == SW_FAIL) return false;
+    if (rc == SW_RETRY) {
       cur_max_ops = (int)chosen.size() / 2;
       continue;
     }
+    for (size_t q : chosen) done[q] = 1;
+    ndone += chosen.size();
     cur_max_ops = max_ops;
-    plan.npasses += sd.npasses;
-    plan.ndiag += sd.ndiag;
-    if (env_int("QB_PLAN_DEBUG", 0))
-      fprintf(stderr, "[qb plan] sweep %zu: ops %zu passes %d tile %#llx L %d swizzle %u warp_private %u split %#x blob %u B slots %zu stage_only %d\n", plan.sweeps.size(),
-              sops.size(), sd.npasses, (unsigned long long)tile_mask, L, hdr.swizzle, hdr.warp_private, sb.split_mask, hdr.blob_bytes, sb.slots.size(), sd.stage_only);
-    if (env_int("QB_PLAN_DEBUG", 0) > 1)
-      for (size_t p_ = 0; p_ < sb.passes.size(); ++p_) {
-        fprintf(stderr, "[qb plan]   pass %zu kind %u rmask %#x stage_mask %#x flags %u handlers:", p_, sb.passes[p_].kind, sb.passes[p_].rmask, sb.passes[p_].stage_mask, sb.passes[p_].flags);
-        for (auto& m_ : sb.micro[p_]) fprintf(stderr, " %d", (int)m_.handler);
-        fprintf(stderr, "\n");
-      }
-    plan.sweeps.push_back(sd);
-    plan.sweep_ops.emplace_back(chosen.begin(), chosen.end());
+  }
+  if (fuse_perm) {
+    const int rc = emit_sweep(held, 0, &pgeom);
+    if (rc != SW_OK) {
+      if (rc == SW_RETRY) err = "the ops held back for the permuting sweep do not fit one sweep program";
+      return false;  // (the caller plans again without the permutation)
+    }
+    plan.perm_fused = 1;
+    plan.pgeom = pgeom;
   }
   return true;
 }
@@ -1321,14 +1659,26 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
 // `replay`: the plan of a program with the same gate structure (targets, controls, which gates are diagonal): its
 // schedule is reused and only the passes are emitted again with the new numbers; false + err when the structure differs
 // (e.g. a rotation angle became 0 and the gate an identity) -- the caller then plans from scratch.
+// `perm`: a qubit permutation to apply after the ops.  plan.perm_fused tells whether it rides on the last sweep (which then
+// writes OUT OF PLACE, launch_sweep's `dst`); otherwise the plan is the plain one and the caller runs K8 after it.
 inline bool plan_program(int n, int dtype, const std::vector<CanonOp>& ops, bool no_fuse, Plan& plan, std::string& err,
-                         const Plan* replay = nullptr) {
-  plan = Plan();
-  plan.sweep_of_op.assign(ops.size(), -1);
+                         const Plan* replay = nullptr, const PermSpec* perm = nullptr) {
   std::vector<PlanOp> pops;
   merge_ops(ops, no_fuse, pops);
-  if (dtype == QB_C128) return build_plan<d2>(n, dtype, pops, no_fuse, plan, err, replay);
-  return build_plan<f2>(n, dtype, pops, no_fuse, plan, err, replay);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    plan = Plan();
+    plan.sweep_of_op.assign(ops.size(), -1);
+    const PermSpec* pm = attempt == 0 ? perm : nullptr;
+    if (replay && (replay->perm_fused != 0) != (pm != nullptr)) {
+      if (replay->perm_fused) { err = "replay: the program was planned with a fused permutation"; return false; }
+      pm = nullptr;
+    }
+    const bool ok = dtype == QB_C128 ? build_plan<d2>(n, dtype, pops, no_fuse, plan, err, replay, pm)
+                                     : build_plan<f2>(n, dtype, pops, no_fuse, plan, err, replay, pm);
+    if (ok) return true;
+    if (pm == nullptr || replay) return false;  // (a failed fusion: plan again without the permutation)
+  }
+  return false;
 }
 
 inline void fill_stats(const Plan& plan, int n, int dtype, int nops, qb_program_stats* st) {
@@ -1339,6 +1689,7 @@ inline void fill_stats(const Plan& plan, int n, int dtype, int nops, qb_program_
   st->ndiag_ops = plan.ndiag;
   st->bytes_moved = (double)plan.sweeps.size() * 2.0 * (dtype == QB_C128 ? 16.0 : 8.0) * (double)(uint64_t(1) << n);
   for (auto& sd : plan.sweeps) st->nstage_sweeps += sd.stage_only ? 1 : 0;
+  st->perm_fused = plan.perm_fused;
 }
 
 }  // namespace qb

@@ -183,7 +183,7 @@ QB_D void team_bar(int team) {
 
 // ---- the kernel -----------------------------------------------------------------------------------------
 template <typename C, bool SO>
-__global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __restrict__ state, const char* __restrict__ prog, const __grid_constant__ TmaDesc tma) {
+__global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __restrict__ state, const char* __restrict__ prog, const __grid_constant__ TmaDesc tma, const __grid_constant__ TmaDesc tma_dst) {
   extern __shared__ __align__(1024) unsigned char smem[];
   C* tiles = reinterpret_cast<C*>(smem);
   char* blob = reinterpret_cast<char*>(smem + SW_NBUF * SW_TILE_BYTES);
@@ -285,7 +285,23 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
       const int b = (int)(j % SW_NBUF);
       mbar_wait_sleep(&done[b], (uint32_t)((j / SW_NBUF) & 1));
       const char* sbase = reinterpret_cast<const char*>(tiles + (size_t)b * tile_elems);
-      if (tma.enabled) {
+      if (hdr.permuted) {
+        // permuting sweep: the compute team left the tile in the DESTINATION layout; it goes out through the destination
+        // tensor map (another buffer) at the tile base with every bit moved to its destination
+        uint64_t contrib = 0;
+        for (int bit = lane; bit < 64; bit += 32)
+          if ((hdr.other_mask >> bit) & 1) contrib |= ((base >> bit) & uint64_t(1)) << hdr.dst_bit[bit];
+        const uint64_t dbase = (uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)contrib) |
+                               ((uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)(contrib >> 32)) << 32);
+        if (lane == 0) {
+          tma_store_5d(&tma_dst.map, (int)((dbase >> tma_dst.shift[0]) & tma_dst.mask[0]), (int)((dbase >> tma_dst.shift[1]) & tma_dst.mask[1]),
+                       (int)((dbase >> tma_dst.shift[2]) & tma_dst.mask[2]), (int)((dbase >> tma_dst.shift[3]) & tma_dst.mask[3]),
+                       (int)((dbase >> tma_dst.shift[4]) & tma_dst.mask[4]), sbase);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(&freeb[b]);
+        }
+      } else if (tma.enabled) {
         if (lane == 0) {
           tma_store_5d(&tma.map, (int)((base >> tma.shift[0]) & tma.mask[0]), (int)((base >> tma.shift[1]) & tma.mask[1]),
                        (int)((base >> tma.shift[2]) & tma.mask[2]), (int)((base >> tma.shift[3]) & tma.mask[3]),
@@ -331,7 +347,7 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
         }
         if (ph.kind == PASS_REGTILE) {
           // R < RB only occurs for n < 4, which qb_apply_program routes to the K1 kernels
-          run_pass<C, RB, GPT, SO>(tile, blob, ts, ph, T, swz_on, ctid, SW_TEAM_THREADS);
+          run_pass<C, RB, GPT, SO>(tile, blob, ts, ph, T, swz_on, ctid, SW_TEAM_THREADS, (C*)nullptr, [team]() { team_bar(team); });
         } else if constexpr (!SO) {
           const DevOp& op = *reinterpret_cast<const DevOp*>(blob + ph.offset);
           if (op.slot == MU_NO_SLOT || ts[op.slot].active) {
@@ -423,19 +439,26 @@ inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask
   return true;
 }
 
+// `dst`: the buffer a PERMUTING sweep (sd.permuted) writes to -- another buffer of the state's size; ignored otherwise.
 inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqubits, int dtype, const SweepDesc& sd,
-                        const char* prog_dev) {
+                        const char* prog_dev, void* dst = nullptr) {
   uint64_t grid = sd.ntiles < (uint64_t)sm_count ? sd.ntiles : (uint64_t)sm_count;
-  TmaDesc tma;
+  TmaDesc tma, tma_dst;
   if (!tma_describe(state, nqubits, dtype, sd.tile_mask, sd.swizzle != 0, tma) && sd.swizzle) return QB_ERR_UNSUPPORTED;  // planned for a swizzled tile
+  if (sd.permuted) {
+    if (!dst || dst == state) return QB_ERR_INVALID;
+    if (!tma_describe(dst, nqubits, dtype, sd.dmask, sd.dswizzle != 0, tma_dst)) return QB_ERR_UNSUPPORTED;
+  } else {
+    tma_dst = tma;
+  }
   const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);
   tma.pad[0] = env_int("QB_SWEEP_SKIP_COMPUTE", 0);
   if (dtype == QB_C128) {
-    if (so) sweep_kernel<double2, true><<<(unsigned)grid, sw_threads<double2, true>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
-    else sweep_kernel<double2, false><<<(unsigned)grid, sw_threads<double2, false>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma);
+    if (so) sweep_kernel<double2, true><<<(unsigned)grid, sw_threads<double2, true>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma, tma_dst);
+    else sweep_kernel<double2, false><<<(unsigned)grid, sw_threads<double2, false>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma, tma_dst);
   } else {
-    if (so) sweep_kernel<float2, true><<<(unsigned)grid, sw_threads<float2, true>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma);
-    else sweep_kernel<float2, false><<<(unsigned)grid, sw_threads<float2, false>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma);
+    if (so) sweep_kernel<float2, true><<<(unsigned)grid, sw_threads<float2, true>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma, tma_dst);
+    else sweep_kernel<float2, false><<<(unsigned)grid, sw_threads<float2, false>(), SW_SMEM_BYTES, stream>>>((float2*)state, prog_dev + sd.blob_offset, tma, tma_dst);
   }
   return cudaPeekAtLastError() == cudaSuccess ? QB_OK : QB_ERR_CUDA;
 }

@@ -55,6 +55,9 @@ class Engine:
         self._freeze_imports()
         self.last_stats = None
         self.permute_swap_runs = True
+        # a run of SWAPs behind a run of gates rides on the LAST sweep of those gates (qb_apply_program_permuted): the sweep
+        # writes its tiles permuted, out of place -- no separate K8 pass over the state
+        self.fuse_permutations = os.environ.get("QB_NO_FUSE_PERM", "0") in ("", "0")
         self.exact_scan_max_bins = EXACT_SCAN_MAX_BINS
 
     def bind_current_stream(self):
@@ -122,6 +125,15 @@ class Engine:
         import gc
 
         gc.collect()
+
+    def reclaim_before(self, nbytes: int):
+        """Called by the backend before it builds a state of ``nbytes``: for states that fill a large part of the device,
+        collect the PREVIOUS execution's cyclic garbage now (< 2 ms once the imports are frozen) -- its state buffer goes
+        back to the allocator's cache and its compiled program is destroyed while the stream is idle -- instead of in the
+        middle of this execution, where whether the buffers fit depended on when Python's collector last ran (measured:
+        plugin-level QFT(32) steps of 145 or 215 ms at random)."""
+        if nbytes >= (1 << 30):
+            self._reclaim()
 
     def basis_state(self, nqubits: int, dtype="complex128", index: int = 0) -> DeviceArray:
         """zero_state (abstract.py:2243-2273) generalised to any basis index."""
@@ -250,14 +262,7 @@ class Engine:
                 self.handle, state.data_ptr(), scratch.data_ptr(), nqubits, _DT[state.dtype], _int_array(dest_of_qubit)
             )
         )
-        if alt is not None:
-            state.tensor, alt.tensor = alt.tensor, state.tensor
-            so, ao = getattr(state, "_owner", None), getattr(alt, "_owner", None)
-            state._owner, alt._owner = ao, so
-        elif getattr(state, "_owner", None) is not None:
-            state.tensor.copy_(scratch)
-        else:
-            state.tensor = scratch
+        self._adopt_result(state, scratch, alt)
         if spans is not None:
             e1.record()
             spans.append(("perm", e0, e1, 1))
@@ -266,6 +271,38 @@ class Engine:
             e1.synchronize()
             return e0.elapsed_time(e1)
         return None
+
+    @staticmethod
+    def _adopt_result(state: DeviceArray, scratch: torch.Tensor, alt: Optional[DeviceArray]):
+        """After an out-of-place launch wrote its result to ``scratch`` (= ``alt.tensor`` when given): re-point ``state``."""
+        if alt is not None:
+            state.tensor, alt.tensor = alt.tensor, state.tensor
+            so, ao = getattr(state, "_owner", None), getattr(alt, "_owner", None)
+            state._owner, alt._owner = ao, so
+        elif getattr(state, "_owner", None) is not None:
+            state.tensor.copy_(scratch)
+        else:
+            state.tensor = scratch
+
+    def _apply_sweeps_permuted(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], dest_of_qubit: Sequence[int], fuse: bool,
+                               timed: bool, alt: Optional[DeviceArray]):
+        """``ops`` then the qubit permutation, the permutation riding on the last sweep (qb_apply_program_permuted with
+        QB_PROGRAM_PERM_FUSED_ONLY: NotImplementedError -- nothing launched -- when it cannot; OutOfMemoryError when no
+        second buffer fits).  The DeviceArray is re-pointed at the result buffer as in ``permute_qubits``."""
+        self.bind_current_stream()
+        scratch = self._alloc(tuple(state.tensor.shape), state.tensor.dtype) if alt is None else alt.tensor
+        stats = _lib.QbProgramStats()
+        arr, keep = pack_ops(ops)
+        flags = (0 if fuse else _lib.QB_PROGRAM_NO_FUSE) | (_lib.QB_PROGRAM_TIME if timed else 0) | _lib.QB_PROGRAM_PERM_FUSED_ONLY
+        _lib.check(
+            self.lib.qb_apply_program_permuted(
+                self.handle, state.data_ptr(), scratch.data_ptr(), nqubits, _DT[state.dtype], arr, len(ops), _int_array(dest_of_qubit),
+                flags, ctypes.byref(stats)
+            )
+        )
+        del keep
+        self._adopt_result(state, scratch, alt)
+        return stats
 
     def permute_raw(self, src_ptr: int, dst_ptr: int, nqubits: int, dtype, dest_of_qubit: Sequence[int]):
         """K8 on raw device pointers (a chunk of a shard as source, possibly a peer-mapped buffer as destination)."""
@@ -285,13 +322,27 @@ class Engine:
         total = _lib.QbProgramStats()
         total.nops = len(ops)
         total.perm_ms, total.nperm = 0.0, 0  # K8 launches inside this program (reported apart from the sweep kernel)
-        segments = split_segments(ops, nqubits, fuse and self.permute_swap_runs)
-        for kind, payload in segments:
+        segments = split_segments(ops, nqubits, fuse and self.permute_swap_runs, fuse and self.fuse_permutations)
+        total.nperm_fused = 0
+        while segments:
+            kind, payload = segments.pop(0)
             if kind == "wide":
                 self.apply_wide(state, nqubits, payload)
                 total.nsweeps += 3
                 total.bytes_moved += 6.0 * state.nbytes
                 continue
+            if kind == "opsperm":
+                gops, dest = payload
+                e0 = _record_event() if spans is not None else None
+                try:
+                    st = self._apply_sweeps_permuted(state, nqubits, gops, dest, fuse, timed, alt)
+                except (torch.cuda.OutOfMemoryError, NotImplementedError):
+                    segments[:0] = ([("ops", gops)] if gops else []) + [("perm", dest)]  # the two-launch form
+                    continue
+                if e0 is not None:
+                    spans.append(("sweep", e0, _record_event(), st.nsweeps))
+                total.nperm_fused += 1
+                kind = "done"
             if kind == "perm":
                 try:
                     ms = self.permute_qubits(state, nqubits, payload, timed=timed, alt=alt, spans=spans)
@@ -307,10 +358,11 @@ class Engine:
                     total.perm_ms += ms or 0.0
                     total.nperm += 1
                     continue
-            e0 = _record_event() if spans is not None else None
-            st = self._apply_sweeps(state, nqubits, payload, fuse, timed)
-            if e0 is not None:
-                spans.append(("sweep", e0, _record_event(), st.nsweeps))
+            if kind != "done":
+                e0 = _record_event() if spans is not None else None
+                st = self._apply_sweeps(state, nqubits, payload, fuse, timed)
+                if e0 is not None:
+                    spans.append(("sweep", e0, _record_event(), st.nsweeps))
             total.nsweeps += st.nsweeps
             total.ndense_passes += st.ndense_passes
             total.ndiag_ops += st.ndiag_ops
@@ -340,11 +392,33 @@ class Engine:
         total.nops = prog.nops
         total.perm_ms, total.nperm = 0.0, 0
         flags = _lib.QB_PROGRAM_TIME if timed else 0
-        for kind, payload in prog.segments:
+        total.nperm_fused = 0
+        for index, (kind, payload) in enumerate(prog.segments):
             if kind == "wide":
                 self.apply_wide(state, prog.nqubits, payload)
                 total.nsweeps += 3
                 total.bytes_moved += 6.0 * state.nbytes
+                continue
+            if kind == "progperm":
+                st = _lib.QbProgramStats()
+                try:
+                    scratch = self._alloc(tuple(state.tensor.shape), state.tensor.dtype) if alt is None else alt.tensor
+                except torch.cuda.OutOfMemoryError:  # no second buffer: the gates in place, the permutation as SWAP gates
+                    gops, dest = prog.fused_source[index]
+                    st = self._apply_sweeps(state, prog.nqubits, list(gops) + swaps_for_permutation(dest), True, timed)
+                else:
+                    e0 = _record_event() if spans is not None else None
+                    _lib.check(self.lib.qb_program_run_permuted(self.handle, payload, state.data_ptr(), scratch.data_ptr(), flags, ctypes.byref(st)))
+                    self._adopt_result(state, scratch, alt)
+                    if e0 is not None:
+                        spans.append(("sweep", e0, _record_event(), st.nsweeps))
+                    total.nperm_fused += 1
+                total.nsweeps += st.nsweeps
+                total.ndense_passes += st.ndense_passes
+                total.ndiag_ops += st.ndiag_ops
+                total.nstage_sweeps += st.nstage_sweeps
+                total.bytes_moved += st.bytes_moved
+                total.elapsed_ms += st.elapsed_ms
                 continue
             if kind == "perm":
                 try:
@@ -562,17 +636,37 @@ class CompiledProgram:
         self.engine, self.nqubits, self.dtype, self.nops = engine, nqubits, np.dtype(dtype), len(ops)
         self.segments = []
         self.nsweeps = 0
-        segments = split_segments(ops, nqubits, fuse and engine.permute_swap_runs)
+        segments = split_segments(ops, nqubits, fuse and engine.permute_swap_runs, fuse and engine.fuse_permutations)
         flags = 0 if fuse else _lib.QB_PROGRAM_NO_FUSE
+        self.fused_source = {}  # segment index of a "progperm" -> (its ops, dest_of_qubit): the no-second-buffer fallback
         # op index in ``ops`` -> (segment index, index inside that segment's program), or (-1, -1) for ops that became a
         # permutation / a wide block (set_params addresses ops by their position in the compiled list)
         self.op_segment = [(-1, -1)] * len(ops)
         position = {id(op): i for i, op in enumerate(ops)}
         try:
-            for kind, payload in segments:
+            while segments:
+                kind, payload = segments.pop(0)
                 if kind == "wide":
                     self.segments.append(("wide", payload))
                     self.nsweeps += 3
+                    continue
+                if kind == "opsperm":
+                    gops, dest = payload
+                    arr, keep = pack_ops(gops)
+                    handle, st = ctypes.c_void_p(), _lib.QbProgramStats()
+                    try:
+                        _lib.check(engine.lib.qb_program_create_permuted(
+                            engine.handle, nqubits, _DT[self.dtype], arr, len(gops), _int_array(dest),
+                            flags | _lib.QB_PROGRAM_PERM_FUSED_ONLY, ctypes.byref(handle), ctypes.byref(st)))
+                    except NotImplementedError:
+                        segments[:0] = ([("ops", gops)] if gops else []) + [("perm", dest)]
+                        continue
+                    del keep
+                    for local, op in enumerate(gops):
+                        self.op_segment[position[id(op)]] = (len(self.segments), local)
+                    self.fused_source[len(self.segments)] = (list(gops), list(dest))
+                    self.segments.append(("progperm", handle))
+                    self.nsweeps += st.nsweeps
                     continue
                 if kind == "perm":
                     self.segments.append(("perm", list(payload)))
@@ -637,7 +731,7 @@ class CompiledProgram:
 
     def close(self):
         for kind, payload in self.segments:
-            if kind == "prog" and payload and getattr(self.engine, "handle", None):
+            if kind in ("prog", "progperm") and payload and getattr(self.engine, "handle", None):
                 self.engine.lib.qb_program_destroy(self.engine.handle, payload)
         self.segments = []
 
@@ -699,9 +793,26 @@ def split_swap_runs(ops: Sequence[Op], nqubits: int):
     return out
 
 
-def split_segments(ops: Sequence[Op], nqubits: int, swap_runs: bool = True):
+def split_segments(ops: Sequence[Op], nqubits: int, swap_runs: bool = True, fuse_perm: bool = False):
     """-> [("ops", [...]) | ("perm", dest_of_qubit) | ("wide", op)]: the queue cut at blocks too wide for a sweep tile pass
-    (Engine.apply_wide) and, between them, at runs of plain SWAPs (K8)."""
+    (Engine.apply_wide) and, between them, at runs of plain SWAPs (K8).  ``fuse_perm``: a permutation, with the run of
+    gates in front of it if any, becomes ("opsperm", (ops, dest_of_qubit)) -- one program whose last sweep permutes."""
+    out = _split_segments(ops, nqubits, swap_runs)
+    if not fuse_perm:
+        return out
+    merged = []
+    for kind, payload in out:
+        if kind == "perm":
+            if merged and merged[-1][0] == "ops":
+                merged[-1] = ("opsperm", (merged[-1][1], payload))
+            else:
+                merged.append(("opsperm", ([], payload)))
+        else:
+            merged.append((kind, payload))
+    return merged
+
+
+def _split_segments(ops: Sequence[Op], nqubits: int, swap_runs: bool = True):
     out, cur = [], []
 
     def flush():

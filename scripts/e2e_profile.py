@@ -51,3 +51,40 @@ for step in range(3):
     t3 = sync()
     print(f"engine {step}: zero state {1e3 * (t1 - t0):.1f} ms, program {1e3 * (t2 - t1):.1f} ms, marginal {1e3 * (t3 - t2):.1f} ms", stats(), flush=True)
     del st, p
+
+# the pieces of the plugin's execute_circuit, host time per call (no synchronisation added: what the host waits for)
+import functools  # noqa: E402
+
+acc = {}
+
+
+def wrap(obj, name):
+    fn = getattr(obj, name)
+
+    @functools.wraps(fn)
+    def inner(*a, **k):
+        t = time.perf_counter()
+        try:
+            return fn(*a, **k)
+        finally:
+            acc[name] = acc.get(name, 0.0) + 1e3 * (time.perf_counter() - t)
+
+    setattr(obj, name, inner)
+
+
+for o, nm in ((be, "zero_state"), (be, "_compiled_circuit"), (eng, "run_program"), (eng, "_alloc"), (eng, "_reclaim"), (be, "calculate_probabilities"),
+              (be, "sample_shots")):
+    wrap(o, nm)
+for step in range(3):
+    acc.clear()
+    t0 = sync()
+    c = QFT(n)
+    c.add(gates.M(*range(10)))
+    res = c(nshots=1000)
+    th = time.perf_counter()
+    t1 = sync()
+    f = res.frequencies(binary=False)
+    t2 = sync()
+    print(f"detail {step}: host returns after {1e3 * (th - t0):.1f} ms, device done {1e3 * (t1 - t0):.1f} ms, frequencies {1e3 * (t2 - t1):.1f} ms; host ms per call:",
+          {k: round(v, 1) for k, v in acc.items()}, flush=True)
+    del c, res, f

@@ -123,3 +123,32 @@ def family_matrix(family, thetas, ntargets, is_diagonal=False):
         raise ValueError("family does not match")
     v = np.array(out[: count.value]).view(np.complex128)
     return v if is_diagonal else v.reshape(1 << ntargets, 1 << ntargets)
+
+
+def apply_program_permuted(state, nqubits, ops, dest_of_qubit, fuse=True, replay=False):
+    """``ops`` then the qubit permutation (qubit q -> dest_of_qubit[q]) through the emulated sweep path with the
+    permutation riding on the last sweep when the planner can fuse it -> (result, stats, fused)."""
+    from qibo_b200 import _lib
+    from qibo_b200.ops import pack_ops
+
+    lib = load()
+    state = np.ascontiguousarray(state).copy()
+    dst = np.full_like(state, np.nan)
+    dtype = _lib.QB_C128 if state.dtype == np.complex128 else _lib.QB_C64
+    arr, keep = pack_ops(ops)
+    stats = _lib.QbProgramStats()
+    fused = ctypes.c_int()
+    dest = (ctypes.c_int * nqubits)(*[int(d) for d in dest_of_qubit])
+    lib.emul_apply_program_permuted.restype = ctypes.c_int
+    lib.emul_apply_program_permuted.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.QbOp), ctypes.c_int,
+        ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(_lib.QbProgramStats), ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+    ]
+    rc = lib.emul_apply_program_permuted(
+        state.ctypes.data, dst.ctypes.data, nqubits, dtype, arr, len(ops), dest, 0 if fuse else _lib.QB_PROGRAM_NO_FUSE,
+        ctypes.byref(stats), ctypes.byref(fused), int(replay),
+    )
+    if rc != 0:
+        raise RuntimeError(lib.emul_last_error().decode())
+    del keep
+    return dst, stats, bool(fused.value)

@@ -20,13 +20,14 @@ constexpr uint32_t EMUL_THREADS = 256;  // the kernel's compute-thread count: sa
 // through run_pass<..., true>, which has no handler switch, and other pass kinds are not executed at all -- so a sweep
 // the planner flags stage_only by mistake gives a wrong state here, as it would on the GPU.
 template <typename C, bool SO>
-static void run_sweep(C* state, const char* blob) {
+static void run_sweep(C* state, const char* blob, C* dst = nullptr) {
   const SweepHeader& hdr = *reinterpret_cast<const SweepHeader*>(blob);
   const int T = (int)hdr.T, L = (int)hdr.L;
   const uint32_t nruns = 1u << (T - L), run = 1u << L;
   const PassHeader* passes = reinterpret_cast<const PassHeader*>(blob + hdr.passes_offset);
   const uint32_t* slot_table = reinterpret_cast<const uint32_t*>(blob + hdr.slots_offset);
-  std::vector<C> tile(size_t(1) << T);
+  std::vector<C> tile(size_t(1) << T), tile2(size_t(1) << T);  // tile2: where a permuting sweep's last pass writes (the
+                                                              // kernel writes in place behind a team barrier)
   std::vector<TileSlot> ts(hdr.nslots + 1);
   const uint32_t swz_on = hdr.swizzle ? 7u : 0u;
   const int GPT = sizeof(C) == 16 ? 1 : 2;  // both group counts the kernel variants use are exercised
@@ -48,17 +49,17 @@ static void run_sweep(C* state, const char* blob) {
     auto regtile = [&](const PassHeader& ph, uint32_t ctid) {
       if (GPT == 1) {
         switch (ph.R) {
-          case 1: run_pass<C, 1, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 2: run_pass<C, 2, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 3: run_pass<C, 3, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          default: run_pass<C, 4, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 1: run_pass<C, 1, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
+          case 2: run_pass<C, 2, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
+          case 3: run_pass<C, 3, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
+          default: run_pass<C, 4, 1, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
         }
       } else {
         switch (ph.R) {
-          case 1: run_pass<C, 1, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 2: run_pass<C, 2, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          case 3: run_pass<C, 3, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
-          default: run_pass<C, 4, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS); break;
+          case 1: run_pass<C, 1, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
+          case 2: run_pass<C, 2, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
+          case 3: run_pass<C, 3, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
+          default: run_pass<C, 4, 2, SO>(tile.data(), blob, ts.data(), ph, T, swz_on, ctid, EMUL_THREADS, tile2.data()); break;
         }
       }
     };
@@ -82,6 +83,16 @@ static void run_sweep(C* state, const char* blob) {
         for (uint32_t task = 0; task < ntasks; ++task) big_read<C>(tile.data(), op, payload, T, swz_on, task, accs[task]);
         for (uint32_t task = 0; task < ntasks; ++task) big_write<C>(tile.data(), op, swz_on, accs[task]);
       }
+    }
+    if (hdr.permuted) {
+      // the storer: destination tile base = every bit of the source base moved to its destination; the tile leaves in
+      // the destination layout (tensor-map order = ascending destination bits, swizzled when planned so)
+      uint64_t dbase = 0;
+      for (int b = 0; b < 64; ++b)
+        if ((hdr.other_mask >> b) & 1) dbase |= ((base >> b) & uint64_t(1)) << hdr.dst_bit[b];
+      const uint32_t dswz_on = hdr.dswizzle ? 7u : 0u;
+      for (uint32_t d = 0; d < (1u << T); ++d) dst[dbase + deposit(d, hdr.dtile_mask)] = tile2[swz<C>(d, dswz_on)];
+      continue;
     }
     for (uint32_t r = 0; r < nruns; ++r) {
       const uint64_t off = deposit(uint64_t(r) << L, hdr.tile_mask);
@@ -116,13 +127,54 @@ extern "C" int emul_apply_program(void* state, int nqubits, int dtype, const qb_
   return QB_OK;
 }
 
-static void run_plan(void* state, int dtype, Plan& plan) {
+static void run_plan(void* state, int dtype, Plan& plan, void* dst = nullptr) {
   for (auto& sd : plan.sweeps) {
     char* blob = plan.blob.data() + sd.blob_offset;
     const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);
-    if (dtype == QB_C128) so ? run_sweep<double2, true>((double2*)state, blob) : run_sweep<double2, false>((double2*)state, blob);
-    else so ? run_sweep<float2, true>((float2*)state, blob) : run_sweep<float2, false>((float2*)state, blob);
+    void* d = sd.permuted ? dst : nullptr;
+    if (dtype == QB_C128) so ? run_sweep<double2, true>((double2*)state, blob, (double2*)d) : run_sweep<double2, false>((double2*)state, blob, (double2*)d);
+    else so ? run_sweep<float2, true>((float2*)state, blob, (float2*)d) : run_sweep<float2, false>((float2*)state, blob, (float2*)d);
   }
+}
+
+// qb_apply_program_permuted in miniature: the ops, then dst[.. qubit dest_of_qubit[q] ..] = state[.. qubit q ..].  *fused = 1
+// when the permutation rode on the last sweep (else the plain plan ran and the permutation is done here index by index).
+extern "C" int emul_apply_program_permuted(void* state, void* dst, int nqubits, int dtype, const qb_op* ops, int nops,
+                                           const int* dest_of_qubit, int flags, qb_program_stats* stats, int* fused, int replay) {
+  std::vector<CanonOp> canon;
+  for (int i = 0; i < nops; ++i) {
+    CanonOp c;
+    if (!canonicalize(nqubits, ops[i].data, ops[i].is_diagonal != 0, ops[i].ntargets, ops[i].targets, ops[i].ncontrols,
+                      ops[i].controls, c, g_err))
+      return QB_ERR_INVALID;
+    canon.push_back(c);
+  }
+  PermSpec perm;
+  for (int q = 0; q < nqubits; ++q) perm.pi[nqubits - 1 - q] = nqubits - 1 - dest_of_qubit[q];
+  Plan plan;
+  const bool no_fuse = (flags & QB_PROGRAM_NO_FUSE) != 0;
+  if (!plan_program(nqubits, dtype, canon, no_fuse, plan, g_err, nullptr, &perm)) return QB_ERR_UNSUPPORTED;
+  if (replay) {  // emit the same program again on the kept schedule (qb_program_set_params with unchanged values)
+    Plan again;
+    if (!plan_program(nqubits, dtype, canon, no_fuse, again, g_err, &plan, &perm)) return QB_ERR_UNSUPPORTED;
+    if (again.perm_fused != plan.perm_fused || again.sweeps.size() != plan.sweeps.size()) {
+      g_err = "replay changed the plan";
+      return QB_ERR_UNSUPPORTED;
+    }
+    plan = again;
+  }
+  if (stats) fill_stats(plan, nqubits, dtype, nops, stats);
+  *fused = plan.perm_fused;
+  run_plan(state, dtype, plan, dst);
+  if (!plan.perm_fused) {
+    const size_t esz = dtype == QB_C128 ? 16 : 8;
+    for (uint64_t x = 0; x < (uint64_t(1) << nqubits); ++x) {
+      uint64_t y = 0;
+      for (int b = 0; b < nqubits; ++b) y |= ((x >> b) & uint64_t(1)) << perm.pi[b];
+      memcpy((char*)dst + y * esz, (const char*)state + x * esz, esz);
+    }
+  }
+  return QB_OK;
 }
 
 // qb_program_set_params in miniature: plan `ops_old`, then emit `ops_new` (same gate structure, new numbers) on the OLD

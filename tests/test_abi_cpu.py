@@ -49,9 +49,9 @@ def test_header_is_plain_c_and_links(tmp_path):
 
 
 def test_struct_layout_matches_header():
-    # qb_op: 2 + 6 + 32 + 2 int32 then a pointer; qb_program_stats: 4 int32, double, 2 float
+    # qb_op: 2 + 6 + 32 + 2 int32 then a pointer; qb_program_stats: 4 int32, double, float, 3 int32
     assert ctypes.sizeof(_lib.QbOp) == 4 * (2 + 6 + 32 + 2) + 8
-    assert ctypes.sizeof(_lib.QbProgramStats) == 32
+    assert ctypes.sizeof(_lib.QbProgramStats) == 40
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")

@@ -613,3 +613,63 @@ def _theta_of(op):
     if op.name == "CRZ":
         return 2 * np.angle(m[3, 3])
     raise KeyError(op.name)
+
+
+# ------------------------------------------------------------------------------------------ permuting sweeps
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("seed", range(4))
+def test_trailing_permutation_rides_on_last_sweep(eng, dtype, seed):
+    """qb_apply_program_permuted / qb_program_create_permuted + run: gates followed by a SWAP run, the permutation written
+    by the last sweep (out of place, destination tensor map) -- against the oracle; the two-launch form (K8) must agree
+    bit for bit; with and without a caller-provided second buffer."""
+    rng = np.random.default_rng(50 + seed)
+    n = int(rng.integers(14, 21))
+    psi = rand_state(n, seed, dtype)
+    keep = int(rng.integers(0, 4))
+    dests = [list(range(n - 1, -1, -1)), list(range(keep)) + list(range(n - 1, keep - 1, -1)), rng.permutation(n).tolist()]
+    from qibo_b200.engine import swaps_for_permutation
+
+    for dest in dests:
+        for ngates in (0, 30):
+            gops = random_zoo(n, ngates, seed) if ngates else []
+            ops = gops + swaps_for_permutation(dest)
+            if len(ops) - len(gops) < 3:
+                continue
+            ref = oracle_run(psi, ops, n)
+            st = eng.upload(psi)
+            stats = eng.apply_program(st, n, ops)
+            assert np.abs(st.numpy() - ref).max() < tol(dtype), (n, dest, ngates)
+            fused = stats.nperm_fused
+            # the two-launch form
+            eng.fuse_permutations = False
+            try:
+                st2 = eng.upload(psi)
+                stats2 = eng.apply_program(st2, n, ops)
+            finally:
+                eng.fuse_permutations = True
+            assert stats2.nperm_fused == 0
+            if fused:
+                assert stats.nperm == 0 and stats2.nperm == 1 and stats.nsweeps <= stats2.nsweeps
+            assert np.abs(st2.numpy() - ref).max() < tol(dtype)
+            # compiled, twice, ping-ponging between two caller-owned buffers
+            prog = eng.compile(n, dtype, ops)
+            a, b = eng.upload(psi), eng.empty((1 << n,), dtype)
+            eng.run_program(prog, a, alt=b)
+            assert np.array_equal(a.numpy(), st.numpy())
+            b.tensor.copy_(eng.upload(psi).tensor)
+            eng.run_program(prog, b, alt=a)
+            assert np.array_equal(b.numpy(), st.numpy())
+            prog.close()
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_qft_with_fused_reversal_vs_oracle(eng, dtype):
+    from qibo_b200 import circuits
+
+    for n in (13, 14, 15, 18, 21):
+        psi = rand_state(n, n, dtype)
+        ref = orc.run_ops(psi, orc.qft_ops(n), n, dtype=dtype)
+        st = eng.upload(psi)
+        stats = eng.apply_program(st, n, circuits.qft(n))
+        assert stats.nperm_fused == (1 if n > (12 if dtype == "complex128" else 13) else 0)
+        assert np.abs(st.numpy() - ref).max() < tol(dtype)

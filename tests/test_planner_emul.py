@@ -273,3 +273,77 @@ def test_schedule_replay_with_new_parameters(case, dtype):
     new0 = build(new_thetas)
     out, replayed = emul.apply_program_replay(psi, n, old, new0)
     assert np.abs(out - oracle_run(psi, new0, n)).max() < tol(dtype)
+
+
+def _permuted_reference(state, n, dest):
+    return np.moveaxis(state.reshape(n * (2,)), list(range(n)), list(dest)).reshape(-1)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [13, 14, 16, 17])
+def test_qft_bit_reversal_rides_on_last_sweep(n, dtype):
+    """Permuting sweep (qb_apply_program_permuted): the QFT's closing SWAP run written by the last sweep, out of place,
+    through the destination layout -- same state as gates + SWAPs in the oracle; also when the program is emitted again
+    on the kept schedule (qb_program_set_params)."""
+    from qibo_b200.engine import split_segments
+
+    ops = ops_from_named(orc.qft_ops(n))
+    segs = split_segments(ops, n, True, True)
+    assert [k for k, _ in segs] == ["opsperm"]
+    gops, dest = segs[0][1]
+    psi = rand_state(n, 300 + n, dtype)
+    ref = orc.run_ops(psi, orc.qft_ops(n), n, dtype=dtype)
+    tile_bits = 12 if dtype == "complex128" else 13
+    for replay in (False, True):
+        out, stats, fused = emul.apply_program_permuted(psi, n, gops, dest, replay=replay)
+        assert fused == (n > tile_bits)
+        assert not np.isnan(out).any()  # every destination amplitude written
+        assert np.abs(out - ref).max() < tol(dtype)
+        if fused:
+            assert stats.perm_fused == 1 and stats.nstage_sweeps == stats.nsweeps or dtype == "complex64"
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_programs_with_trailing_permutation(dtype, seed):
+    """Zoo programs (dense blocks, controls, fans, swaps) followed by random permutations: fused when the geometry allows,
+    otherwise the plain plan + permutation -- the result is the same either way; the pure permutation (no gate) too."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(14, 17))
+    psi = rand_state(n, seed, dtype)
+    perms = [list(range(n - 1, -1, -1)), rng.permutation(n).tolist()]
+    # partial reversals (what a rank of a sharded QFT ends with: the leading qubits stay)
+    keep = int(rng.integers(1, 4))
+    perms.append(list(range(keep)) + list(range(n - 1, keep - 1, -1)))
+    nfused = 0
+    for dest in perms:
+        for ngates in (0, 25):
+            ops = random_zoo(n, ngates, seed) if ngates else []
+            ref = _permuted_reference(oracle_run(psi, ops, n) if ops else psi, n, dest)
+            out, stats, fused = emul.apply_program_permuted(psi, n, ops, dest)
+            nfused += int(fused)
+            assert not np.isnan(out).any()
+            assert np.abs(out - ref).max() < tol(dtype), (n, dest, ngates, fused)
+    assert nfused >= 2
+
+
+def test_sharded_qft_tail_fuses_into_one_sweep():
+    """The last local segment of every rank of a sharded QFT -- three stages on the leading local qubits, then the reversal
+    of the others -- is ONE permuting sweep (tile = 5 + 4 row bits + the three stage bits)."""
+    from qibo_b200.engine import split_segments
+
+    n = 16
+    named = []
+    for q in range(3):
+        named.append(("H", (q,), ()))
+        for j in range(q + 1, 3):
+            named.append(("CU1", (j, q), (np.pi / 2 ** (j - q),)))
+    named += [("SWAP", (3 + q, n - 1 - q), ()) for q in range((n - 3) // 2)]
+    ops = ops_from_named(named)
+    segs = split_segments(ops, n, True, True)
+    assert [k for k, _ in segs] == ["opsperm"]
+    gops, dest = segs[0][1]
+    psi = rand_state(n, 5, "complex128")
+    out, stats, fused = emul.apply_program_permuted(psi, n, gops, dest)
+    assert fused and stats.nsweeps == 1
+    assert np.abs(out - orc.run_ops(psi, named, n)).max() < 1e-12
