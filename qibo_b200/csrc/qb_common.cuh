@@ -82,6 +82,25 @@ QB_HD double2 creal_fma(double k, double2 v, double2 c) { double2 d; d.x = fma(k
 QB_HD double2 creal_mul(double k, double2 v) { double2 d; d.x = k * v.x; d.y = k * v.y; return d; }
 QB_HD double2 creal_add(double2 a, double2 b) { double2 d; d.x = a.x + b.x; d.y = a.y + b.y; return d; }
 
+// v = -v when `bit` (0/1) is set: one XOR per component on the sign bits (integer pipe; the FP pipes stay free for the gates)
+#if defined(__CUDA_ARCH__)
+QB_D void flip_sign(float2& v, uint32_t bit) {
+  const uint32_t m = bit << 31;
+  v.x = __uint_as_float(__float_as_uint(v.x) ^ m);
+  v.y = __uint_as_float(__float_as_uint(v.y) ^ m);
+}
+QB_D void flip_sign(double2& v, uint32_t bit) {
+  const int m = (int)(bit << 31);
+  v.x = __hiloint2double(__double2hiint(v.x) ^ m, __double2loint(v.x));
+  v.y = __hiloint2double(__double2hiint(v.y) ^ m, __double2loint(v.y));
+}
+QB_D uint32_t popc32(uint32_t x) { return (uint32_t)__popc(x); }
+#else
+QB_HD void flip_sign(float2& v, uint32_t bit) { if (bit) { v.x = -v.x; v.y = -v.y; } }
+QB_HD void flip_sign(double2& v, uint32_t bit) { if (bit) { v.x = -v.x; v.y = -v.y; } }
+QB_HD uint32_t popc32(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+#endif
+
 // ---- bit utilities --------------------------------------------------------------------------------
 // insert a zero bit at position p (bits >= p move up by one)
 QB_HD uint64_t insert_zero(uint64_t x, int p) {

@@ -251,6 +251,29 @@ template <typename C, int R> QB_HD void mu_diagk(C* v, const MicroOp& mo, const 
   }
 }
 
+// a set of +-1 diagonal gates (MH_SIGNS, qb_planner.hpp): sign of register index j = bit j of the mask built here
+template <typename C, int R> QB_HD void mu_signs(C* v, uint32_t t0, uint32_t g16, uint32_t zmask, const uint16_t* sp, uint32_t aux) {
+  constexpr int D = 1 << R;
+  uint32_t m = g16;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    uint32_t mr = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if ((j >> r) & 1) mr |= 1u << j;
+    if ((popc32(t0 & sp[r]) ^ (aux >> r)) & 1u) m ^= mr;
+  }
+  uint32_t c = popc32(t0 & (zmask & 0xFFFFu)) ^ (aux >> 4) ^ (zmask >> 31);
+  const uint32_t np = sp[4];
+  for (uint32_t k = 0; k < np; ++k) {
+    const uint32_t pm = sp[5 + k];
+    c ^= (t0 & pm) == pm ? 1u : 0u;
+  }
+  if (c & 1u) m = ~m;
+#pragma unroll
+  for (int j = 0; j < D; ++j) flip_sign(v[j], (m >> j) & 1u);
+}
+
 struct alignas(16) MicroHot { uint32_t w0, creg, cthr, payload; };  // first 16 bytes of MicroOp
 
 // one fused stage: 2x2 gate on register bit I ((a+b, a-b) or a real matrix), then the fan controlled by bit I
@@ -438,6 +461,13 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
       case MH_PHASE_M: { const C ph = inl[0]; QB_EACH((mu_phase<C, R, R + 1>(v[u], ph, hot.creg))) } break;
       QB_CASE_PAIRS(MH_PHASE_C2, { const C ph = inl[0]; QB_EACH((mu_phase2<C, R, HI, LO>(v[u], ph))) })
       case MH_DIAGK: QB_EACH((mu_diagk<C, R>(v[u], mo, blob, ts[slot].aux, t0[u]))) break;
+      case MH_SIGNS: {  // (creg / cthr carry the sign table and the thread-bit mask: `run` does not apply)
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(mo.inl);
+        const uint32_t aux = slot != MU_NO_SLOT ? ts[slot].aux : 0u;
+#pragma unroll
+        for (int u = 0; u < GPT; ++u)
+          if (valid[u]) mu_signs<C, R>(v[u], t0[u], hot.creg, hot.cthr, sp, aux);
+      } break;
       case MH_REAL_LAYER: {
         const C* m = reinterpret_cast<const C*>(blob + hot.payload);
         const uint32_t present = mo.k;
@@ -530,6 +560,15 @@ template <typename C> QB_HD void micro_prephase(const MicroOp& mo, const char* b
       tab += (1u << nb);
     }
     *reinterpret_cast<C*>(ts.ext) = s;
+  } else if (mo.type == MU_SIGNS) {
+    // parities of the bits outside the tile: bit r = over the partners of register bit r, bit 4 = over the lone terms
+    uint32_t aux = 0;
+    for (int e = 0; e < 5; ++e) {
+      uint64_t x = base & mo.ext_mask[e];
+      x ^= x >> 32;
+      aux |= (popc32((uint32_t)x) & 1u) << e;
+    }
+    ts.aux = aux;
   } else if (mo.type == MU_DIAGK) {
     const int k = (int)mo.k;
     uint32_t aux = 0;

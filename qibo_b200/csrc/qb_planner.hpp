@@ -13,7 +13,9 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
@@ -29,7 +31,7 @@ namespace qb {
 // bits": every thread owns groups of 2^R amplitudes that differ only in those bits, loads them once,
 // applies the pass's whole list of MICRO-OPS in registers and stores them once.  A BIG pass applies one
 // dense gate on 3..6 targets (threads share a group, inputs re-read from shared memory).
-enum MicroType { MU_DENSE1 = 1, MU_DENSE2 = 2, MU_SWAP = 3, MU_FAN = 4, MU_DIAGK = 5, MU_PHASE = 6 };
+enum MicroType { MU_DENSE1 = 1, MU_DENSE2 = 2, MU_SWAP = 3, MU_FAN = 4, MU_DIAGK = 5, MU_PHASE = 6, MU_SIGNS = 7 };
 enum PassKind { PASS_REGTILE = 1, PASS_BIG = 2 };
 
 // One handler code per micro-op: (operation, register bit(s), control mode) flattened so that the kernel needs a
@@ -57,7 +59,11 @@ enum MicroHandler {
   MH_PHASE_C2 = 55,    // +P  lone phase whose two register-bit controls are the pair (hi, lo): CZ / CU1 with both qubits
                        //  among the register bits -- compile-time masks (ncu, round 2: the run-time mask form MH_PHASE_M
                        //  tests every register index, ~3 instructions per amplitude instead of 1/4)
-  MH_COUNT = 61,
+  MH_SIGNS = 61,       //     a SET of +-1 diagonal gates (CZ, Z and products of them) merged into one dispatch: the sign of
+                       //     register index j is bit j of  G16 ^ sum_r a_r MASK_r ^ c  with a_r / c parities of the thread's
+                       //     tile bits (and, through the slot, of the bits outside the tile) -- round 2: a lone CZ costs as
+                       //     much as an RY in this kernel (all of it dispatch), the ansatz has as many CZs as RYs
+  MH_COUNT = 62,
 };
 
 constexpr int SWEEP_MAX_SLOTS = 48;        // ops per sweep that need per-tile set-up (controls / factors from outside the tile)
@@ -188,7 +194,12 @@ struct PlanOp {
   cd scalar = cd(1.0, 0.0);
   std::vector<int> src;         // indices of the original ops merged into this one
   int special = 0;              // 1: apply as (a+b, a-b); the scalar of the gate rides in another gate of the sweep
+  // CK_SIGNS (made inside emit_regtile_pass from runs of +-1 diagonal gates): x -> (-1)^(neg + sum over terms of x_a [x_b])
+  std::vector<std::pair<int, int>> sign_terms;  // (bit a, bit b) or (bit a, -1)
+  int sign_neg = 0;
 };
+constexpr int CK_SIGNS = 100;
+constexpr int SIGNS_MAX_PAIRS = 27;  // thread-level pairs one MH_SIGNS op can carry inline
 
 struct SweepDesc {
   int permuted = 0;          // the sweep writes its tiles, permuted, into ANOTHER buffer (launch_sweep needs `dst`)
@@ -705,7 +716,156 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
   std::vector<MicroOp> mops;
   const int pass_index = (int)sb.passes.size();
   const PlanOp* prev_op = nullptr;
-  for (const PlanOp* pp : ops) {
+  // ---- runs of +-1 diagonal gates (CZ, Z, CZ fans) -> one CK_SIGNS op each.  Diagonal gates commute with each other and
+  // with every gate that mixes none of their bits, so a sign gate may wait (move later) until a gate mixes one of the
+  // bits it touches; everything collected until then is applied by ONE micro-op.
+  std::deque<PlanOp> synth;
+  std::vector<const PlanOp*> merged_ops;
+  // OPT-IN (QB_SIGNS=1): measured on B200 (profiles/r2o_*), the 32-qubit ansatz runs 1.88 s with it against 1.75 s without --
+  // the sixteen sign flips per register group cost more issue slots than the two or three lone-phase dispatches they replace
+  // (a lone CZ flips four); kept for circuits with long runs of +-1 gates per pass.
+  if (env_int("QB_SIGNS", 0) && R == 4) {
+    auto loc = [&](int pos) {  // 0 = register bit, 1 = thread (tile, non-register) bit, 2 = outside the tile
+      if (!((sb.tile_mask >> pos) & 1)) return 2;
+      return rbit_of_local[sb.local_of_pos[pos]] >= 0 ? 0 : 1;
+    };
+    auto is_pm1 = [](cd v) { return v == cd(1.0, 0.0) || v == cd(-1.0, 0.0); };
+    // terms of a +-1 phase op, false when it is not one (or has a term MH_SIGNS cannot evaluate)
+    auto sign_terms_of = [&](const PlanOp& p, std::vector<std::pair<int, int>>& terms, int& neg) {
+      terms.clear();
+      neg = 0;
+      if (p.kind != CK_PHASE || p.cpos.size() > 1 || !is_pm1(p.scalar)) return false;
+      for (auto& kv : p.fan)
+        if (!is_pm1(kv.second.first) || !is_pm1(kv.second.second)) return false;
+      const int a = p.cpos.empty() ? -1 : p.cpos[0];
+      int toggles_a = p.scalar.real() < 0 ? 1 : 0;  // factors on the whole slice x_a = 1 (or on everything when a < 0)
+      for (auto& kv : p.fan) {
+        const bool f0 = kv.second.first.real() < 0, f1 = kv.second.second.real() < 0;
+        if (f0) ++toggles_a;
+        if (f0 != f1) terms.push_back(a < 0 ? std::make_pair(kv.first, -1) : std::make_pair(a, kv.first));
+      }
+      if (toggles_a & 1) {
+        if (a < 0) neg = 1;
+        else terms.push_back({a, -1});
+      }
+      for (auto& t : terms) {
+        if (t.second < 0) continue;
+        const int la_ = loc(t.first), lb_ = loc(t.second);
+        if ((la_ == 2 && lb_ != 0) || (lb_ == 2 && la_ != 0)) return false;  // thread x outside, outside x outside
+      }
+      return true;
+    };
+    std::vector<const PlanOp*> members;
+    std::vector<std::pair<int, int>> acc_terms;
+    int acc_neg = 0, acc_thread_pairs = 0;
+    uint64_t support = 0;
+    auto flush = [&]() {
+      if (members.size() >= 2) {
+        PlanOp sp;
+        sp.kind = CK_SIGNS;
+        sp.sign_terms = acc_terms;
+        sp.sign_neg = acc_neg;
+        for (const PlanOp* m_ : members) sp.src.insert(sp.src.end(), m_->src.begin(), m_->src.end());
+        synth.push_back(std::move(sp));
+        merged_ops.push_back(&synth.back());
+      } else {
+        for (const PlanOp* m_ : members) merged_ops.push_back(m_);
+      }
+      members.clear();
+      acc_terms.clear();
+      acc_neg = 0;
+      acc_thread_pairs = 0;
+      support = 0;
+    };
+    std::vector<std::pair<int, int>> terms;
+    for (const PlanOp* pp : ops) {
+      int neg = 0;
+      if (sign_terms_of(*pp, terms, neg)) {
+        int tp = 0;
+        for (auto& t : terms)
+          if (t.second >= 0 && loc(t.first) == 1 && loc(t.second) == 1) ++tp;
+        if (acc_thread_pairs + tp > SIGNS_MAX_PAIRS) flush();
+        members.push_back(pp);
+        acc_terms.insert(acc_terms.end(), terms.begin(), terms.end());
+        acc_neg ^= neg;
+        acc_thread_pairs += tp;
+        for (auto& t : terms) support |= (uint64_t(1) << t.first) | (t.second >= 0 ? uint64_t(1) << t.second : 0);
+        continue;
+      }
+      uint64_t x = 0;
+      if (pp->kind == CK_DENSE || pp->kind == CK_SWAP)
+        for (int t : pp->tpos) x |= uint64_t(1) << t;
+      if (x & support) flush();
+      merged_ops.push_back(pp);
+    }
+    flush();
+  } else {
+    merged_ops = ops;
+  }
+  for (const PlanOp* pp : merged_ops) {
+    if (pp->kind == CK_SIGNS) {
+      // G16: sign table over the register index; P[r]: thread bits whose value toggles the sign of register bit r's half;
+      // zmask: thread bits that toggle everything; pairs: thread-bit pairs; E[r] / E[4]: the same from outside the tile
+      MicroOp m;
+      memset(&m, 0, sizeof(m));
+      memset(m.tbit, 0xFF, sizeof(m.tbit));
+      memset(m.rsel, 0xFF, sizeof(m.rsel));
+      m.R = (uint16_t)R;
+      m.slot = (uint16_t)MU_NO_SLOT;
+      m.type = MU_SIGNS;
+      m.handler = MH_SIGNS;
+      uint32_t g16 = 0, zmask = 0;
+      uint16_t P[4] = {0, 0, 0, 0};
+      std::vector<uint16_t> pairs;
+      auto regmask = [&](int r) {
+        uint32_t mk = 0;
+        for (int j = 0; j < (1 << R); ++j)
+          if ((j >> r) & 1) mk |= 1u << j;
+        return mk;
+      };
+      auto in_tile = [&](int pos) { return ((sb.tile_mask >> pos) & 1) != 0; };
+      auto rb_of = [&](int pos) { return in_tile(pos) ? rbit_of_local[sb.local_of_pos[pos]] : -1; };  // -1: not a register bit
+      for (auto t : pp->sign_terms) {
+        int a = t.first, b = t.second;
+        if (b < 0) {
+          if (!in_tile(a)) m.ext_mask[4] ^= uint64_t(1) << a;
+          else if (rb_of(a) >= 0) g16 ^= regmask(rb_of(a));
+          else zmask ^= 1u << sb.local_of_pos[a];
+          continue;
+        }
+        if (rb_of(a) < 0 && rb_of(b) >= 0) std::swap(a, b);  // a: the register bit when there is one
+        if (rb_of(a) >= 0) {
+          const int r = rb_of(a);
+          if (!in_tile(b)) m.ext_mask[r] ^= uint64_t(1) << b;
+          else if (rb_of(b) >= 0) g16 ^= regmask(r) & regmask(rb_of(b));
+          else P[r] ^= (uint16_t)(1u << sb.local_of_pos[b]);
+        } else {
+          const uint16_t pm = (uint16_t)((1u << sb.local_of_pos[a]) | (1u << sb.local_of_pos[b]));
+          auto it = std::find(pairs.begin(), pairs.end(), pm);
+          if (it != pairs.end()) pairs.erase(it);  // the same pair twice cancels
+          else pairs.push_back(pm);
+        }
+      }
+      if ((int)pairs.size() > SIGNS_MAX_PAIRS) { err = "internal: too many thread-level pairs in a sign set"; return false; }
+      m.creg = g16;
+      m.cthr = zmask | (pp->sign_neg ? 0x80000000u : 0u);
+      uint16_t* inl16 = reinterpret_cast<uint16_t*>(m.inl);
+      for (int r = 0; r < 4; ++r) inl16[r] = P[r];
+      inl16[4] = (uint16_t)pairs.size();
+      for (size_t k = 0; k < pairs.size(); ++k) inl16[5 + k] = pairs[k];
+      bool needs_slot = false;
+      for (int e = 0; e < 5; ++e)
+        if (m.ext_mask[e]) needs_slot = true;
+      if (needs_slot) {
+        m.slot = (uint16_t)sb.slots.size();
+        sb.slots.push_back({pass_index, (int)mops.size()});
+      }
+      sb.payload_owner.push_back({pass_index, (int)mops.size()});
+      sb.payloads.push_back({});
+      mops.push_back(m);
+      prev_op = pp;
+      continue;
+    }
     // A two-qubit controlled phase right after an uncontrolled one-qubit gate on one of its qubits (the tail of a QFT:
     // H(q) CU1(q, q+1)) is re-rooted as a one-entry fan controlled by that qubit, so that the pair fuses into a stage op
     // and the pass stays a straight-line stage pass.  (A pure phase is symmetric in its qubits.)

@@ -347,3 +347,47 @@ def test_sharded_qft_tail_fuses_into_one_sweep():
     out, stats, fused = emul.apply_program_permuted(psi, n, gops, dest)
     assert fused and stats.nsweeps == 1
     assert np.abs(out - orc.run_ops(psi, named, n)).max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("seed", range(8))
+def test_merged_sign_gates(dtype, seed, low_bits, monkeypatch):
+    """MH_SIGNS (opt-in, QB_SIGNS=1): runs of +-1 diagonal gates (CZ, Z, CZ fans sharing a control, CCZ left alone) between
+    layers of one-qubit gates become one micro-op per pass; register x register, register x thread, register x
+    outside-the-tile and thread x thread pairs, lone Z terms on every kind of bit, a global -1."""
+    monkeypatch.setenv("QB_SIGNS", "1")
+    rng = np.random.default_rng(4000 + seed)
+    n = int(rng.integers(14, 18))
+    named = []
+    for layer in range(int(rng.integers(2, 5))):
+        for q in range(n):
+            r = rng.random()
+            if r < 0.6:
+                named.append(("RY", (q,), (float(rng.uniform(0, 6)),)))
+            elif r < 0.75:
+                named.append(("H", (q,), ()))
+        style = int(rng.integers(0, 3))
+        if style == 0:  # the ansatz's ladder
+            for q in range(0, n - 1, 2):
+                named.append(("CZ", (q, q + 1), ()))
+            for q in range(1, n - 1, 2):
+                named.append(("CZ", (q, q + 1), ()))
+            named.append(("CZ", (0, n - 1), ()))
+        elif style == 1:  # random pairs, some twice (they cancel), Z gates, a global sign through Z X Z X
+            for _ in range(int(rng.integers(5, 40))):
+                a, b = rng.permutation(n)[:2].tolist()
+                named.append(("CZ", (a, b), ()))
+                if rng.random() < 0.2:
+                    named.append(("Z", (int(rng.integers(0, n)),), ()))
+        else:  # fans: one control, many partners; three-qubit phases stay separate ops
+            c = int(rng.integers(0, n))
+            for q in rng.permutation(n)[: int(rng.integers(2, n))].tolist():
+                if q != c:
+                    named.append(("CZ", (c, q), ()))
+            a, b, c3 = rng.permutation(n)[:3].tolist()
+            named.append(("CCZ", (a, b, c3), ()))
+            named.append(("CU1", (a, b), (float(rng.uniform(0.1, 3)),)))
+    psi = rand_state(n, seed, dtype)
+    ref = orc.run_ops(psi, named, n, dtype=dtype)
+    out, stats = emul.apply_program(psi, n, ops_from_named(named))
+    assert np.abs(out - ref).max() < tol(dtype)
