@@ -1603,6 +1603,25 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
           for (auto& kv : p.fan) sd_[q] |= uint64_t(1) << kv.first;
         if (p.kind == CK_PHASE || p.kind == CK_DIAG) ++sd.ndiag;
       }
+      // balanced passes: when every tile bit is mixed by exactly one gate of the sweep (QFT-like: the passes partition the
+      // stage bits), spread the bits evenly over the minimal number of passes -- 3 + 3 instead of 4 + 2 stages.  A pass whose
+      // register bits are the FOUR lowest tile bits leaves only two conflict-free lane bits below the swizzle range
+      // (ncu, permuting sweep of QFT(31): 32 % of the shared-memory wavefronts were bank conflicts with 4 + 2)
+      int reg_cap = R;
+      if (!no_fuse && !env_int("QB_NO_BALANCED_PASSES", 0)) {
+        uint64_t mixed = 0;
+        size_t nmix = 0;
+        for (size_t q = 0; q < M; ++q)
+          if (sx[q]) {
+            mixed |= sx[q];
+            ++nmix;
+          }
+        const int nbits = (int)__builtin_popcountll(mixed);
+        if (nbits > R && nmix == (size_t)nbits) {
+          const int npass = (nbits + R - 1) / R;
+          reg_cap = (nbits + npass - 1) / npass;
+        }
+      }
       std::vector<char> placed(M, 0);
       size_t nplaced = 0, head = 0;
       while (nplaced < M) {
@@ -1628,7 +1647,7 @@ inline bool build_plan(int n, int dtype, const std::vector<PlanOp>& pops, bool n
             if (p.kind == CK_DENSE || p.kind == CK_SWAP)
               for (int t : p.tpos) need |= 1u << sb.local_of_pos[t];
             if (__builtin_popcount(need) > R) { err = "internal: gate needs more register bits than a pass has"; return SW_FAIL; }
-            if (__builtin_popcount(cur_r | need) > R) {
+            if (__builtin_popcount(cur_r | need) > std::max(reg_cap, (int)__builtin_popcount(need))) {
               ok = false;
             } else {
               cur_r |= need;
