@@ -119,6 +119,9 @@ typedef struct {
 
 #define QB_PROGRAM_TIME 1      /* bracket with CUDA events, synchronise, fill elapsed_ms */
 #define QB_PROGRAM_NO_FUSE 2   /* one sweep per gate (gate-by-gate accounting)           */
+#define QB_PROGRAM_INPUT_ZERO 8 /* qb_apply_program* / qb_program_run*: the input is |0...0> (zero_state, abstract.py:2243-2273) and `state` is
+                                  UNINITIALISED memory: the first sweep makes its tiles instead of reading them, so the 2^n-amplitude fill
+                                  and one read pass disappear (a program without a sweep fills `state` first) */
 #define QB_PROGRAM_PERM_FUSED_ONLY 4 /* *_permuted calls: QB_ERR_UNSUPPORTED (nothing launched) when the permutation cannot ride on a sweep */
 int qb_apply_program(qb_handle h, void* state, int nqubits, int dtype, const qb_op* ops, int nops, int flags,
                      qb_program_stats* stats /* may be NULL */);

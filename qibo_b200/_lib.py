@@ -15,7 +15,7 @@ QB_C64, QB_C128 = 0, 1
 QB_F32, QB_F64 = 0, 1
 QB_OK, QB_ERR_INVALID, QB_ERR_OOM, QB_ERR_CUDA, QB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 QB_MAX_OP_TARGETS, QB_MAX_OP_CONTROLS = 6, 32
-QB_PROGRAM_TIME, QB_PROGRAM_NO_FUSE, QB_PROGRAM_PERM_FUSED_ONLY = 1, 2, 4
+QB_PROGRAM_TIME, QB_PROGRAM_NO_FUSE, QB_PROGRAM_PERM_FUSED_ONLY, QB_PROGRAM_INPUT_ZERO = 1, 2, 4, 8
 QB_SCAN_EXACT, QB_SCAN_PARALLEL = 0, 1
 
 

@@ -19,6 +19,7 @@ States returned to Qibo are :class:`qibo_b200.array.DeviceArray` objects (GPU re
 inside).  This module imports qibo; everything below it (engine, ops, C ABI) does not.
 """
 
+import os
 from collections import Counter
 
 import numpy as np
@@ -58,11 +59,13 @@ class B200Backend(NumpyBackend):
         self._engines = {}
         # Circuit objects keep their compiled program between executions (parameter slots, _compiled_circuit)
         self.compile_circuits = True
+        # execute_circuit without an initial state: no 2^n-amplitude fill, the first sweep of the compiled program makes the
+        # |0...0> tiles (QB_PROGRAM_INPUT_ZERO)
+        self.lazy_zero_state = os.environ.get("QB_NO_LAZY_ZERO", "0") in ("", "0")
         index = 0
         if device is not None:
             index = self._parse_device(device)
         elif torch.distributed.is_available() and torch.distributed.is_initialized():
-            import os
 
             index = int(os.environ.get("LOCAL_RANK", 0))
         self.device = f"/GPU:{index}"
@@ -387,8 +390,19 @@ class B200Backend(NumpyBackend):
         nqubits = circuit.nqubits
         density_matrix = circuit.density_matrix
         self.engine_gpu.reclaim_before((16 if self.dtype != "complex64" else 8) << (2 * nqubits if density_matrix else nqubits))
+        lazy_zero = False
         if initial_state is None:
-            state = self.zero_state(nqubits, density_matrix=density_matrix)
+            if self.compile_circuits and self.lazy_zero_state:
+                # zero_state (abstract.py:2243-2273) without the fill: the compiled program's first sweep makes the |0...0>
+                # tiles itself (QB_PROGRAM_INPUT_ZERO); written out below if the queue takes the general path after all
+                self._validate_nqubits(nqubits, density_matrix=density_matrix)
+                flat_n = 2 * nqubits if density_matrix else nqubits
+                state = self.engine_gpu.uninitialised_state(flat_n, self._state_dtype(None))
+                if density_matrix:
+                    state = state.reshape(2**nqubits, 2**nqubits)
+                lazy_zero = True
+            else:
+                state = self.zero_state(nqubits, density_matrix=density_matrix)
         else:
             # the caller's array is never clobbered (SURVEY 8b ownership): device inputs are cloned
             state = self._to_device(initial_state)
@@ -397,9 +411,12 @@ class B200Backend(NumpyBackend):
         program = None
         if self.compile_circuits and str(state.dtype) in ("complex64", "complex128"):
             program = self._compiled_circuit(circuit, nqubits, density_matrix, state.dtype)
+        if lazy_zero and program is None:
+            self.engine_gpu._write_zero_state(state.reshape(-1) if density_matrix else state, 2 * nqubits if density_matrix else nqubits)
+            lazy_zero = False
         if program is not None:
             flat = state.reshape(-1) if density_matrix else state
-            self.engine_gpu.run_program(program, flat)
+            self.engine_gpu.run_program(program, flat, input_zero=lazy_zero)
             if flat is not state and flat.tensor.data_ptr() != state.tensor.data_ptr():
                 state.tensor = flat.tensor.reshape(state.shape)
             for gate in circuit.queue:

@@ -229,12 +229,18 @@ static int grid_for(uint64_t count, int threads, int sm_count, int waves = 16) {
   return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
+static int set_basis_locked(qb_context* h, void* state, int nqubits, int dtype, uint64_t index);
+
 int qb_state_set_basis(qb_handle h, void* state, int nqubits, int dtype, uint64_t index) {
   if (!h || !valid_state_args(state, nqubits, dtype)) return fail(QB_ERR_INVALID, "bad state arguments");
-  uint64_t count = uint64_t(1) << nqubits;
-  if (index >= count) return fail(QB_ERR_INVALID, "basis index out of range");
+  if (index >= (uint64_t(1) << nqubits)) return fail(QB_ERR_INVALID, "basis index out of range");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard guard(h->device);
+  return set_basis_locked(h, state, nqubits, dtype, index);
+}
+
+static int set_basis_locked(qb_context* h, void* state, int nqubits, int dtype, uint64_t index) {
+  uint64_t count = uint64_t(1) << nqubits;
   int grid = grid_for(count, 256, h->sm_count);
   if (dtype == QB_C128)
     k6_fill<double2><<<grid, 256, 0, h->stream>>>((double2*)state, count, cmake<double2>(0, 0), index, 1);
@@ -506,9 +512,13 @@ static const PermSpec* fusable(const PermSpec* perm) { return perm && tma_encode
 
 // the sweeps of a plan, then -- when a permutation was asked for and does not ride on the last sweep -- K8 into `dst`
 static int launch_plan(qb_context* h, void* state, void* dst, int nqubits, int dtype, const Plan& plan, const char* prog_dev,
-                       const PermSpec* perm) {
+                       const PermSpec* perm, bool input_zero = false) {
+  if (input_zero && plan.sweeps.empty()) {  // nothing will make the state on the way: write it
+    const int rc = set_basis_locked(h, state, nqubits, dtype, 0);
+    if (rc != QB_OK) return rc;
+  }
   for (size_t s = 0; s < plan.sweeps.size(); ++s) {
-    const int rc = launch_sweep(h->stream, h->sm_count, state, nqubits, dtype, plan.sweeps[s], prog_dev, dst);
+    const int rc = launch_sweep(h->stream, h->sm_count, state, nqubits, dtype, plan.sweeps[s], prog_dev, dst, input_zero && s == 0);
     if (rc != QB_OK) {
       const std::string what = cudaGetErrorString(cudaGetLastError());
       return fail(rc, "sweep launch failed: " + what + " [" + sweep_resources(dtype) + "]");
@@ -576,6 +586,10 @@ static int apply_program_impl(qb_handle h, void* state, void* dst, int nqubits, 
     // apply the queue gate by gate
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
+    if (flags & QB_PROGRAM_INPUT_ZERO) {
+      rc = set_basis_locked(h, state, nqubits, dtype, 0);
+      if (rc != QB_OK) return rc;
+    }
     if (stats) {
       memset(stats, 0, sizeof(*stats));
       stats->nops = nops;
@@ -623,7 +637,7 @@ static int apply_program_impl(qb_handle h, void* state, void* dst, int nqubits, 
     QB_CUDA(cudaMemcpyAsync(h->prog_dev, h->prog_host, need, cudaMemcpyHostToDevice, h->stream));
   }
   if (flags & QB_PROGRAM_TIME) QB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  rc = launch_plan(h, state, dst, nqubits, dtype, plan, (const char*)h->prog_dev, perm);
+  rc = launch_plan(h, state, dst, nqubits, dtype, plan, (const char*)h->prog_dev, perm, (flags & QB_PROGRAM_INPUT_ZERO) != 0);
   if (rc != QB_OK) return rc;
   QB_CUDA(cudaEventRecord(h->prog_done, h->stream));
   if (flags & QB_PROGRAM_TIME) {
@@ -756,6 +770,10 @@ static int program_run_impl(qb_handle h, qb_program p, void* state, void* dst, i
   if (stats) *stats = p->stats;
   if (flags & QB_PROGRAM_TIME) QB_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (p->nqubits < 4) {
+    if (flags & QB_PROGRAM_INPUT_ZERO) {
+      int rc = set_basis_locked(h, state, p->nqubits, p->dtype, 0);
+      if (rc != QB_OK) return rc;
+    }
     for (auto& c : p->canon) {
       int rc = p->dtype == QB_C128 ? apply_canon_k1<double2>(h, state, p->nqubits, c) : apply_canon_k1<float2>(h, state, p->nqubits, c);
       if (rc != QB_OK) return rc;
@@ -765,7 +783,8 @@ static int program_run_impl(qb_handle h, qb_program p, void* state, void* dst, i
       if (rc != QB_OK) return rc;
     }
   } else {
-    int rc = launch_plan(h, state, dst, p->nqubits, p->dtype, p->plan, (const char*)p->dev, p->has_perm ? &p->perm : nullptr);
+    int rc = launch_plan(h, state, dst, p->nqubits, p->dtype, p->plan, (const char*)p->dev, p->has_perm ? &p->perm : nullptr,
+                         (flags & QB_PROGRAM_INPUT_ZERO) != 0);
     if (rc != QB_OK) return rc;
   }
   if (flags & QB_PROGRAM_TIME) {

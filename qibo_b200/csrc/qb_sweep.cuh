@@ -262,6 +262,21 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
         __syncwarp();
       }
       char* sbase = reinterpret_cast<char*>(tiles + (size_t)b * tile_elems);
+      if (tma.pad[1]) {
+        // the input is |0...0> and has not been written anywhere (QB_PROGRAM_INPUT_ZERO): the tile is made here instead of
+        // being read -- the first sweep of an execution is write-only and the 2^n-amplitude fill before it disappears
+        int4* zt = reinterpret_cast<int4*>(sbase);
+        for (uint32_t i = lane; i < tile_bytes / 16; i += 32) zt[i] = make_int4(0, 0, 0, 0);
+        if (lane == 0 && base == 0) {
+          C one;
+          one.x = 1;
+          one.y = 0;
+          tiles[(size_t)b * tile_elems] = one;  // tile-local index 0 sits at offset 0 in either layout
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(fullb);
+        continue;
+      }
       if (tma.enabled) {
         if (lane == 0) {
           mbar_expect_tx(fullb, tile_bytes);
@@ -440,8 +455,9 @@ inline bool tma_describe(void* state, int nqubits, int dtype, uint64_t tile_mask
 }
 
 // `dst`: the buffer a PERMUTING sweep (sd.permuted) writes to -- another buffer of the state's size; ignored otherwise.
+// `input_zero`: the state is |0...0> and `state` holds nothing yet -- the loader makes the tiles instead of reading them.
 inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqubits, int dtype, const SweepDesc& sd,
-                        const char* prog_dev, void* dst = nullptr) {
+                        const char* prog_dev, void* dst = nullptr, bool input_zero = false) {
   uint64_t grid = sd.ntiles < (uint64_t)sm_count ? sd.ntiles : (uint64_t)sm_count;
   TmaDesc tma, tma_dst;
   if (!tma_describe(state, nqubits, dtype, sd.tile_mask, sd.swizzle != 0, tma) && sd.swizzle) return QB_ERR_UNSUPPORTED;  // planned for a swizzled tile
@@ -453,6 +469,7 @@ inline int launch_sweep(cudaStream_t stream, int sm_count, void* state, int nqub
   }
   const bool so = sd.stage_only != 0 && !env_int("QB_NO_STAGE_KERNEL", 0);
   tma.pad[0] = env_int("QB_SWEEP_SKIP_COMPUTE", 0);
+  tma.pad[1] = input_zero ? 1 : 0;
   if (dtype == QB_C128) {
     if (so) sweep_kernel<double2, true><<<(unsigned)grid, sw_threads<double2, true>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma, tma_dst);
     else sweep_kernel<double2, false><<<(unsigned)grid, sw_threads<double2, false>(), SW_SMEM_BYTES, stream>>>((double2*)state, prog_dev + sd.blob_offset, tma, tma_dst);

@@ -107,11 +107,14 @@ class Engine:
         collector.  Before a large allocation that would not fit, collect."""
         nbytes = int(np.prod(shape)) * torch.empty((), dtype=tdtype).element_size()
         if nbytes >= (1 << 30):
-            # (the allocator's own counters first: cudaMemGetInfo costs ~1.5 ms)
+            # the allocator's own counters first: when its cache can serve the request nothing else is asked.  (cudaMemGetInfo
+            # costs 0.5-1.5 ms as a rule but was seen to take 30-100 ms at random in the plugin-level QFT(32) loop --
+            # profiles/r2s_e2e_profile2.txt --, where the second 64 GiB buffer of a step used to take this branch because of
+            # a safety margin on top of an exactly fitting cached block.)
             cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-            if cached < nbytes + (1 << 28):
+            if cached < nbytes:
                 free, _ = torch.cuda.mem_get_info(self.device)
-                if free + cached < nbytes + (1 << 28):
+                if free < nbytes + (1 << 28):
                     self._reclaim()
         try:
             return torch.empty(shape, dtype=tdtype, device=self.device)
@@ -140,6 +143,14 @@ class Engine:
         out = self.empty((1 << nqubits,), dtype)
         _lib.check(self.lib.qb_state_set_basis(self.handle, out.data_ptr(), nqubits, _DT[np.dtype(dtype)], index))
         return out
+
+    def uninitialised_state(self, nqubits: int, dtype="complex128") -> DeviceArray:
+        """A state buffer with NOTHING written to it, for ``run_program(..., input_zero=True)`` / ``apply_program(...,
+        input_zero=True)``: the first sweep of the program makes the |0...0> tiles itself."""
+        return self.empty((1 << nqubits,), dtype)
+
+    def _write_zero_state(self, state: DeviceArray, nqubits: int):
+        _lib.check(self.lib.qb_state_set_basis(self.handle, state.data_ptr(), nqubits, _DT[np.dtype(state.dtype)], 0))
 
     def filled_state(self, nqubits: int, value: complex, dtype="complex128") -> DeviceArray:
         """plus_state (abstract.py:2199-2221): every amplitude equal to ``value``."""
@@ -231,13 +242,15 @@ class Engine:
         return state
 
     # ---- K2: a gate queue -------------------------------------------------------------------------
-    def _apply_sweeps(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool, timed: bool):
+    def _apply_sweeps(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool, timed: bool, extra_flags: int = 0):
         self.bind_current_stream()
         stats = _lib.QbProgramStats()
         if len(ops) == 0:
+            if extra_flags & _lib.QB_PROGRAM_INPUT_ZERO:
+                self._write_zero_state(state, nqubits)
             return stats
         arr, keep = pack_ops(ops)
-        flags = (0 if fuse else _lib.QB_PROGRAM_NO_FUSE) | (_lib.QB_PROGRAM_TIME if timed else 0)
+        flags = (0 if fuse else _lib.QB_PROGRAM_NO_FUSE) | (_lib.QB_PROGRAM_TIME if timed else 0) | extra_flags
         _lib.check(
             self.lib.qb_apply_program(
                 self.handle, state.data_ptr(), nqubits, _DT[state.dtype], arr, len(ops), flags, ctypes.byref(stats)
@@ -285,7 +298,7 @@ class Engine:
             state.tensor = scratch
 
     def _apply_sweeps_permuted(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], dest_of_qubit: Sequence[int], fuse: bool,
-                               timed: bool, alt: Optional[DeviceArray]):
+                               timed: bool, alt: Optional[DeviceArray], extra_flags: int = 0):
         """``ops`` then the qubit permutation, the permutation riding on the last sweep (qb_apply_program_permuted with
         QB_PROGRAM_PERM_FUSED_ONLY: NotImplementedError -- nothing launched -- when it cannot; OutOfMemoryError when no
         second buffer fits).  The DeviceArray is re-pointed at the result buffer as in ``permute_qubits``."""
@@ -293,7 +306,7 @@ class Engine:
         scratch = self._alloc(tuple(state.tensor.shape), state.tensor.dtype) if alt is None else alt.tensor
         stats = _lib.QbProgramStats()
         arr, keep = pack_ops(ops)
-        flags = (0 if fuse else _lib.QB_PROGRAM_NO_FUSE) | (_lib.QB_PROGRAM_TIME if timed else 0) | _lib.QB_PROGRAM_PERM_FUSED_ONLY
+        flags = (0 if fuse else _lib.QB_PROGRAM_NO_FUSE) | (_lib.QB_PROGRAM_TIME if timed else 0) | _lib.QB_PROGRAM_PERM_FUSED_ONLY | extra_flags
         _lib.check(
             self.lib.qb_apply_program_permuted(
                 self.handle, state.data_ptr(), scratch.data_ptr(), nqubits, _DT[state.dtype], arr, len(ops), _int_array(dest_of_qubit),
@@ -313,7 +326,7 @@ class Engine:
         )
 
     def apply_program(self, state: DeviceArray, nqubits: int, ops: Sequence[Op], fuse: bool = True, timed: bool = False,
-                      alt: Optional[DeviceArray] = None, spans: Optional[list] = None):
+                      alt: Optional[DeviceArray] = None, spans: Optional[list] = None, input_zero: bool = False):
         """Apply ``ops`` in order, several gates per HBM sweep.  Runs of >= MIN_SWAP_RUN uncontrolled SWAP gates (the
         bit reversal ending a QFT) become ONE out-of-place permutation sweep when a scratch buffer fits in memory.
         Returns the planner/timing statistics.  ``timed``: CUDA-event time per segment, read back at once (the host waits
@@ -324,6 +337,12 @@ class Engine:
         total.perm_ms, total.nperm = 0.0, 0  # K8 launches inside this program (reported apart from the sweep kernel)
         segments = split_segments(ops, nqubits, fuse and self.permute_swap_runs, fuse and self.fuse_permutations)
         total.nperm_fused = 0
+        # ``input_zero``: ``state`` is uninitialised memory standing for |0...0>; the first sweep program makes it
+        # (QB_PROGRAM_INPUT_ZERO), anything else that comes first needs it written
+        zero_flag = _lib.QB_PROGRAM_INPUT_ZERO if input_zero else 0
+        if zero_flag and (not segments or segments[0][0] not in ("ops", "opsperm")):
+            self._write_zero_state(state, nqubits)
+            zero_flag = 0
         while segments:
             kind, payload = segments.pop(0)
             if kind == "wide":
@@ -335,10 +354,14 @@ class Engine:
                 gops, dest = payload
                 e0 = _record_event() if spans is not None else None
                 try:
-                    st = self._apply_sweeps_permuted(state, nqubits, gops, dest, fuse, timed, alt)
+                    st = self._apply_sweeps_permuted(state, nqubits, gops, dest, fuse, timed, alt, zero_flag)
                 except (torch.cuda.OutOfMemoryError, NotImplementedError):
                     segments[:0] = ([("ops", gops)] if gops else []) + [("perm", dest)]  # the two-launch form
+                    if zero_flag and not gops:
+                        self._write_zero_state(state, nqubits)
+                        zero_flag = 0
                     continue
+                zero_flag = 0
                 if e0 is not None:
                     spans.append(("sweep", e0, _record_event(), st.nsweeps))
                 total.nperm_fused += 1
@@ -360,7 +383,8 @@ class Engine:
                     continue
             if kind != "done":
                 e0 = _record_event() if spans is not None else None
-                st = self._apply_sweeps(state, nqubits, payload, fuse, timed)
+                st = self._apply_sweeps(state, nqubits, payload, fuse, timed, zero_flag)
+                zero_flag = 0
                 if e0 is not None:
                     spans.append(("sweep", e0, _record_event(), st.nsweeps))
             total.nsweeps += st.nsweeps
@@ -382,7 +406,7 @@ class Engine:
         return CompiledProgram(self, nqubits, dtype, ops, fuse)
 
     def run_program(self, prog: "CompiledProgram", state: DeviceArray, timed: bool = False, alt: Optional[DeviceArray] = None,
-                    spans: Optional[list] = None):
+                    spans: Optional[list] = None, input_zero: bool = False):
         """Apply a compiled program to ``state`` (same nqubits / dtype / device as it was compiled for).  ``timed`` /
         ``spans`` as in ``apply_program``."""
         self.bind_current_stream()
@@ -393,6 +417,11 @@ class Engine:
         total.perm_ms, total.nperm = 0.0, 0
         flags = _lib.QB_PROGRAM_TIME if timed else 0
         total.nperm_fused = 0
+        # ``input_zero``: as in ``apply_program`` -- the first segment's first sweep makes |0...0> when it is a sweep program
+        zero_flag = _lib.QB_PROGRAM_INPUT_ZERO if input_zero else 0
+        if zero_flag and (not prog.segments or prog.segments[0][0] not in ("prog", "progperm")):
+            self._write_zero_state(state, prog.nqubits)
+            zero_flag = 0
         for index, (kind, payload) in enumerate(prog.segments):
             if kind == "wide":
                 self.apply_wide(state, prog.nqubits, payload)
@@ -405,14 +434,16 @@ class Engine:
                     scratch = self._alloc(tuple(state.tensor.shape), state.tensor.dtype) if alt is None else alt.tensor
                 except torch.cuda.OutOfMemoryError:  # no second buffer: the gates in place, the permutation as SWAP gates
                     gops, dest = prog.fused_source[index]
-                    st = self._apply_sweeps(state, prog.nqubits, list(gops) + swaps_for_permutation(dest), True, timed)
+                    st = self._apply_sweeps(state, prog.nqubits, list(gops) + swaps_for_permutation(dest), True, timed, zero_flag)
                 else:
                     e0 = _record_event() if spans is not None else None
-                    _lib.check(self.lib.qb_program_run_permuted(self.handle, payload, state.data_ptr(), scratch.data_ptr(), flags, ctypes.byref(st)))
+                    _lib.check(self.lib.qb_program_run_permuted(self.handle, payload, state.data_ptr(), scratch.data_ptr(), flags | zero_flag,
+                                                                ctypes.byref(st)))
                     self._adopt_result(state, scratch, alt)
                     if e0 is not None:
                         spans.append(("sweep", e0, _record_event(), st.nsweeps))
                     total.nperm_fused += 1
+                zero_flag = 0
                 total.nsweeps += st.nsweeps
                 total.ndense_passes += st.ndense_passes
                 total.ndiag_ops += st.ndiag_ops
@@ -438,7 +469,8 @@ class Engine:
                 continue
             st = _lib.QbProgramStats()
             e0 = _record_event() if spans is not None else None
-            _lib.check(self.lib.qb_program_run(self.handle, payload, state.data_ptr(), flags, ctypes.byref(st)))
+            _lib.check(self.lib.qb_program_run(self.handle, payload, state.data_ptr(), flags | zero_flag, ctypes.byref(st)))
+            zero_flag = 0
             if e0 is not None:
                 spans.append(("sweep", e0, _record_event(), st.nsweeps))
             total.nsweeps += st.nsweeps

@@ -75,14 +75,19 @@ def wrap(obj, name):
 for o, nm in ((be, "zero_state"), (be, "_compiled_circuit"), (eng, "run_program"), (eng, "_alloc"), (eng, "_reclaim"), (be, "calculate_probabilities"),
               (be, "sample_shots")):
     wrap(o, nm)
-for step in range(3):
+for step in range(int(os.environ.get("DETAIL_STEPS", 3))):
     acc.clear()
     t0 = sync()
     c = QFT(n)
     c.add(gates.M(*range(10)))
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     res = c(nshots=1000)
+    e1.record()
     th = time.perf_counter()
     t1 = sync()
+    acc["device_span_ms"] = e0.elapsed_time(e1)
     f = res.frequencies(binary=False)
     t2 = sync()
     print(f"detail {step}: host returns after {1e3 * (th - t0):.1f} ms, device done {1e3 * (t1 - t0):.1f} ms, frequencies {1e3 * (t2 - t1):.1f} ms; host ms per call:",

@@ -673,3 +673,38 @@ def test_qft_with_fused_reversal_vs_oracle(eng, dtype):
         stats = eng.apply_program(st, n, circuits.qft(n))
         assert stats.nperm_fused == (1 if n > (12 if dtype == "complex128" else 13) else 0)
         assert np.abs(st.numpy() - ref).max() < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_first_sweep_makes_the_zero_state(eng, dtype):
+    """QB_PROGRAM_INPUT_ZERO: the buffer handed in is uninitialised (filled with NaNs here) and stands for |0...0>; the
+    first sweep's loader makes the tiles.  Bit-identical to running on a written zero state -- compiled and uncompiled,
+    with a fused permutation, for programs that start with a permutation / have no gate at all, and below 4 qubits."""
+    from qibo_b200 import circuits
+    from qibo_b200.engine import swaps_for_permutation
+
+    rng = np.random.default_rng(9)
+    cases = []
+    for n in (2, 3, 9, 14, 17, 21):
+        cases.append((n, circuits.qft(n)))
+        if n >= 9:
+            cases.append((n, random_zoo(n, 25, n)))
+    cases.append((16, swaps_for_permutation(list(range(15, -1, -1))) + circuits.qft(16, with_swaps=False)))  # permutation first
+    cases.append((15, []))
+    cases.append((15, [Op(np.eye(2), (3,))]))  # canonicalises to nothing: no sweep runs
+    for n, ops in cases:
+        ref_state = eng.basis_state(n, dtype)
+        eng.apply_program(ref_state, n, ops)
+        ref = ref_state.numpy()
+        for compiled in (False, True):
+            st = eng.uninitialised_state(n, dtype)
+            st.tensor.fill_(float("nan"))
+            if compiled:
+                prog = eng.compile(n, dtype, ops)
+                eng.run_program(prog, st, input_zero=True)
+                prog.close()
+            else:
+                eng.apply_program(st, n, ops, input_zero=True)
+            out = st.numpy()
+            assert not np.isnan(out).any(), (n, len(ops), compiled)
+            assert np.array_equal(out, ref), (n, len(ops), compiled)
