@@ -526,6 +526,7 @@ def run_gpu(args):
         compiled = eng.compile(n, args.dtype, ops)
         verify = verify_single_qft(eng, compiled, n, args.dtype)
         state = eng.basis_state(n, args.dtype)
+        alt = eng.empty((1 << n,), args.dtype)  # the second buffer the permuting last sweep writes to: resident like the state
 
         class _S:  # one step's counters + event spans (nothing waits for the GPU inside the step loop)
             def __init__(self):
@@ -533,7 +534,7 @@ def run_gpu(args):
 
         def step():
             s = _S()
-            st = eng.run_program(compiled, state, spans=s.spans)
+            st = eng.run_program(compiled, state, alt=alt, spans=s.spans)
             s.nsweeps, s.nstage_sweeps, s.nperm = st.nsweeps, st.nstage_sweeps, st.nperm
             return s
 
@@ -596,7 +597,7 @@ def run_gpu(args):
 
     e2e, e2e_engine, anchor, configs = None, None, None, None
     if world == 1:
-        del state
+        del state, alt
         torch.cuda.empty_cache()
         mq = list(range(min(10, n)))
         h2d_prog = sum(op.data.nbytes for op in ops) + len(ops) * 176

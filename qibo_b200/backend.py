@@ -62,6 +62,7 @@ class B200Backend(NumpyBackend):
         # execute_circuit without an initial state: no 2^n-amplitude fill, the first sweep of the compiled program makes the
         # |0...0> tiles (QB_PROGRAM_INPUT_ZERO)
         self.lazy_zero_state = os.environ.get("QB_NO_LAZY_ZERO", "0") in ("", "0")
+        Engine._freeze_imports(again=True)  # qibo and its dependencies are imported by now
         index = 0
         if device is not None:
             index = self._parse_device(device)

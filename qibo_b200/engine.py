@@ -87,12 +87,15 @@ class Engine:
     _gc_frozen = False
 
     @classmethod
-    def _freeze_imports(cls):
+    def _freeze_imports(cls, again: bool = False):
         """Once per process, when the first engine is created (i.e. right after the imports, before any circuit of this
         backend exists): move the long-lived module objects (qibo, sympy, torch: ~3e5 tracked objects) out of the cyclic
         collector's scans, so that the collections ``_alloc`` triggers under memory pressure cost < 1 ms instead of
-        ~170 ms.  Objects created later are collected as usual.  QB_NO_GC_FREEZE=1 leaves the collector alone."""
-        if cls._gc_frozen or os.environ.get("QB_NO_GC_FREEZE", "") not in ("", "0"):
+        ~170 ms.  Objects created later are collected as usual.  QB_NO_GC_FREEZE=1 leaves the collector alone.  ``again``:
+        the backend calls this once more when it is constructed -- a process that made an Engine BEFORE importing qibo
+        (bench.py does) would otherwise scan qibo's and sympy's import-time objects on every collection (measured: the
+        plugin-level QFT(32) step 167 ms instead of 138 ms)."""
+        if (cls._gc_frozen and not again) or os.environ.get("QB_NO_GC_FREEZE", "") not in ("", "0"):
             return
         import gc
 
