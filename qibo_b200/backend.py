@@ -329,7 +329,7 @@ class B200Backend(NumpyBackend):
             return None
         key = (tuple(map(id, plain)), nqubits, density_matrix, str(dtype), id(self.engine_gpu))
         cached = getattr(circuit, "_qb200_program", None)
-        if cached is not None and cached["key"] == key:
+        if cached is not None and cached.get("program") is not None and cached["key"] == key:
             self._update_parameters(cached)
             return cached["program"]
         ops, slots = [], []

@@ -60,6 +60,11 @@ class Engine:
         self.fuse_permutations = os.environ.get("QB_NO_FUSE_PERM", "0") in ("", "0")
         self.exact_scan_max_bins = EXACT_SCAN_MAX_BINS
 
+    def __reduce__(self):
+        # (pickled with the backend that owns it -- joblib's process pools in qibo/parallel.py, MeasurementResult symbols:
+        # a library handle means nothing in another process: the copy opens its own context on the same device index)
+        return (Engine, (self.device.index,))
+
     def bind_current_stream(self):
         """Follow torch's current stream (``with torch.cuda.stream(s):``): the library's kernels and torch's copies /
         allocations of the same buffers must be ordered on ONE stream.  Called at the top of every entry point; a no-op
@@ -663,9 +668,17 @@ class _RawCuda:
             pass
 
 
+def _dropped_program():
+    return None
+
+
 class CompiledProgram:
     """Segments of a gate queue compiled for one Engine: ("prog", qb_program handle) for runs of gates, ("perm", dest) for
-    runs of plain SWAPs (K8).  Frees its device programs with the object."""
+    runs of plain SWAPs (K8).  Frees its device programs with the object.  Pickles to None: the handles are device-resident
+    programs of THIS process (a Circuit that carries its compiled program is compiled again where it is unpickled)."""
+
+    def __reduce__(self):
+        return (_dropped_program, ())
 
     def __init__(self, engine: "Engine", nqubits: int, dtype, ops: Sequence[Op], fuse: bool = True):
         self.engine, self.nqubits, self.dtype, self.nops = engine, nqubits, np.dtype(dtype), len(ops)

@@ -455,3 +455,34 @@ def test_state_host_io_streaming_and_dump_load(backends, tmp_path, monkeypatch):
     loaded = load_result(str(path))
     assert isinstance(loaded, QuantumState)
     np.testing.assert_array_equal(np.asarray(ours.to_numpy(loaded.state())), plain)
+
+
+def test_pickling_backend_and_circuits_with_compiled_programs(backends):
+    """qibo/parallel.py ships the backend and the circuits to joblib worker PROCESSES (tests/test_parallel.py:46-62), and
+    MeasurementResult symbols are pickled with their backend (tests/test_measurements.py:470-480).  A circuit that has run
+    carries its compiled program (device-resident, this process only): it must pickle to "no program" and be compiled again
+    where it lands, and an Engine must come back as a fresh context, not as a copied library handle."""
+    import pickle
+
+    from qibo import gates
+    from qibo.models import QFT
+
+    ours, ref = backends
+    c = QFT(9)
+    c.add(gates.M(0, 3))
+    first = ours.execute_circuit(c, nshots=10)
+    assert getattr(c, "_qb200_program", None) is not None and c._qb200_program["program"] is not None
+    c2 = pickle.loads(pickle.dumps(c))
+    assert c2._qb200_program["program"] is None
+    be2 = pickle.loads(pickle.dumps(ours))
+    assert be2.engine_gpu is not ours.engine_gpu and be2.engine_gpu.handle.value != ours.engine_gpu.handle.value
+    target = ref.execute_circuit(QFT(9)).state()
+    for backend, circuit in ((ours, c2), (be2, c2), (be2, c)):
+        out = backend.execute_circuit(circuit, nshots=10).state(numpy=True)
+        assert np.abs(out - target).max() < 1e-12
+    # the reference's own entry point: worker processes
+    circuits = [QFT(n) for n in range(1, 9)]
+    serial = [ours.execute_circuit(x) for x in circuits]
+    parallel = ours.execute_circuits(circuits, processes=2)
+    for a, b in zip(serial, parallel):
+        assert np.abs(a.state(numpy=True) - b.state(numpy=True)).max() < 1e-12
