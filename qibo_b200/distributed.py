@@ -764,7 +764,12 @@ class ShardedProgram:
         the local chunk copied last).  The ranks then continue in their second buffers."""
         entries = alltoall_push_entries(self.rank, self.nlocal, pairs)
         k = len(pairs)
-        sub_n = self.nlocal - k
+        chunk_n = self.nlocal - k
+        sub_bits = getattr(piped, "sub_bits", 0)
+        if sub_bits and any(hi - lo != (1 << chunk_n) for _, _, _, lo, hi in entries):
+            raise RuntimeError("internal: pieces of a chunk need whole-chunk all-to-all entries")
+        sub_n = chunk_n - sub_bits  # qubits of one piece: what piped.ops are indexed for
+        npieces, piece_elems = 1 << sub_bits, 1 << sub_n
         elem = state.tensor.element_size()
         eng = self.engine
         main = torch.cuda.current_stream(state.tensor.device)
@@ -812,19 +817,23 @@ class ShardedProgram:
                     ev = torch.cuda.Event()
                     ev.record(stream)
                     stays.append(ev)
-                stays_view = DeviceArray(peer.alt.tensor[b : b + (1 << sub_n)])
+                stays_at = b
         for r2, a, b, lo, hi in order:
             if r2 == self.rank:
                 continue
-            sweep_chunk(DeviceArray(state.tensor[a : a + (1 << sub_n)]))
-            done = torch.cuda.Event()
-            done.record(main)
-            dma(dst[r2] + b * elem, src0 + a * elem, hi - lo, done)
+            for piece in range(npieces):  # piece by piece: swept on the compute stream, then on its way
+                off = piece * piece_elems
+                sweep_chunk(DeviceArray(state.tensor[a + off : a + off + piece_elems]))
+                done = torch.cuda.Event()
+                done.record(main)
+                dma(dst[r2] + (b + off) * elem, src0 + (a + off) * elem, piece_elems, done)
             out.exchange_bytes += 2 * elem * (hi - lo)
         if stays is not None:
             for ev in stays:
                 main.wait_event(ev)
-            sweep_chunk(stays_view)
+            for piece in range(npieces):
+                off = stays_at + piece * piece_elems
+                sweep_chunk(DeviceArray(peer.alt.tensor[off : off + piece_elems]))
         for stream in copies:
             landed = torch.cuda.Event()
             landed.record(stream)
@@ -923,11 +932,15 @@ class ShardedProgram:
 
 
 class PipedOps:
-    """The tail of a local segment that rides on the exchange after it: ``ops`` act on the nlocal - k lower local qubits
-    of one chunk (re-indexed), ``nlocal_ops`` are the same gates in shard numbering (transports without pipelining)."""
+    """The tail of a local segment that rides on the exchange after it: ``ops`` act on the nlocal - k - sub_bits lower local
+    qubits of one piece of a chunk (re-indexed), ``nlocal_ops`` are the same gates in shard numbering (transports without
+    pipelining).  ``sub_bits``: the tail touches none of the ``sub_bits`` local qubits below the k leading ones either, so
+    every chunk is swept and sent in 2^sub_bits pieces -- the first DMA copy starts after one piece has been swept, not one
+    chunk (QFT(33) on 2 GPUs: the ONE remote chunk is half a shard; in one piece its 49 ms copy could only start when all
+    of its sweeps were done)."""
 
-    def __init__(self, ops, nlocal_ops):
-        self.ops, self.nlocal_ops = ops, nlocal_ops
+    def __init__(self, ops, nlocal_ops, sub_bits=0):
+        self.ops, self.nlocal_ops, self.sub_bits = ops, nlocal_ops, sub_bits
         self.full_key = ("full", nlocal_ops)
 
     def __getitem__(self, i):  # (_compiled keys a segment by identity and reads its ops from [1])
@@ -953,8 +966,16 @@ def split_for_pipeline(nlocal: int, dtype, ops: Sequence[Op], k: int):
     tail = [o for o, s in zip(ops, sweep_of_op) if s > last]
     if not tail:
         return list(ops), None
-    shifted = [Op(o.data, tuple(q - k for q in o.targets), tuple(q - k for q in o.controls), is_diagonal=o.is_diagonal) for o in tail]
-    return head, PipedOps(shifted, tail)
+    # pieces: as many further leading qubits as the tail leaves alone, down to pieces of 2^QB_PIPE_PIECE_QUBITS amplitudes
+    # (default 28: 4 GiB of complex128 -- the sweeps of a piece still fill the GPU many times over)
+    first_touched = min((q for o in tail for q in tuple(o.targets) + tuple(o.controls)), default=nlocal)
+    piece = int(os.environ.get("QB_PIPE_PIECE_QUBITS", "28"))
+    sub = max(0, min(first_touched - k, (nlocal - k) - piece))
+    if os.environ.get("QB_NO_PIPE_PIECES", "0") not in ("", "0") or nlocal - k - sub < 4:
+        sub = 0
+    ks = k + sub
+    shifted = [Op(o.data, tuple(q - ks for q in o.targets), tuple(q - ks for q in o.controls), is_diagonal=o.is_diagonal) for o in tail]
+    return head, PipedOps(shifted, tail, sub)
 
 
 def _span_begin(spans, tensor):

@@ -324,6 +324,30 @@ def test_all_shards_on_one_gpu(case, n, dtype, world, layout, transport):
     assert np.abs(grp.gather() - ref2).max() < t
 
 
+@pytest.mark.parametrize("n,world,dtype", [(20, 2, "complex128"), (21, 4, "complex128"), (22, 8, "complex64"), (20, 2, "complex64")])
+def test_pipelined_exchange_in_pieces(n, world, dtype, monkeypatch):
+    """Every chunk of the pipelined exchange swept and sent in 2^s pieces (the tail of the local segment leaves the s local
+    qubits below the leading ones alone): forced here at small n by asking for 2^13-amplitude pieces."""
+    from qibo_b200.distributed import SingleDeviceGroup
+    from qibo_b200.engine import Engine
+
+    monkeypatch.setenv("QB_PIPE_PIECE_QUBITS", "13")
+    eng = Engine(0)
+    ops, psi, ref, ref2 = _group_reference("qft", n, dtype)
+    grp = SingleDeviceGroup(eng, n, world, dtype, ops, global_qubits="auto")
+    grp.configure(pipeline=True, alltoall_push=True, alltoall=True)
+    pieces = [seg[4].sub_bits for prog in grp.programs for seg in prog.segments if seg[0] == "exchange" and len(seg) > 4 and seg[4] is not None]
+    assert pieces and max(pieces) >= 1
+    grp.scatter(psi)
+    stats = grp.run()
+    t = 1e-12 if dtype == "complex128" else 1e-5
+    assert np.abs(grp.gather() - ref).max() < t
+    assert all(s.pipelined == 1 and s.nchunk_sweeps > 0 for s in stats)
+    grp.scatter(ref)
+    grp.run(compiled=False)
+    assert np.abs(grp.gather() - ref2).max() < t
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_reference_distributed_cases_under_torchrun():
     """tests/dist_reference_cases.py: the reference's own distributed tests (entropy callbacks, measurements, collapse)
