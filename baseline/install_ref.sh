@@ -27,11 +27,14 @@ if [ -d "$REF/tests" ]; then
   rm -rf "$DST/tests"
   mkdir -p "$DST/tests"
   cp "$REF"/tests/__init__.py "$REF"/tests/conftest.py "$DST/tests/"
+  [ -f "$REF/tests/utils.py" ] && cp "$REF/tests/utils.py" "$DST/tests/"
   for t in test_gates_gates test_gates_density_matrix test_gates_special test_gates_abstract test_backends test_backends_global \
            test_models_circuit_fuse test_models_qft test_models_circuit_execution test_models_circuit_features \
            test_models_circuit_parametrized test_models_circuit test_measurements test_measurements_probabilistic \
            test_measurements_collapse test_result test_states test_models_distcircuit test_models_distcircuit_execution \
-           test_callbacks test_parallel test_models_circuit_noise test_hamiltonians_terms test_models_variational; do
+           test_callbacks test_parallel test_models_circuit_noise test_hamiltonians_terms test_models_variational \
+           test_models_evolution test_hamiltonians_trotter test_hamiltonians_symbolic test_hamiltonians_models \
+           test_gates_channels test_noise test_derivative test_models_grover test_models_encodings; do
     [ -f "$REF/tests/$t.py" ] && cp "$REF/tests/$t.py" "$DST/tests/"
   done
   [ -d "$REF/tests/regressions" ] && cp -r "$REF/tests/regressions" "$DST/tests/"

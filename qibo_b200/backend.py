@@ -53,7 +53,9 @@ class B200Backend(NumpyBackend):
         self.platform = "cuda-sm100a"
         self.supports_multigpu = True
         self.oom_error = (torch.cuda.OutOfMemoryError, _lib.QiboB200OutOfMemory, MemoryError)
-        self.tensor_types = (np.ndarray,)
+        # (DeviceArray is what this backend returns as a state: models/evolution.py:105, hamiltonians and parallel.py test
+        # `isinstance(x, backend.tensor_types)` to tell a tensor from a result object)
+        self.tensor_types = (np.ndarray, DeviceArray)
         self.versions = {"qibo": qibo_version, "numpy": np.__version__, "torch": torch.__version__,
                          "qibo_b200": _lib.load().qb_version()}
         self._engines = {}
