@@ -486,3 +486,25 @@ def test_pickling_backend_and_circuits_with_compiled_programs(backends):
     parallel = ours.execute_circuits(circuits, processes=2)
     for a, b in zip(serial, parallel):
         assert np.abs(a.state(numpy=True) - b.state(numpy=True)).max() < 1e-12
+
+
+@pytest.mark.parametrize("accelerators", [None, {"/GPU:0": 2}])
+def test_trotter_state_evolution(backends, accelerators):
+    """f4: Trotter evolution circuits (models/evolution.py:77-111, hamiltonians.circuit(dt)) run on the same sweep kernels --
+    against the reference backend, step by step through a callback, with and without `accelerators` (one process: the
+    logical devices collapse onto this GPU)."""
+    from qibo import callbacks, hamiltonians, models
+
+    ours, ref = backends
+    n, dt = 5, 0.05
+    finals = []
+    for backend, acc in ((ours, accelerators), (ref, None)):
+        ham = hamiltonians.TFIM(n, h=1.0, dense=False, backend=backend)
+        energy = callbacks.Energy(hamiltonians.TFIM(n, h=1.0, backend=backend))
+        evolution = models.StateEvolution(ham, dt, callbacks=[energy], accelerators=acc)
+        psi0 = np.ones(2**n, dtype=np.complex128) / np.sqrt(2**n)
+        final = evolution(final_time=0.5, initial_state=psi0.copy())
+        finals.append((backend.to_numpy(final), [float(np.real(backend.to_numpy(x))) for x in energy[:]]))
+    (psi_a, e_a), (psi_b, e_b) = finals
+    assert np.abs(psi_a - psi_b).max() < 1e-12
+    assert np.allclose(e_a, e_b, atol=1e-12)
