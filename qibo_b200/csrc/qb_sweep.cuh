@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
   const uint32_t tile_elems = 1u << T;
   for (uint32_t r = tid; r < nruns; r += SW_THREADS) run_off[r] = deposit(uint64_t(r) << L, hdr.tile_mask) * sizeof(C);
   if (tid == 0) {
-    for (int b = 0; b < SW_NFULL; ++b) mbar_init(&full[b], 1);
+    for (int b = 0; b < SW_NFULL; ++b) mbar_init(&full[b], 2);  // the tile's bytes (expect_tx) + its slot states (loader)
     for (int b = 0; b < SW_NBUF; ++b) {
       mbar_init(&done[b], 1);
       mbar_init(&freeb[b], 1);
@@ -245,9 +245,40 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
       uint64_t* fullb = &full[i % SW_NFULL];
       // buffer b was last used by tile i-3: wait until the storer has drained it
       if (i >= SW_NBUF) mbar_wait_sleep(&freeb[b], (uint32_t)(((i / SW_NBUF) - 1) & 1));
-      // per-tile set-up of the ops that depend on bits outside the tile (control predicates, fan factors), by the
-      // otherwise idle lanes of this warp: off the compute warps' critical path.  Published by the mbarrier
-      // arrive below (release) -> the compute threads' wait on `full` (acquire).
+      // The copy is issued FIRST: the buffer has just come free and every cycle until the load is under way is a bubble
+      // in the buffer's load -> compute -> store cycle (three buffers per SM: the sweep's throughput).  The per-tile set-up
+      // of the ops that depend on bits outside the tile (control predicates, fan factors) -- done by the otherwise idle
+      // lanes of this warp, off the compute warps' critical path -- then runs while the bytes are in flight.  `full` counts
+      // two arrivals: the copy's expect_tx and, after the set-up, the release of the slot states (-> the compute
+      // threads' acquire when they wait on `full`).
+      char* sbase = reinterpret_cast<char*>(tiles + (size_t)b * tile_elems);
+      const bool synth = tma.pad[1] != 0;
+      if (synth) {
+        // the input is |0...0> and has not been written anywhere (QB_PROGRAM_INPUT_ZERO): the tile is made here instead of
+        // being read -- the first sweep of an execution is write-only and the 2^n-amplitude fill before it disappears
+        int4* zt = reinterpret_cast<int4*>(sbase);
+        for (uint32_t k = lane; k < tile_bytes / 16; k += 32) zt[k] = make_int4(0, 0, 0, 0);
+        if (lane == 0 && base == 0) {
+          C one;
+          one.x = 1;
+          one.y = 0;
+          tiles[(size_t)b * tile_elems] = one;  // tile-local index 0 sits at offset 0 in either layout
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(fullb);
+      } else if (tma.enabled) {
+        if (lane == 0) {
+          mbar_expect_tx(fullb, tile_bytes);
+          tma_load_5d(sbase, &tma.map, (int)((base >> tma.shift[0]) & tma.mask[0]), (int)((base >> tma.shift[1]) & tma.mask[1]),
+                      (int)((base >> tma.shift[2]) & tma.mask[2]), (int)((base >> tma.shift[3]) & tma.mask[3]),
+                      (int)((base >> tma.shift[4]) & tma.mask[4]), fullb);
+        }
+      } else {
+        if (lane == 0) mbar_expect_tx(fullb, tile_bytes);
+        __syncwarp();
+        const char* gbase = reinterpret_cast<const char*>(state + base);
+        for (uint32_t r = lane; r < nruns; r += 32) bulk_g2s(sbase + r * run_bytes, gbase + run_off[r], run_bytes, fullb);
+      }
       {
         TileSlot* ts = tslots + b * SWEEP_MAX_SLOTS;
         for (int sl = lane; sl < nslots; sl += 32) {
@@ -260,35 +291,7 @@ __global__ void __launch_bounds__(sw_threads<C, SO>(), 1) sweep_kernel(C* __rest
           }
         }
         __syncwarp();
-      }
-      char* sbase = reinterpret_cast<char*>(tiles + (size_t)b * tile_elems);
-      if (tma.pad[1]) {
-        // the input is |0...0> and has not been written anywhere (QB_PROGRAM_INPUT_ZERO): the tile is made here instead of
-        // being read -- the first sweep of an execution is write-only and the 2^n-amplitude fill before it disappears
-        int4* zt = reinterpret_cast<int4*>(sbase);
-        for (uint32_t i = lane; i < tile_bytes / 16; i += 32) zt[i] = make_int4(0, 0, 0, 0);
-        if (lane == 0 && base == 0) {
-          C one;
-          one.x = 1;
-          one.y = 0;
-          tiles[(size_t)b * tile_elems] = one;  // tile-local index 0 sits at offset 0 in either layout
-        }
-        __syncwarp();
         if (lane == 0) mbar_arrive(fullb);
-        continue;
-      }
-      if (tma.enabled) {
-        if (lane == 0) {
-          mbar_expect_tx(fullb, tile_bytes);
-          tma_load_5d(sbase, &tma.map, (int)((base >> tma.shift[0]) & tma.mask[0]), (int)((base >> tma.shift[1]) & tma.mask[1]),
-                      (int)((base >> tma.shift[2]) & tma.mask[2]), (int)((base >> tma.shift[3]) & tma.mask[3]),
-                      (int)((base >> tma.shift[4]) & tma.mask[4]), fullb);
-        }
-      } else {
-        if (lane == 0) mbar_expect_tx(fullb, tile_bytes);
-        __syncwarp();
-        const char* gbase = reinterpret_cast<const char*>(state + base);
-        for (uint32_t r = lane; r < nruns; r += 32) bulk_g2s(sbase + r * run_bytes, gbase + run_off[r], run_bytes, fullb);
       }
     }
   } else if (tid < 64) {
