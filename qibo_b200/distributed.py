@@ -555,6 +555,13 @@ class ShardedProgram:
         self._copy_stream = None
         self.segments = []
         runs = exchange_runs(self.plan.segments)
+        # OPT-IN (QB_SINK_LOW_QUBITS=5): measured on 2 B200s, QFT(33): 161.8 ms with the five lowest stages sunk behind the
+        # exchange, 142.3 ms without -- the exchange phase does not get shorter with fewer stages in its chunk sweeps (it is
+        # three passes over the shard next to the DMA traffic, 93 ms either way) and the last sweep, now eight stages with the
+        # arrived qubits' ascending-order fans, leaves the stage-only kernel (23 -> 45 ms)
+        if self.pipeline:
+            runs = sink_behind_exchanges(runs, self.nlocal, int(os.environ.get("QB_SINK_LOW_QUBITS", "0")),
+                                         int(os.environ.get("QB_SINK_MAX_BITS", "3")))
         for i, (kind, payload) in enumerate(runs):
             if kind == "local":
                 prev = self.segments[-1] if self.segments else None
@@ -931,6 +938,54 @@ class ShardedProgram:
         return self.assemble(torch.cat(parts).cpu().numpy())
 
 
+_SWAP4 = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+def sink_behind_exchanges(runs, nlocal: int, low_bits: int, max_mixed_after: int):
+    """Plan-level rewrite, before the ops are specialised per rank: for every run of exchanges between two local segments,
+    the END of the segment in front -- from the first gate that mixes one of the ``low_bits`` lowest state bits on, all of
+    whose mixing gates act on those bits only -- moves behind the exchange when the segment behind mixes at most
+    ``max_mixed_after`` qubits (a sharded QFT: the stages on the arrived qubits + the closing permutation: a nearly empty
+    sweep whose tile spans the lowest bits anyway).  A gate moved past an exchange is the same gate with the exchanged bits
+    relabelled (global bit <-> local bit), so a CU1 between a low qubit and a qubit that was global in front of the
+    exchange is a CU1 on two LOCAL bits behind it -- it must not be specialised for the old rank bits.  Five stages less in
+    the chunk sweeps of the pipelined exchange (compute-bound 8-stage sweeps, what the exchange phase takes)."""
+    if low_bits <= 0:
+        return runs
+    runs = [(k, list(p)) for k, p in runs]
+
+    def is_swap(o):
+        return not o.cbits and len(o.tbits) == 2 and not o.is_diagonal and np.shape(o.data) == (4, 4) and np.array_equal(o.data, _SWAP4)
+
+    for i in range(1, len(runs) - 1):
+        if runs[i][0] != "exchange" or runs[i - 1][0] != "local" or runs[i + 1][0] != "local":
+            continue
+        before, pairs, after = runs[i - 1][1], runs[i][1], runs[i + 1][1]
+        mixed_after = {b for o in after if not _is_diagonal_op(o) and not is_swap(o) for b in tuple(o.tbits) + tuple(o.cbits)}
+        if len(mixed_after) > max_mixed_after:
+            continue
+        exchanged = {b for pr in pairs for b in pr}
+        start = len(before)
+        for j in range(len(before) - 1, -1, -1):
+            o = before[j]
+            # (a mixing gate must stay on local bits: none of the exchanged ones, whatever the size of the register)
+            if not _is_diagonal_op(o) and any(b >= low_bits or b in exchanged for b in tuple(o.tbits) + tuple(o.cbits)):
+                break
+            start = j
+        while start < len(before) and _is_diagonal_op(before[start]):
+            start += 1  # leading diagonal gates stay with the gate in front of them
+        if start >= len(before):
+            continue
+        relabel = {}
+        for g, l in pairs:
+            relabel[g], relabel[l] = l, g
+        moved = [PhysOp(o.data, tuple(relabel.get(b, b) for b in o.tbits), tuple(relabel.get(b, b) for b in o.cbits), o.is_diagonal)
+                 for o in before[start:]]
+        runs[i - 1] = ("local", before[:start])
+        runs[i + 1] = ("local", moved + after)
+    return runs
+
+
 class PipedOps:
     """The tail of a local segment that rides on the exchange after it: ``ops`` act on the nlocal - k - sub_bits lower local
     qubits of one piece of a chunk (re-indexed), ``nlocal_ops`` are the same gates in shard numbering (transports without
@@ -945,6 +1000,13 @@ class PipedOps:
 
     def __getitem__(self, i):  # (_compiled keys a segment by identity and reads its ops from [1])
         return (None, self.ops)[i]
+
+
+def _is_diagonal_op(o: Op) -> bool:
+    if o.is_diagonal:
+        return True
+    d = np.asarray(o.data)
+    return d.ndim == 2 and not np.count_nonzero(d - np.diag(np.diagonal(d)))
 
 
 def split_for_pipeline(nlocal: int, dtype, ops: Sequence[Op], k: int):

@@ -647,20 +647,40 @@ def test_sharded_measurement_matches_oracle(world):
     assert mismatch <= 2  # a uniform within rounding of a rank boundary of the CDF may land on the neighbouring bin
 
 
-def test_pipelined_exchange_splits_the_qft():
+def test_pipelined_exchange_splits_the_qft(monkeypatch):
     """What the chunk pipeline does to the sharded QFT: the sweeps after the first one touch none of the leading local
-    qubits, so they ride on the exchange chunk by chunk (host logic; the numbers are checked above)."""
+    qubits, so they ride on the exchange chunk by chunk (host logic; the numbers are checked above); with the opt-in
+    QB_SINK_LOW_QUBITS=5 the stages on the five lowest bits move behind the exchange."""
     from qibo_b200 import circuits
     from qibo_b200.distributed import ShardedProgram
+
+    monkeypatch.setenv("QB_SINK_LOW_QUBITS", "5")
 
     prog = ShardedProgram(None, 24, "complex128", circuits.qft(24), global_qubits="auto", world_=8, rank_=5)
     kinds = [seg[0] for seg in prog.segments]
     assert kinds.count("exchange") == 1
     x = prog.segments[kinds.index("exchange")]
-    assert len(x[1]) == 3 and x[4] is not None and len(x[4].ops) > 100
+    assert len(x[1]) == 3 and x[4] is not None and len(x[4].ops) > 80
     assert all(min(op.targets + op.controls) >= 0 for op in x[4].ops)
     head = prog.segments[kinds.index("exchange") - 1][1]
     assert len(head) > 0
+    # the stages on the five lowest state bits sink behind the exchange, in front of the stages on the arrived qubits: the
+    # last segment is then ONE full sweep (with the closing permutation), the chunk sweeps lose five stages
+    after = prog.segments[kinds.index("exchange") + 1][1]
+    from qibo_b200.distributed import _is_diagonal_op
+
+    mixing = [op.targets[0] for op in after if len(op.targets) == 1 and not _is_diagonal_op(op)]
+    assert mixing[:5] == [16, 17, 18, 19, 20] and sorted(mixing[5:8]) == [0, 1, 2]
+    assert not any(q >= 16 for op in x[4].nlocal_ops if len(op.targets) == 1 and not _is_diagonal_op(op) for q in op.targets)
+
+
+@pytest.mark.parametrize("sink", ["0", "5", "3"])
+def test_sharded_qft_with_and_without_sunk_stages(sink, monkeypatch):
+    """The gates that sink behind an exchange (QB_SINK_LOW_QUBITS low state bits; 0 = none): the gathered state of a
+    sharded QFT is the oracle's either way (gloo, world size 4, real exchanges, NumPy shard executor)."""
+    monkeypatch.setenv("QB_SINK_LOW_QUBITS", sink)
+    err, nex, planned = _run(4, "qft", 10, seed=6, layout="auto")
+    assert err < 1e-12 and nex == planned == 2
 
 
 @pytest.mark.parametrize("case,n,world", [("qft", 17, 8), ("qft", 15, 2), ("variational", 16, 4), ("zoo", 16, 4)])
