@@ -551,6 +551,9 @@ class ShardedProgram:
         self.fuse_perm = os.environ.get("QB_A2A_FUSE_PERM", "0") not in ("", "0")  # experimental, see split_trailing_permutation
         # chunk-pipelined exchange (DMA copies over peer memory overlapped with the local sweeps before them)
         self.pipeline = os.environ.get("QB_NO_PIPELINE", "") in ("", "0")
+        # the chunk of a pipelined exchange that stays on its rank: swept out of place into the second buffer (its last
+        # sweep writes there) instead of being copied first and swept afterwards
+        self.local_out_of_place = os.environ.get("QB_NO_LOCAL_OUT_OF_PLACE", "") in ("", "0")
         self.copy_streams = int(os.environ.get("QB_COPY_STREAMS", "4"))
         self._copy_stream = None
         self.segments = []
@@ -786,8 +789,14 @@ class ShardedProgram:
             self._copy_stream = [torch.cuda.Stream(device=state.tensor.device) for _ in range(max(1, self.copy_streams))]
         copies = self._copy_stream
         prog = None
+        copying = None  # the same ops with the last sweep writing into the second buffer: the chunk that stays needs no copy
         if piped.ops:
             prog = self._compiled(piped, piped.ops, nqubits=sub_n) if compiled else None
+            if compiled and self.local_out_of_place:
+                key = ("copying", id(piped))
+                if key not in self._programs:
+                    self._programs[key] = eng.compile_copying(sub_n, self.dtype, piped.ops)
+                copying = self._programs[key]
         dst = peer.alt_ptrs
         src0 = state.data_ptr()
         peer.fence()  # every rank is done reading what is now its second buffer
@@ -818,13 +827,15 @@ class ShardedProgram:
         stays = None
         for r2, a, b, lo, hi in order:
             if r2 == self.rank:
-                dma(dst[r2] + b * elem, src0 + a * elem, hi - lo, start)
+                stays_at, stays_from = b, a
                 stays = []
+                if copying is not None:
+                    continue  # swept straight into the second buffer at the end
+                dma(dst[r2] + b * elem, src0 + a * elem, hi - lo, start)
                 for stream in copies:
                     ev = torch.cuda.Event()
                     ev.record(stream)
                     stays.append(ev)
-                stays_at = b
         for r2, a, b, lo, hi in order:
             if r2 == self.rank:
                 continue
@@ -840,7 +851,14 @@ class ShardedProgram:
                 main.wait_event(ev)
             for piece in range(npieces):
                 off = stays_at + piece * piece_elems
-                sweep_chunk(DeviceArray(peer.alt.tensor[off : off + piece_elems]))
+                if copying is not None:
+                    src_off = stays_from + piece * piece_elems
+                    st = eng.run_copying(copying, DeviceArray(state.tensor[src_off : src_off + piece_elems]),
+                                         DeviceArray(peer.alt.tensor[off : off + piece_elems]))
+                    out.nsweeps += st.nsweeps
+                    out.nchunk_sweeps += st.nsweeps
+                else:
+                    sweep_chunk(DeviceArray(peer.alt.tensor[off : off + piece_elems]))
         for stream in copies:
             landed = torch.cuda.Event()
             landed.record(stream)

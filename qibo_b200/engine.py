@@ -413,6 +413,32 @@ class Engine:
         ``run_program`` then costs kernel launches only -- no canonicalisation, planning or program upload per call."""
         return CompiledProgram(self, nqubits, dtype, ops, fuse)
 
+    # ---- out-of-place programs: the result lands in ANOTHER buffer (the identity "permutation" rides on the last sweep)
+    def compile_copying(self, nqubits: int, dtype, ops: Sequence[Op]):
+        """``ops`` compiled so that the LAST sweep writes its tiles to another buffer (qb_program_create_permuted with the
+        identity permutation): a program that has to end up elsewhere anyway -- the chunk of a pipelined exchange that stays
+        on its rank -- saves the copy.  None when the queue is not one sweep program or the planner cannot fuse."""
+        segments = split_segments(ops, nqubits, True, False)
+        if len(segments) != 1 or segments[0][0] != "ops" or not self.fuse_permutations:
+            return None
+        arr, keep = pack_ops(ops)
+        handle, st = ctypes.c_void_p(), _lib.QbProgramStats()
+        try:
+            _lib.check(self.lib.qb_program_create_permuted(
+                self.handle, nqubits, _DT[np.dtype(dtype)], arr, len(ops), _int_array(list(range(nqubits))),
+                _lib.QB_PROGRAM_PERM_FUSED_ONLY, ctypes.byref(handle), ctypes.byref(st)))
+        except NotImplementedError:
+            return None
+        del keep
+        return _CopyingProgram(self, handle, st.nsweeps)
+
+    def run_copying(self, prog: "_CopyingProgram", src: DeviceArray, dst: DeviceArray):
+        """Apply a ``compile_copying`` program to ``src``; the result is in ``dst`` (``src`` holds an intermediate state)."""
+        self.bind_current_stream()
+        st = _lib.QbProgramStats()
+        _lib.check(self.lib.qb_program_run_permuted(self.handle, prog.handle, src.data_ptr(), dst.data_ptr(), 0, ctypes.byref(st)))
+        return st
+
     def run_program(self, prog: "CompiledProgram", state: DeviceArray, timed: bool = False, alt: Optional[DeviceArray] = None,
                     spans: Optional[list] = None, input_zero: bool = False):
         """Apply a compiled program to ``state`` (same nqubits / dtype / device as it was compiled for).  ``timed`` /
@@ -670,6 +696,27 @@ class _RawCuda:
 
 def _dropped_program():
     return None
+
+
+class _CopyingProgram:
+    """Handle of an out-of-place sweep program (Engine.compile_copying); freed with the object, pickles to None."""
+
+    def __init__(self, engine, handle, nsweeps):
+        self.engine, self.handle, self.nsweeps = engine, handle, nsweeps
+
+    def __reduce__(self):
+        return (_dropped_program, ())
+
+    def close(self):
+        if self.handle and getattr(self.engine, "handle", None):
+            self.engine.lib.qb_program_destroy(self.engine.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CompiledProgram:
