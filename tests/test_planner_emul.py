@@ -391,3 +391,19 @@ def test_merged_sign_gates(dtype, seed, low_bits, monkeypatch):
     ref = orc.run_ops(psi, named, n, dtype=dtype)
     out, stats = emul.apply_program(psi, n, ops_from_named(named))
     assert np.abs(out - ref).max() < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_out_of_place_program_identity_permutation(dtype):
+    """Engine.compile_copying: a program whose last sweep writes into ANOTHER buffer (the identity permutation riding on a
+    permuting sweep) -- what the chunk of a pipelined exchange that stays on its rank runs.  QFT stages without the
+    closing swaps (the chunk programs of a sharded QFT) and a zoo program; the source buffer may be left in an
+    intermediate state, the destination must be complete."""
+    for n, named in ((15, [g for g in orc.qft_ops(15) if g[0] != "SWAP"]), (16, None)):
+        ops = ops_from_named(named) if named is not None else random_zoo(n, 30, 3)
+        psi = rand_state(n, 40 + n, dtype)
+        ref = oracle_run(psi, ops, n)
+        out, stats, fused = emul.apply_program_permuted(psi, n, ops, list(range(n)))
+        assert fused and stats.perm_fused == 1
+        assert not np.isnan(out).any()
+        assert np.abs(out - ref).max() < tol(dtype)
