@@ -854,7 +854,11 @@ _SWAP_MATRIX = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]
 
 
 def is_plain_swap(op: Op) -> bool:
-    return (not op.is_diagonal) and len(op.targets) == 2 and not op.controls and np.array_equal(op.data, _SWAP_MATRIX)
+    if op.is_diagonal or len(op.targets) != 2 or op.controls:
+        return False
+    d = op.data
+    # (two entries decide for every gate but the SWAP-like ones: no 16-element comparison per CU1 of a QFT)
+    return d[0, 0] == 1 and d[1, 2] == 1 and np.array_equal(d, _SWAP_MATRIX)
 
 
 def split_swap_runs(ops: Sequence[Op], nqubits: int):

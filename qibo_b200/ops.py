@@ -53,5 +53,5 @@ def pack_ops(ops: Sequence[Op]):
         for j, q in enumerate(op.controls):
             c.controls[j] = q
         c.is_diagonal = 1 if op.is_diagonal else 0
-        c.data = op.data.ctypes.data
+        c.data = op.data.__array_interface__["data"][0]  # (the address; `.ctypes.data` builds a ctypes object per call)
     return arr, [op.data for op in ops]
