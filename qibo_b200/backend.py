@@ -36,6 +36,12 @@ from qibo_b200 import _lib
 from qibo_b200.array import DeviceArray
 from qibo_b200.array import torch_dtype as torch_dtype_of
 from qibo_b200.engine import Engine, frequencies_from_samples
+
+_PLAIN_NUMBERS = (float, int, np.float64, np.float32, np.int64)
+# fixed-arity gates whose matrix is a function of their numeric parameters alone (backends/npmatrices.py)
+_CACHED_MATRIX_GATES = frozenset(
+    "H X Y Z S SDG T TDG SX SXDG RX RY RZ U1 U2 U3 GPI GPI2 CNOT CY CZ CSX CSXDG CRX CRY CRZ CU1 CU2 CU3 SWAP iSWAP SiSWAP SiSWAPDG "
+    "FSWAP fSim SYC RXX RYY RZZ RZX RXXYY MS GIVENS RBS ECR TOFFOLI CCZ DEUTSCH".split())
 from qibo_b200.ops import Op
 
 # gates whose matrix the library evaluates from the angle (qb_program_set_params): class name -> QB_GATE_*
@@ -64,6 +70,7 @@ class B200Backend(NumpyBackend):
         # execute_circuit without an initial state: no 2^n-amplitude fill, the first sweep of the compiled program makes the
         # |0...0> tiles (QB_PROGRAM_INPUT_ZERO)
         self.lazy_zero_state = os.environ.get("QB_NO_LAZY_ZERO", "0") in ("", "0")
+        self._matrix_cache = {}
         Engine._freeze_imports(again=True)  # qibo and its dependencies are imported by now
         index = 0
         if device is not None:
@@ -210,12 +217,25 @@ class B200Backend(NumpyBackend):
             # packs them into the same HBM sweep anyway, and neither the host-side scipy product of matrix_fused
             # (abstract.py:2680-2717, ~0.5 ms per block) nor a dense complex 2^r x 2^r multiply per amplitude is paid
             return [op for member in gate.gates for op in self._gate_ops(member, nqubits, density_matrix)]
-        matrix = np.asarray(gate.matrix(self))
         if gate.is_controlled_by:
             targets, controls = tuple(gate.target_qubits), tuple(gate.control_qubits)
         else:
             targets, controls = tuple(gate.qubits), ()
-        matrix = matrix.astype(np.complex128, copy=False)
+        # gate.matrix(backend) builds a fresh array per call (npmatrices.py); a queue repeats few distinct matrices (a QFT:
+        # H, SWAP and one CU1 per distance), so they are kept by (gate class, shape, parameters).  Only plain numeric
+        # parameters make a key: Unitary-like gates (array parameters) and symbolic ones are evaluated every time.
+        key = None
+        params = gate.parameters
+        if gate.__class__.__name__ in _CACHED_MATRIX_GATES and not gate.symbolic_parameters and all(type(p) in _PLAIN_NUMBERS for p in params):
+            key = (gate.__class__, len(targets), len(controls), tuple(params), self.dtype)
+        matrix = self._matrix_cache.get(key) if key is not None else None
+        if matrix is None:
+            matrix = np.ascontiguousarray(np.asarray(gate.matrix(self)).astype(np.complex128, copy=False))
+            if key is not None:
+                if len(self._matrix_cache) >= 4096:
+                    self._matrix_cache.clear()
+                matrix.setflags(write=False)
+                self._matrix_cache[key] = matrix
         if not density_matrix:
             return [Op(matrix, targets, controls, name=gate.__class__.__name__)]
         return [
