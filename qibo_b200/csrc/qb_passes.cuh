@@ -352,6 +352,8 @@ QB_HD void stage_full(C (&v)[GPT][1 << R], const uint32_t* g, const MicroOp* mop
   }
 }
 
+template <typename C> struct alignas(2 * sizeof(C)) Pair { C a, b; };  // two adjacent amplitudes: one 16-byte access for complex64
+
 // One REGTILE pass over the tile.  Each thread keeps GPT groups in registers at once, so that the decode of a
 // micro-op is paid once per GPT * 2^R amplitudes.  `ts` = this team's per-tile slot states.
 // A PASS_PERMUTED_STORE pass (the last pass of a permuting sweep) writes its groups to `out` (the kernel: the same buffer,
@@ -380,7 +382,25 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
     for (int i = 0; i < R; ++i) t = insert_zero32(t, ph.pos[i]);
     t0[u] = t;
     p0[u] = swz<C>(t, swz_on);
-    if (valid[u]) {
+  }
+  // PASS_PAIRED_GROUPS (complex64, two groups per thread that differ in tile bit 0): one 16-byte access per pair
+  bool paired = false;
+  if constexpr (GPT == 2 && sizeof(C) == 8) paired = (ph.flags & PASS_PAIRED_GROUPS) != 0 && !(ph.flags & PASS_PERMUTED_STORE);
+  if constexpr (GPT == 2 && sizeof(C) == 8) {
+    if (paired) {
+      uint32_t o = p0[0];  // even: group 2c, register bits zero; the partner amplitude of group 2c + 1 is the next element
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const Pair<C> w = *reinterpret_cast<const Pair<C>*>(&tile[o]);
+        v[0][k ^ (k >> 1)] = w.a;
+        v[1][k ^ (k >> 1)] = w.b;
+        if (k + 1 < D) o ^= stride[gray_flip(k)];
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < GPT; ++u) {
+    if (valid[u] && !paired) {
       // Gray-code walk over the 2^R register indices: consecutive addresses differ by ONE stride (ncu, round 2: the
       // address arithmetic of the tile loads / stores was 20 % of a layered sweep's instructions)
       uint32_t o = p0[u];
@@ -494,6 +514,20 @@ QB_HD void run_pass(C* tile, const char* blob, const TileSlot* ts, const PassHea
     for (int u = 0; u < GPT; ++u) p0[u] = swz<C>(dtab[ctid + (uint32_t)u * nct], dswz_on);
     barrier();
     if (out) tile = out;
+  }
+  if constexpr (GPT == 2 && sizeof(C) == 8) {
+    if (paired) {
+      uint32_t o = p0[0];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        Pair<C> w;
+        w.a = v[0][k ^ (k >> 1)];
+        w.b = v[1][k ^ (k >> 1)];
+        *reinterpret_cast<Pair<C>*>(&tile[o]) = w;
+        if (k + 1 < D) o ^= stride[gray_flip(k)];
+      }
+      return;
+    }
   }
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {

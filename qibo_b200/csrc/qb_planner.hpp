@@ -154,6 +154,9 @@ static_assert(sizeof(PassHeader) % 16 == 0, "PassHeader must stay 16-byte aligne
 // amplitude and stage, 5.2 of them FP64).  Every pass of a QFT but the one holding its last Hadamard qualifies.
 constexpr uint32_t PASS_PERMUTED_STORE = 2u;  // the pass writes its groups in the destination layout of a permuting sweep
 constexpr uint32_t PASS_PERMUTED_DSWZ = 4u;   // ... which is swizzled
+constexpr uint32_t PASS_PAIRED_GROUPS = 8u;   // complex64: the thread's two groups differ in tile bit 0 alone, so one 16-byte
+                                              // shared-memory access moves an amplitude of each (cost model, round 2: a
+                                              // complex64 pass ran at twice the shared-memory floor on 8-byte accesses)
 constexpr uint32_t PASS_FULL_STAGE = 1u;  // flags bits 4-7: which of the stages use the real-matrix form (MH_STAGE_R)
 // (stage mask | real mask << 4) combinations the kernel instantiates: four stages, or the three lowest (the second pass of a
 // 7-stage sweep), each with or without a real-matrix stage on bit 0
@@ -486,6 +489,11 @@ inline uint32_t pad_register_bits(int T, int R, uint32_t need, uint32_t smask) {
     if (!(((rmask | smask) >> lb) & 1)) rmask |= 1u << lb;
   return rmask;
 }
+// complex64, full tile, two groups per thread, tile bit 0 not a register bit: the pass can pair its groups (PASS_PAIRED_GROUPS)
+inline bool paired_groups(int T, int R, int csize, uint32_t rmask, uint32_t smask) {
+  if (csize != 8 || smask != 0 || (rmask & 1u) || env_int("QB_NO_PAIRED_GROUPS", 0)) return false;
+  return (1u << (T - R)) == 2u * (uint32_t)SWEEP_TEAM_THREADS && T == SWEEP_TILE_BYTES_LOG2 - 3 && R == regtile_bits_for(QB_C64);
+}
 // uint16 table: thread slot (u * SWEEP_TEAM_THREADS + ctid) -> group index (over the non-register bits, ascending)
 inline std::vector<uint16_t> make_group_table(int T, int R, int csize, uint32_t rmask, uint32_t smask) {
   const int gbits = T - R;
@@ -496,6 +504,14 @@ inline std::vector<uint16_t> make_group_table(int T, int R, int csize, uint32_t 
   std::vector<uint16_t> tab((size_t)gpt * SWEEP_TEAM_THREADS, 0xFFFF);
   const uint32_t all = (1u << T) - 1;
   if (smask == 0) {
+    if (paired_groups(T, R, csize, rmask, smask)) {
+      // thread c owns groups 2c and 2c + 1: group bit 0 is tile bit 0, the two amplitudes sit in one 16-byte chunk
+      for (uint32_t c = 0; c < (uint32_t)SWEEP_TEAM_THREADS; ++c) {
+        tab[c] = (uint16_t)(2 * c);
+        tab[(size_t)SWEEP_TEAM_THREADS + c] = (uint16_t)(2 * c + 1);
+      }
+      return tab;
+    }
     for (uint32_t g = 0; g < ngroups; ++g) tab[g] = (uint16_t)g;
     return tab;
   }
@@ -1184,6 +1200,7 @@ inline bool emit_regtile_pass(SweepBuilder<C>& sb, const std::vector<const PlanO
     sb.dtab_of_pass[sb.passes.size()] = (int)sb.gtabs.size();
     sb.gtabs.push_back(std::move(dt));
   } else {
+    if (paired_groups(T, R, (int)sizeof(C), rmask, sb.split_mask)) ph.flags |= PASS_PAIRED_GROUPS;
     auto it = sb.gtab_of_rmask.find(rmask);
     if (it == sb.gtab_of_rmask.end()) {
       it = sb.gtab_of_rmask.emplace(rmask, (int)sb.gtabs.size()).first;
